@@ -1,0 +1,469 @@
+// capi.cu -- C ABI of libambigram_b200.so (see include/ambigram_b200.h).
+//
+// Host side of the boundary: flattens the caller's problems into DevProblem
+// records, drives the Stage-A / Stage-B device searches, and maps results back
+// to the reference's own numbering (element_cn[x] in variableIdx order,
+// localhap.cpp:122-133, 204-211).  No search arithmetic happens on the host.
+#include "../../include/ambigram_b200.h"
+#include "ambi_common.cuh"
+#include "stage_a.h"
+#include "stage_b.h"
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+#include <string>
+#include <algorithm>
+#include <dlfcn.h>
+
+using namespace ambi;
+
+// ---- minimal NCCL surface, resolved at run time (libnccl.so.2) -------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+        for (int i = 0; names[i] && !lib; ++i) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllGather && AllReduce;
+    }
+};
+static NcclApi g_nccl;
+enum { kNcclUint32 = 3, kNcclInt32 = 2, kNcclMin = 3 };   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+struct ambi_ctx {
+    ambi_config cfg;
+    cudaStream_t stream = nullptr;
+    StageA sa;
+    StageB sb;
+    ncclComm_t comm = nullptr;
+    uint32_t *d_gather = nullptr;      // world * 40 words
+    std::string err;
+    ambi_batch *resident = nullptr;
+};
+
+struct ambi_batch {
+    int count = 0;
+    std::vector<DevProblem> probs;
+    std::vector<int32_t> bias;
+    bool ran = false;
+};
+
+static thread_local std::string g_err;
+
+static int fail(ambi_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg;
+    g_err = msg;
+    return code;
+}
+
+extern "C" int ambi_abi_version(void) { return AMBI_ABI_VERSION; }
+
+extern "C" const char *ambi_status_string(int s)
+{
+    switch (s) {
+    case AMBI_OK: return "ok";
+    case AMBI_INFEASIBLE: return "infeasible";
+    case AMBI_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case AMBI_ERR_BAD_ARG: return "bad argument";
+    case AMBI_ERR_TOO_LARGE: return "partition has more than AMBI_MAX_SEGMENTS segments";
+    case AMBI_ERR_CUDA: return "CUDA error";
+    case AMBI_ERR_FRONTIER_OVERFLOW: return "candidate buffers exhausted (raise node_capacity)";
+    case AMBI_ERR_NOT_HALF_INTEGRAL: return "copy numbers are not half-integral";
+    case AMBI_ERR_NCCL: return "NCCL error";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *ambi_last_error(const ambi_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int ambi_init(ambi_ctx **out, const ambi_config *cfg)
+{
+    if (!out) return AMBI_ERR_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, AMBI_ERR_NO_DEVICE, std::string("ambi_init: no CUDA device: ") + cudaGetErrorString(e));
+    }
+    ambi_ctx *ctx = new ambi_ctx();
+    memset(&ctx->cfg, 0, sizeof ctx->cfg);
+    if (cfg) ctx->cfg = *cfg;
+    if (ctx->cfg.world <= 0) ctx->cfg.world = 1;
+    if (ctx->cfg.device < 0 || ctx->cfg.device >= ndev) { delete ctx; return fail(nullptr, AMBI_ERR_BAD_ARG, "ambi_init: bad device ordinal"); }
+    if ((e = cudaSetDevice(ctx->cfg.device)) != cudaSuccess) { delete ctx; return fail(nullptr, AMBI_ERR_CUDA, cudaGetErrorString(e)); }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, AMBI_ERR_CUDA, cudaGetErrorString(e)); }
+    if (ctx->sa.init(ctx->stream, ctx->cfg.node_capacity, ctx->cfg.beam_width, ctx->cfg.rank, ctx->cfg.world, ctx->cfg.shard_level)) {
+        std::string m = ctx->sa.error(); delete ctx; return fail(nullptr, AMBI_ERR_CUDA, m);
+    }
+    if (ctx->sb.init(ctx->stream)) { std::string m = ctx->sb.error(); delete ctx; return fail(nullptr, AMBI_ERR_CUDA, m); }
+    *out = ctx;
+    return AMBI_OK;
+}
+
+extern "C" void ambi_destroy(ambi_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    cudaFree(ctx->d_gather);
+    ctx->sa.release(); ctx->sb.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void *ambi_ctx_stream(ambi_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int ambi_ctx_sync(ambi_ctx *ctx)
+{
+    if (!ctx) return AMBI_ERR_BAD_ARG;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    return e == cudaSuccess ? AMBI_OK : fail(ctx, AMBI_ERR_CUDA, cudaGetErrorString(e));
+}
+extern "C" uint64_t ambi_ctx_launch_count(const ambi_ctx *ctx) { return ctx ? ctx->sa.launches() + ctx->sb.launches() : 0; }
+
+extern "C" int ambi_nccl_unique_id(void *id128)
+{
+    if (!id128) return AMBI_ERR_BAD_ARG;
+    if (!g_nccl.load()) return fail(nullptr, AMBI_ERR_NCCL, "cannot load libnccl.so.2");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return fail(nullptr, AMBI_ERR_NCCL, "ncclGetUniqueId failed");
+    memcpy(id128, &id, 128);
+    return AMBI_OK;
+}
+
+extern "C" int ambi_comm_init(ambi_ctx *ctx, const void *id128)
+{
+    if (!ctx || !id128) return AMBI_ERR_BAD_ARG;
+    if (!g_nccl.load()) return fail(ctx, AMBI_ERR_NCCL, "cannot load libnccl.so.2");
+    cudaSetDevice(ctx->cfg.device);
+    ncclUniqueId id; memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, ctx->cfg.world, id, ctx->cfg.rank);
+    if (r != 0) return fail(ctx, AMBI_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    if (cudaMalloc(&ctx->d_gather, (size_t)(ctx->cfg.world + 1) * 40 * 4) != cudaSuccess) return fail(ctx, AMBI_ERR_CUDA, "cudaMalloc gather");
+    return AMBI_OK;
+}
+
+// ---- problem flattening ----------------------------------------------------
+static int to_dev(const ambi_bfb_problem &p, DevProblem &d, std::string &why)
+{
+    memset(&d, 0, sizeof d);
+    if (p.n < 1) { why = "n < 1"; return AMBI_ERR_BAD_ARG; }
+    if (p.n > AMBI_MAX_SEGMENTS) { why = "n > AMBI_MAX_SEGMENTS"; return AMBI_ERR_TOO_LARGE; }
+    if (!p.seg_cn2 || !p.fbi_cn2) { why = "null copy-number arrays"; return AMBI_ERR_BAD_ARG; }
+    d.n = p.n;
+    d.loop_ub = p.loop_ub < 0 ? 0 : p.loop_ub;
+    d.lmax = d.loop_ub < 2 ? d.loop_ub : 2;
+    long long z = 0;
+    for (int i = 0; i < p.n; ++i) {
+        if (p.seg_cn2[i] < 0 || p.fbi_cn2[i] < 0) { why = "negative copy number"; return AMBI_ERR_BAD_ARG; }
+        d.c2[i] = p.seg_cn2[i]; d.j2[i] = p.fbi_cn2[i];
+        z += (long long)p.seg_cn2[i] + p.fbi_cn2[i];
+    }
+    if (z > 0x3fffffff) { why = "copy numbers too large"; return AMBI_ERR_BAD_ARG; }
+    d.zero_score = (int32_t)z;
+    if (p.n_tgs > 0 && (p.flags & AMBI_FLAG_JUNC_INFO) && p.tgs_pairs) {
+        for (int t = 0; t < p.n_tgs; ++t) {
+            int s = p.tgs_pairs[2 * t] - p.start_id, e = p.tgs_pairs[2 * t + 1] - p.start_id;
+            if (s > e) std::swap(s, e);
+            if (s < 0 || e >= p.n) continue;
+            if (s == 0 && e == p.n - 1) continue;                 // LGM:4690
+            d.tgs_mask[s] |= 1u << e; d.has_tgs = 1;
+        }
+    }
+    return AMBI_OK;
+}
+
+static void decode_codes(uint32_t code, int n, int out[4])
+{
+    // inverse of ambi_ip_code / ambi_il_code: columns p1<p2, l1<=l2 (or -1)
+    out[0] = out[1] = out[2] = out[3] = -1;
+    int ip = code >> 10, il = code & 1023;
+    if (ip) {
+        int q1 = 0; while (ambi_ip_code(q1 + 1, -1) <= ip) ++q1;
+        int off = ip - ambi_ip_code(q1, -1);
+        out[0] = n - 1 - q1;
+        if (off > 0) out[1] = n - 1 - (off - 1);
+    }
+    if (il) {
+        int q1 = 0; while (ambi_il_code(q1 + 1, -1) <= il) ++q1;
+        int off = il - ambi_il_code(q1, -1);
+        out[2] = n - 1 - q1;
+        if (off > 0) out[3] = (off - 1 == q1) ? out[2] : n - 1 - (off - 1);
+    }
+}
+
+static inline int pair_index(int n, int a, int b) { return a * n - a * (a - 1) / 2 + (b - a); }
+
+static void rows_to_element_cn(int n, const uint32_t *rows, int32_t *x)
+{
+    const int H = n * (n + 1) / 2;
+    memset(x, 0, sizeof(int32_t) * 2 * H);
+    if (n == 1) { x[0] = (rows[0] >> 20) & 1; x[1] = rows[0] & 0xfffff; return; }
+    for (int a = 0; a < n; ++a) {
+        int c[4]; decode_codes(rows[a], n, c);
+        if (c[0] >= 0) x[pair_index(n, a, c[0])] += 1;
+        if (c[1] >= 0) x[pair_index(n, a, c[1])] += 1;
+        if (c[2] >= 0) x[H + pair_index(n, a, c[2])] += 1;
+        if (c[3] >= 0) x[H + pair_index(n, a, c[3])] += 1;
+    }
+}
+
+extern "C" int ambi_bfb_better(int32_t n, int64_t sa, const int32_t *xa, int64_t sb, const int32_t *xb)
+{
+    if (sa != sb) return sa < sb;
+    const int H = n * (n + 1) / 2;
+    for (int a = 0; a < n; ++a) {
+        for (int b = a; b < n; ++b) { int i = pair_index(n, a, b); if (xa[i] != xb[i]) return xa[i] < xb[i]; }
+        for (int b = a; b < n; ++b) { int i = H + pair_index(n, a, b); if (xa[i] != xb[i]) return xa[i] < xb[i]; }
+    }
+    return 0;
+}
+
+// ---- device-resident batch -------------------------------------------------
+extern "C" int ambi_batch_upload(ambi_ctx *ctx, int32_t count, const ambi_bfb_problem *problems, ambi_batch **out)
+{
+    if (!ctx || !out || count <= 0 || !problems) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_batch_upload: bad argument");
+    cudaSetDevice(ctx->cfg.device);
+    ambi_batch *b = new ambi_batch();
+    b->count = count; b->probs.resize(count); b->bias.resize(count);
+    for (int i = 0; i < count; ++i) {
+        std::string why;
+        int rc = to_dev(problems[i], b->probs[i], why);
+        if (rc) { delete b; return fail(ctx, rc, "problem " + std::to_string(i) + ": " + why); }
+        b->bias[i] = problems[i].bias;
+    }
+    if (ctx->sa.upload(b->probs.data(), count)) { delete b; return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error()); }
+    cudaStreamSynchronize(ctx->stream);
+    ctx->resident = b;
+    *out = b;
+    return AMBI_OK;
+}
+
+extern "C" int ambi_batch_run(ambi_ctx *ctx, ambi_batch *b)
+{
+    if (!ctx || !b || ctx->resident != b) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_batch_run: batch is not resident");
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->sa.run(false)) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
+    b->ran = true;
+    return AMBI_OK;
+}
+
+static int fetch_into(ambi_ctx *ctx, ambi_batch *b, ambi_bfb_solution *sol, bool shard)
+{
+    std::vector<HostResult> hr(b->count);
+    int rc = ctx->sa.fetch(hr.data());
+    if (rc == -4) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
+    int worst = AMBI_OK;
+    for (int i = 0; i < b->count; ++i) {
+        const int n = b->probs[i].n;
+        ambi_bfb_solution &s = sol[i];
+        s.status = hr[i].status;
+        if (shard && hr[i].status == -4) s.status = AMBI_OK;      // this shard saw no completed assignment
+        s.score2 = hr[i].score2;
+        s.objective2 = hr[i].score2 - 2ll * b->bias[i];
+        s.candidates_scored = hr[i].candidates; s.nodes_expanded = hr[i].nodes;
+        s.incumbent_score2 = hr[i].incumbent;
+        s.seconds = hr[i].seconds; s.seconds_to_best = hr[i].seconds_to_best;
+        if (s.element_cn) {
+            if (hr[i].score2 != 0x7fffffff) rows_to_element_cn(n, hr[i].rows, s.element_cn);
+            else memset(s.element_cn, 0, sizeof(int32_t) * n * (n + 1));
+        }
+        if (s.status < worst) worst = s.status;
+    }
+    if (worst == AMBI_ERR_FRONTIER_OVERFLOW) return fail(ctx, worst, ctx->sa.error());
+    if (worst) return fail(ctx, worst, "search returned no assignment");
+    return AMBI_OK;
+}
+
+extern "C" int ambi_batch_fetch(ambi_ctx *ctx, ambi_batch *b, ambi_bfb_solution *solutions)
+{
+    if (!ctx || !b || !solutions || ctx->resident != b || !b->ran) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_batch_fetch: nothing to fetch");
+    cudaSetDevice(ctx->cfg.device);
+    return fetch_into(ctx, b, solutions, false);
+}
+
+extern "C" void ambi_batch_free(ambi_ctx *ctx, ambi_batch *b)
+{
+    if (ctx && ctx->resident == b) ctx->resident = nullptr;
+    delete b;
+}
+
+// ---- Seam A ---------------------------------------------------------------
+extern "C" int ambi_bfb_solve_batch(ambi_ctx *ctx, int32_t count, const ambi_bfb_problem *problems,
+                                    ambi_bfb_solution *solutions)
+{
+    if (!ctx || !solutions) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_solve_batch: bad argument");
+    ambi_batch *b = nullptr;
+    int rc = ambi_batch_upload(ctx, count, problems, &b);
+    if (rc) return rc;
+    rc = ambi_batch_run(ctx, b);
+    if (!rc) rc = ambi_batch_fetch(ctx, b, solutions);
+    ambi_batch_free(ctx, b);
+    return rc;
+}
+
+extern "C" int ambi_bfb_solve_shard(ambi_ctx *ctx, const ambi_bfb_problem *problem, ambi_bfb_solution *solution)
+{
+    if (!ctx || !problem || !solution) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_solve_shard: bad argument");
+    ambi_batch *b = nullptr;
+    int rc = ambi_batch_upload(ctx, 1, problem, &b);
+    if (rc) return rc;
+    if (ctx->sa.run(ctx->cfg.world > 1)) { ambi_batch_free(ctx, b); return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error()); }
+    b->ran = true;
+    rc = fetch_into(ctx, b, solution, ctx->cfg.world > 1);
+    ambi_batch_free(ctx, b);
+    return rc;
+}
+
+extern "C" int ambi_bfb_solve(ambi_ctx *ctx, const ambi_bfb_problem *problem, ambi_bfb_solution *solution)
+{
+    if (!ctx || !problem || !solution) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_solve: bad argument");
+    if (ctx->cfg.world <= 1 || !ctx->comm) return ambi_bfb_solve_batch(ctx, 1, problem, solution);
+    // prefix-sharded: every rank explores the subtrees hashed to it, then one all-gather of the
+    // (score, row codes) records over NVLink picks the global arg-min in (score, search order)
+    const int n = problem->n;
+    std::vector<int32_t> x((size_t)n * (n + 1));
+    ambi_bfb_solution local = *solution;
+    local.element_cn = x.data();
+    int rc = ambi_bfb_solve_shard(ctx, problem, &local);
+    if (rc) return rc;
+    const int W = ctx->cfg.world;
+    // pack: [score, n rows re-encoded from element_cn in search order]
+    std::vector<uint32_t> rec(40, 0), all((size_t)W * 40);
+    rec[0] = (uint32_t)local.score2;
+    // per-row keys comparable as integers: recompute the row codes from x
+    const int H = n * (n + 1) / 2;
+    for (int a = 0; a < n && n > 1; ++a) {
+        int p[2] = {-1, -1}, l[2] = {-1, -1}, np = 0, nl = 0;
+        for (int b2 = a; b2 < n; ++b2) {
+            if (x[pair_index(n, a, b2)] && np < 2) p[np++] = b2;
+            for (int c = 0; c < x[H + pair_index(n, a, b2)] && nl < 2; ++c) l[nl++] = b2;
+        }
+        int ip = np == 0 ? 0 : (np == 1 ? ambi_ip_code(n - 1 - p[0], -1) : ambi_ip_code(n - 1 - p[0], n - 1 - p[1]));
+        int il = nl == 0 ? 0 : (nl == 1 ? ambi_il_code(n - 1 - l[0], -1) : ambi_il_code(n - 1 - l[0], n - 1 - l[1]));
+        rec[1 + a] = ((uint32_t)ip << 10) | (uint32_t)il;
+    }
+    if (n == 1) { rec[1] = 0x80000000u | ((uint32_t)x[0] << 20) | (uint32_t)x[1]; }
+    rec[34] = (uint32_t)(local.candidates_scored & 0xffffffffu); rec[35] = (uint32_t)(local.candidates_scored >> 32);
+    rec[36] = (uint32_t)(local.nodes_expanded & 0xffffffffu); rec[37] = (uint32_t)(local.nodes_expanded >> 32);
+    cudaSetDevice(ctx->cfg.device);
+    uint32_t *d_send = ctx->d_gather, *d_recv = ctx->d_gather + 40;
+    cudaMemcpyAsync(d_send, rec.data(), 160, cudaMemcpyHostToDevice, ctx->stream);
+    ncclResult_t r = g_nccl.AllGather(d_send, d_recv, 40, kNcclUint32, ctx->comm, ctx->stream);
+    if (r != 0) return fail(ctx, AMBI_ERR_NCCL, "ncclAllGather failed");
+    cudaMemcpyAsync(all.data(), d_recv, (size_t)W * 160, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(ctx, AMBI_ERR_CUDA, "all-gather sync failed");
+    int best = 0; uint64_t cands = 0, nodes = 0;
+    for (int w = 0; w < W; ++w) {
+        const uint32_t *q = &all[(size_t)w * 40], *bq = &all[(size_t)best * 40];
+        cands += (uint64_t)q[34] | ((uint64_t)q[35] << 32); nodes += (uint64_t)q[36] | ((uint64_t)q[37] << 32);
+        bool better = false;
+        if ((int32_t)q[0] != (int32_t)bq[0]) better = (int32_t)q[0] < (int32_t)bq[0];
+        else for (int a = 0; a < n; ++a) if (q[1 + a] != bq[1 + a]) { better = q[1 + a] < bq[1 + a]; break; }
+        if (better) best = w;
+    }
+    const uint32_t *bq = &all[(size_t)best * 40];
+    solution->score2 = (int32_t)bq[0];
+    solution->objective2 = solution->score2 - 2ll * problem->bias;
+    solution->candidates_scored = cands; solution->nodes_expanded = nodes;
+    solution->incumbent_score2 = local.incumbent_score2;
+    solution->seconds = local.seconds; solution->seconds_to_best = local.seconds_to_best;
+    solution->status = solution->score2 == 0x7fffffff ? AMBI_ERR_CUDA : AMBI_OK;
+    if (solution->element_cn) rows_to_element_cn(n, bq + 1, solution->element_cn);
+    return solution->status;
+}
+
+// ---- Seam B ---------------------------------------------------------------
+// constructDAG (LGM:3276-3378) on the host side of the boundary.
+extern "C" int ambi_bfb_construct_dag(int32_t n, int32_t start_id, const int32_t *x, ambi_dag *dag)
+{
+    if (!x || !dag || n < 1 || n > AMBI_MAX_SEGMENTS) return AMBI_ERR_BAD_ARG;
+    memset(dag, 0, sizeof *dag);
+    const int H = n * (n + 1) / 2;
+    struct Node { int kind, a, b, cn; std::string key; };
+    std::vector<Node> loops, pats;
+    for (int a = 0; a < n; ++a)
+        for (int b = a; b < n; ++b) {
+            int i = pair_index(n, a, b);
+            if (x[i] > 0) pats.push_back({0, a + start_id, b + start_id, x[i], std::to_string(a + start_id) + "," + std::to_string(b + start_id)});
+            if (x[H + i] > 0) loops.push_back({1, a + start_id, b + start_id, x[H + i], std::to_string(a + start_id) + "," + std::to_string(b + start_id)});
+        }
+    // std::map<string,int> iteration order: "l:..." keys before "p:...", each in string order (LGM:3279)
+    auto bykey = [](const Node &u, const Node &v) { return u.key < v.key; };
+    std::sort(loops.begin(), loops.end(), bykey);
+    std::sort(pats.begin(), pats.end(), bykey);
+    // loops by decreasing length, stable (LGM:3303 as intended; see DESIGN.md on k > 16)
+    std::stable_sort(loops.begin(), loops.end(), [](const Node &u, const Node &v) { return (u.b - u.a) > (v.b - v.a); });
+    const int k = (int)(loops.size() + pats.size());
+    if (k > AMBI_MAX_COMPONENTS) return AMBI_ERR_TOO_LARGE;
+    std::vector<Node> nodes(loops); nodes.insert(nodes.end(), pats.begin(), pats.end());
+    dag->k = k;
+    for (int i = 0; i < k; ++i) { dag->kind[i] = (int8_t)nodes[i].kind; dag->a[i] = (int16_t)nodes[i].a; dag->b[i] = (int16_t)nodes[i].b; dag->cn[i] = (int16_t)nodes[i].cn; }
+    std::vector<std::vector<int>> adj(k), parents(k);
+    auto share = [&](int i, int j) { return nodes[i].a == nodes[j].a || nodes[i].b == nodes[j].b; };
+    auto len = [&](int i) { return nodes[i].b - nodes[i].a; };
+    for (int i = 0; i < k; ++i) if (nodes[i].kind == 0) {
+        for (int j = 0; j < k; ++j) if (nodes[j].kind == 0 && share(i, j) && len(i) > len(j)) { adj[i].push_back(j); parents[j].push_back(i); }   // p -> p
+        for (int j = 0; j < k; ++j) if (nodes[j].kind == 1 && share(i, j) && len(i) > len(j)) { adj[i].push_back(j); parents[j].push_back(i); }   // p -> l
+    }
+    for (int i = 0; i < k; ++i) if (nodes[i].kind == 1) {
+        for (int j = 0; j < k; ++j) {                                                                  // l -> p
+            if (std::find(parents[i].begin(), parents[i].end(), j) != parents[i].end()) continue;
+            if (nodes[j].kind == 0 && share(i, j)) {
+                if (len(i) > len(j)) { adj[i].push_back(j); parents[j].push_back(i); }
+                else for (int par : parents[i])
+                    if (std::find(adj[par].begin(), adj[par].end(), j) != adj[par].end()) { adj[i].push_back(j); parents[j].push_back(i); break; }
+            }
+        }
+        for (int j = 0; j < k; ++j) if (nodes[j].kind == 1 && share(i, j) && len(i) > len(j)) { adj[i].push_back(j); parents[j].push_back(i); }   // l -> l
+    }
+    for (int i = 0; i < k; ++i) for (int j : adj[i]) dag->adj[i] |= 1ull << j;
+    return AMBI_OK;
+}
+
+extern "C" int ambi_bfb_first_valid_order_batch(ambi_ctx *ctx, int32_t count, const ambi_dag *dags,
+                                                const int32_t *reversed, ambi_order_result *results)
+{
+    if (!ctx || !dags || !results || count <= 0) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_first_valid_order_batch: bad argument");
+    cudaSetDevice(ctx->cfg.device);
+    int rc = ctx->sb.run(count, dags, reversed, results);
+    if (rc == -2) return fail(ctx, AMBI_ERR_BAD_ARG, ctx->sb.error());
+    if (rc == -3) return fail(ctx, AMBI_ERR_TOO_LARGE, ctx->sb.error());
+    if (rc) return fail(ctx, AMBI_ERR_CUDA, ctx->sb.error());
+    return AMBI_OK;
+}
+
+extern "C" int ambi_bfb_first_valid_order(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, ambi_order_result *result)
+{
+    return ambi_bfb_first_valid_order_batch(ctx, 1, dag, &reversed, result);
+}
+
+extern "C" int ambi_bfb_expand_path(const int32_t *bkp, int32_t bkp_len, int32_t *path_out, int32_t cap)
+{
+    // LGM:3661-3670: each pair (first,last) of a monotone run expands to every id in between
+    int len = 0;
+    for (int j = 1; j < bkp_len; j += 2) {
+        int u = bkp[j - 1], v = bkp[j];
+        if (u > 0) { for (int k = u; k <= v; ++k) { if (len < cap) path_out[len] = k; ++len; } }
+        else { for (int k = -u; k >= -v; --k) { if (len < cap) path_out[len] = -k; ++len; } }
+    }
+    return len;
+}

@@ -1,0 +1,58 @@
+// stage_a.h -- host driver of the Stage-A device search (see stage_a.cu).
+#pragma once
+#include "ambi_common.cuh"
+
+namespace ambi {
+
+struct HostResult {
+    int64_t score2;
+    int32_t incumbent;
+    int32_t status;
+    unsigned long long candidates, nodes;
+    uint32_t rows[AMBI_MAXN];
+    double seconds, seconds_to_best;
+};
+
+class StageA {
+public:
+    StageA();
+    ~StageA();
+    int init(cudaStream_t stream, int64_t node_capacity, int beam_width, int rank, int world, int shard_level);
+    void release();
+    // copy `count` problem descriptors to the device (async on the ctx stream)
+    int upload(const DevProblem *host_probs, int count);
+    // enqueue the whole search (incumbent pass + exact pass); no host sync
+    int run(bool sharded);
+    // wait and read back per-problem results
+    int fetch(HostResult *out);
+    const char *error() const { return err_; }
+    unsigned long long launches() const { return launches_; }
+    int count() const { return count_; }
+
+private:
+    int ensure_problem_arrays(int count);
+    void free_problem_arrays();
+    int run_level(int level, int cur, bool beam, int shard_world);
+
+    cudaStream_t stream_ = nullptr;
+    uint32_t cap_ = 0, tsize_ = 0, gen_ = 1;
+    int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
+    int stride_ = 0, sms_ = 148;
+    uint8_t *buf_[2] = {nullptr, nullptr};
+    uint32_t *list_[2] = {nullptr, nullptr};
+    uint8_t *dead_ = nullptr;
+    unsigned long long *table_ = nullptr;
+    uint32_t *counters_ = nullptr;
+    uint8_t *ptab_ = nullptr, *ltab_ = nullptr;
+    // per-problem arrays
+    int prob_cap_ = 0, count_ = 0, nmax_ = 0;
+    DevProblem *d_probs_ = nullptr;
+    int32_t *d_limit_ = nullptr, *d_incumbent_ = nullptr, *d_best_score_ = nullptr, *d_beam_score_ = nullptr, *d_fmin_ = nullptr;
+    uint32_t *d_best_rows_ = nullptr, *d_beam_rows_ = nullptr, *d_hist_ = nullptr, *d_ticket_ = nullptr;
+    unsigned long long *d_cand_ = nullptr, *d_node_ = nullptr;
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long launches_ = 0;
+    char err_[256];
+};
+
+}  // namespace ambi

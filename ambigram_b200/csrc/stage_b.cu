@@ -1,0 +1,303 @@
+// stage_b.cu -- Stage B of the BFB search on sm_100a (kernel K4).
+//
+// Replaces allTopologicalOrders + the order loop of getBFB (reference
+// src/LocalGenomicMap.cpp:3380-3409, 3514-3697).  The reference materialises
+// every topological order of the component DAG and assembles each one from
+// scratch; the first order (lexicographic in node numbering, lowest free index
+// first, LGM:3389-3391) whose components can all be placed wins.  Placing
+// order[i] only depends on order[0..i-1], so a failed placement prunes the
+// whole subtree: the device walks the tree of *assemblable prefixes* instead.
+//
+// One warp per DAG.  The (first, second) prefixes are numbered t = 0,1,... in
+// lexicographic order and dealt round-robin to the 32 lanes; each lane runs a
+// depth-first search below its prefixes with the breakpoint path kept in local
+// memory as signed int8 segment offsets and an O(1) undo record per depth.
+// The winner is the solution with the smallest t (shared-memory atomicMin),
+// which is the lexicographically first valid order.
+#include "stage_b.h"
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace ambi {
+
+constexpr int MAXK = AMBI_MAX_COMPONENTS;
+constexpr int MAXPATH = 1024;
+
+struct DevDag {
+    int32_t k, base, reversed, pad;
+    int8_t kind[MAXK];
+    int8_t a[MAXK], b[MAXK], cn[MAXK];     // relative ids (id - base + 1 >= 1)
+    uint64_t adj[MAXK];
+};
+
+struct DevOrderOut {
+    int32_t found, used_flipped, bkp_len, pad;
+    unsigned long long tested;
+    int32_t order[MAXK];
+    int32_t bkp[MAXPATH];
+};
+
+struct Undo { int16_t f; int16_t cnt; int8_t old; int8_t had; };
+
+// try to place node v on the breakpoint path (getBFB body, LGM:3572-3644)
+__device__ __forceinline__ bool place(const DevDag &D, int v, int8_t *B, int &len, Undo &u)
+{
+    const int a = D.a[v], b = D.b[v];
+    if (D.kind[v] == 0) {                              // pattern: must extend the tail
+        const int tail = B[len - 1];
+        if (len + 2 > MAXPATH) return false;
+        if (tail == -a) { B[len] = (int8_t)a; B[len + 1] = (int8_t)b; }
+        else if (tail == b) { B[len] = (int8_t)-b; B[len + 1] = (int8_t)-a; }
+        else return false;
+        len += 2; u.f = -1; u.cnt = 2; u.had = 0; u.old = 0;
+        return true;
+    }
+    // loop: find a run end (odd index) equal to a- (then b+) with the nesting test
+    int f = -1; bool first = true;
+    for (int i = len - 1; i >= 1; i -= 2)
+        if (B[i] == -a && (i == len - 1 || abs((int)B[i - 1]) >= abs((int)B[i + 2]))) { f = i; break; }
+    if (f < 0) {
+        first = false;
+        for (int i = len - 1; i >= 1; i -= 2)
+            if (B[i] == b && (i == len - 1 || abs((int)B[i - 1]) <= abs((int)B[i + 2]))) { f = i; break; }
+    }
+    if (f < 0) return false;
+    const int cn = D.cn[v], add = 4 * cn;
+    if (len + add > MAXPATH) return false;
+    u.f = (int16_t)f; u.cnt = (int16_t)add; u.had = 0; u.old = 0;
+    if (f + 1 < len) { u.had = 1; u.old = B[f + 1]; B[f + 1] = (int8_t)(first ? a : -b); }
+    for (int i = len - 1; i > f; --i) B[i + add] = B[i];
+    for (int c = 0; c < cn; ++c) {
+        int8_t *q = B + f + 1 + 4 * c;
+        if (first) { q[0] = (int8_t)a; q[1] = (int8_t)b; q[2] = (int8_t)-b; q[3] = (int8_t)-a; }
+        else       { q[0] = (int8_t)-b; q[1] = (int8_t)-a; q[2] = (int8_t)a; q[3] = (int8_t)b; }
+    }
+    len += add;
+    return true;
+}
+
+__device__ __forceinline__ void unplace(int8_t *B, int &len, const Undo &u)
+{
+    if (u.f < 0) { len -= u.cnt; return; }
+    const int f = u.f, add = u.cnt;
+    for (int i = f + 1 + add; i < len; ++i) B[i - add] = B[i];
+    len -= add;
+    if (u.had) B[f + 1] = u.old;
+}
+
+// seed the path with the first node (LGM:3524-3568)
+__device__ __forceinline__ void seed(const DevDag &D, int v, bool forward, int8_t *B, int &len)
+{
+    const int a = D.a[v], b = D.b[v];
+    len = 0;
+    if (D.kind[v] == 0) {
+        if (forward) { B[0] = (int8_t)a; B[1] = (int8_t)b; } else { B[0] = (int8_t)-b; B[1] = (int8_t)-a; }
+        len = 2;
+    } else {
+        for (int c = 0; c < D.cn[v]; ++c) {
+            if (forward) { B[len] = (int8_t)a; B[len + 1] = (int8_t)b; B[len + 2] = (int8_t)-b; B[len + 3] = (int8_t)-a; }
+            else         { B[len] = (int8_t)-b; B[len + 1] = (int8_t)-a; B[len + 2] = (int8_t)a; B[len + 3] = (int8_t)b; }
+            len += 4;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_first_valid_order(const DevDag *dags, DevOrderOut *outs, int count, uint32_t *work)
+{
+    __shared__ DevDag s_dag[4];
+    __shared__ int s_best[4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    DevDag &D = s_dag[wib];
+
+    for (;;) {
+        uint32_t wi = 0;
+        if (lane == 0) wi = atomicAdd(work, 1u);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= (uint32_t)count) break;
+        __syncwarp();
+        {   // stage the DAG in shared memory
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&dags[wi]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&D);
+            for (int i = lane; i < (int)(sizeof(DevDag) / 4); i += 32) dst[i] = src[i];
+        }
+        __syncwarp();
+        const int k = D.k;
+        DevOrderOut &O = outs[wi];
+        unsigned long long tested = 0;
+        int found_flip = -1;
+
+        int8_t B[MAXPATH];
+        uint8_t order[MAXK], indeg[MAXK], nexti[MAXK];
+        Undo undo[MAXK];
+
+        for (int attempt = 0; attempt < 2 && found_flip < 0 && k > 0; ++attempt) {
+            const bool forward = (attempt == 0) ? !D.reversed : (D.reversed != 0);   // LGM:3516, 3691-3695
+            if (lane == 0) s_best[wib] = 0x7fffffff;
+            __syncwarp();
+            // indegrees (localhap.cpp:244-250)
+            for (int i = 0; i < k; ++i) indeg[i] = 0;
+            for (int i = 0; i < k; ++i) { uint64_t m = D.adj[i]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]++; } }
+            uint64_t visited = 0;
+            int len = 0, my_t = -1;
+            bool have = false;
+            int t = 0;
+            // enumerate (first, second) prefixes in lexicographic order
+            for (int v0 = 0; v0 < k && !have; ++v0) {
+                if (indeg[v0] != 0) continue;
+                if (k == 1) {
+                    if (lane == 0) { seed(D, v0, forward, B, len); order[0] = (uint8_t)v0; ++tested; have = true; my_t = 0; atomicMin(&s_best[wib], 0); }
+                    break;
+                }
+                // remove v0
+                { uint64_t m = D.adj[v0]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]--; } }
+                visited |= 1ull << v0;
+                for (int v1 = 0; v1 < k && !have; ++v1) {
+                    if (indeg[v1] != 0 || ((visited >> v1) & 1)) continue;
+                    const int tt = t++;
+                    if ((tt & 31) != lane) continue;
+                    if (tt > *(volatile int *)&s_best[wib]) continue;
+                    // assemble the two-node prefix
+                    seed(D, v0, forward, B, len);
+                    order[0] = (uint8_t)v0;
+                    ++tested;
+                    if (!place(D, v1, B, len, undo[1])) continue;
+                    order[1] = (uint8_t)v1;
+                    if (k == 2) { have = true; my_t = tt; atomicMin(&s_best[wib], tt); break; }
+                    { uint64_t m = D.adj[v1]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]--; } }
+                    visited |= 1ull << v1;
+                    // depth-first search below, lowest free index first (LGM:3389-3391)
+                    int d = 2; nexti[2] = 0;
+                    unsigned steps = 0;
+                    bool aborted = false;
+                    while (d >= 2) {
+                        if ((++steps & 63) == 0 && tt > *(volatile int *)&s_best[wib]) { aborted = true; break; }
+                        int v = nexti[d];
+                        while (v < k && (indeg[v] != 0 || ((visited >> v) & 1))) ++v;
+                        if (v >= k) {                          // exhausted: backtrack
+                            --d;
+                            if (d < 2) break;
+                            int pv = order[d];
+                            unplace(B, len, undo[d]);
+                            visited &= ~(1ull << pv);
+                            { uint64_t m = D.adj[pv]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]++; } }
+                            continue;
+                        }
+                        nexti[d] = (uint8_t)(v + 1);
+                        ++tested;
+                        if (!place(D, v, B, len, undo[d])) continue;
+                        order[d] = (uint8_t)v;
+                        if (d == k - 1) { have = true; my_t = tt; atomicMin(&s_best[wib], tt); break; }
+                        visited |= 1ull << v;
+                        { uint64_t m = D.adj[v]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]--; } }
+                        ++d; nexti[d] = 0;
+                    }
+                    if (have) break;
+                    if (aborted) {
+                        // unwind bookkeeping to the two-node prefix
+                        for (int dd = d - 1; dd >= 2; --dd) {
+                            int pv = order[dd];
+                            visited &= ~(1ull << pv);
+                            uint64_t m = D.adj[pv]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]++; }
+                        }
+                    }
+                    // restore v1
+                    visited &= ~(1ull << v1);
+                    { uint64_t m = D.adj[v1]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]++; } }
+                }
+                if (have) break;
+                visited &= ~(1ull << v0);
+                { uint64_t m = D.adj[v0]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]++; } }
+            }
+            __syncwarp();
+            const int best = s_best[wib];
+            if (best != 0x7fffffff) {
+                found_flip = attempt;
+                if (have && my_t == best) {
+                    O.found = 1; O.used_flipped = attempt; O.bkp_len = len;
+                    for (int i = 0; i < k; ++i) O.order[i] = order[i];
+                    for (int i = 0; i < len; ++i) { int v = B[i]; O.bkp[i] = v > 0 ? v - 1 + D.base : -(-v - 1 + D.base); }
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) tested += __shfl_xor_sync(0xffffffffu, tested, o);
+        if (lane == 0) {
+            O.tested = tested;
+            if (found_flip < 0) { O.found = 0; O.used_flipped = 0; O.bkp_len = 0; }
+        }
+        __syncwarp();
+    }
+}
+
+#define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    snprintf(err_, sizeof err_, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return -4; } } while (0)
+
+StageB::StageB() { err_[0] = 0; }
+StageB::~StageB() { release(); }
+void StageB::release() { cudaFree(d_dags_); cudaFree(d_out_); cudaFree(d_work_); d_dags_ = d_out_ = d_work_ = nullptr; cap_ = 0; }
+
+int StageB::init(cudaStream_t stream)
+{
+    stream_ = stream;
+    int dev = 0; CKB(cudaGetDevice(&dev));
+    CKB(cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev));
+    CKB(cudaMalloc(&d_work_, 64));
+    return 0;
+}
+
+int StageB::ensure(int count)
+{
+    if (count <= cap_) return 0;
+    cudaFree(d_dags_); cudaFree(d_out_); d_dags_ = d_out_ = nullptr;
+    int c = count < 64 ? 64 : count;
+    CKB(cudaMalloc(&d_dags_, (size_t)c * sizeof(DevDag)));
+    CKB(cudaMalloc(&d_out_, (size_t)c * sizeof(DevOrderOut)));
+    cap_ = c;
+    return 0;
+}
+
+int StageB::run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_order_result *results)
+{
+    if (count <= 0) return 0;
+    if (int rc = ensure(count)) return rc;
+    std::vector<DevDag> h(count);
+    for (int i = 0; i < count; ++i) {
+        const ambi_dag &g = dags[i];
+        DevDag &d = h[i];
+        memset(&d, 0, sizeof d);
+        if (g.k < 0 || g.k > MAXK) { snprintf(err_, sizeof err_, "dag %d: k=%d out of range", i, g.k); return -2; }
+        int base = 0x7fffffff, top = 0;
+        for (int v = 0; v < g.k; ++v) { if (g.a[v] < base) base = g.a[v]; if (g.b[v] > top) top = g.b[v]; }
+        if (g.k == 0) base = 1;
+        if (g.k > 0 && top - base + 1 > 120) { snprintf(err_, sizeof err_, "dag %d: segment span too large", i); return -3; }
+        d.k = g.k; d.base = base; d.reversed = reversed ? reversed[i] : 0;
+        for (int v = 0; v < g.k; ++v) {
+            d.kind[v] = g.kind[v]; d.a[v] = (int8_t)(g.a[v] - base + 1); d.b[v] = (int8_t)(g.b[v] - base + 1);
+            d.cn[v] = (int8_t)g.cn[v]; d.adj[v] = g.adj[v];
+        }
+    }
+    CKB(cudaMemcpyAsync(d_dags_, h.data(), (size_t)count * sizeof(DevDag), cudaMemcpyHostToDevice, stream_));
+    CKB(cudaMemsetAsync(d_work_, 0, 64, stream_));
+    CKB(cudaMemsetAsync(d_out_, 0, (size_t)count * sizeof(DevOrderOut), stream_));
+    int blocks = (count + 3) / 4; if (blocks > sms_ * 8) blocks = sms_ * 8;
+    k_first_valid_order<<<blocks, 128, 0, stream_>>>((const DevDag *)d_dags_, (DevOrderOut *)d_out_, count, (uint32_t *)d_work_);
+    ++launches_;
+    CKB(cudaGetLastError());
+    std::vector<DevOrderOut> ho(count);
+    CKB(cudaMemcpyAsync(ho.data(), d_out_, (size_t)count * sizeof(DevOrderOut), cudaMemcpyDeviceToHost, stream_));
+    CKB(cudaStreamSynchronize(stream_));
+    for (int i = 0; i < count; ++i) {
+        ambi_order_result &r = results[i];
+        memset(&r, 0, sizeof r);
+        r.found = ho[i].found; r.used_flipped = ho[i].used_flipped; r.bkp_len = ho[i].bkp_len;
+        r.orders_tested = ho[i].tested; r.status = 0;
+        for (int v = 0; v < dags[i].k; ++v) r.order[v] = ho[i].order[v];
+        for (int v = 0; v < ho[i].bkp_len && v < 1024; ++v) r.bkp[v] = ho[i].bkp[v];
+    }
+    return 0;
+}
+
+}  // namespace ambi

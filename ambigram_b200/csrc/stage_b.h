@@ -1,0 +1,29 @@
+// stage_b.h -- host driver of the Stage-B device search (see stage_b.cu).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/ambigram_b200.h"
+
+namespace ambi {
+
+class StageB {
+public:
+    StageB();
+    ~StageB();
+    int init(cudaStream_t stream);
+    void release();
+    // first valid topological order for each DAG (orientation per reversed[i], flipped if none)
+    int run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_order_result *results);
+    const char *error() const { return err_; }
+    unsigned long long launches() const { return launches_; }
+
+private:
+    int ensure(int count);
+    cudaStream_t stream_ = nullptr;
+    int cap_ = 0, sms_ = 148;
+    void *d_dags_ = nullptr, *d_out_ = nullptr, *d_work_ = nullptr;
+    unsigned long long launches_ = 0;
+    char err_[256];
+};
+
+}  // namespace ambi

@@ -1,0 +1,132 @@
+"""ctypes wrapper of the CPU oracle (oracle/ambi_oracle.c).  TEST INFRASTRUCTURE: imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "_build", "libambi_oracle.so")
+MAXK = 64
+I32P = C.POINTER(C.c_int32)
+
+
+class Stats(C.Structure):
+    _fields_ = [("score2", C.c_int64), ("candidates", C.c_int64), ("nodes", C.c_int64), ("unique", C.c_int32),
+                ("status", C.c_int32)]
+
+
+class Dag(C.Structure):
+    _fields_ = [("k", C.c_int32), ("kind", C.c_int8 * MAXK), ("a", C.c_int16 * MAXK), ("b", C.c_int16 * MAXK),
+                ("cn", C.c_int16 * MAXK), ("adj", C.c_uint64 * MAXK)]
+
+    def nodes(self):
+        return [("l" if self.kind[i] else "p", self.a[i], self.b[i], self.cn[i]) for i in range(self.k)]
+
+    def edges(self):
+        return [(i, j) for i in range(self.k) for j in range(self.k) if (self.adj[i] >> j) & 1]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(ORACLE_DIR, "ambi_oracle.c")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "_build/libambi_oracle.so"])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_bruteforce.restype = C.c_int64
+        _lib.orc_count_valid_orders.restype = C.c_int64
+    return _lib
+
+
+def _arr(v) -> np.ndarray:
+    return np.ascontiguousarray(v, dtype=np.int32)
+
+
+def _tgs_rel(problem) -> Tuple[np.ndarray, int]:
+    """absolute (min,max) ids -> 0-based offsets as orc_* expects"""
+    t = [int(v) - problem.start_id for v in problem.tgs_pairs]
+    return _arr(t if t else [0, 0]), len(t) // 2
+
+
+def solve(problem, want_unique: bool = True):
+    """-> (x[n(n+1)], Stats) for an ambigram_b200.capi.Problem"""
+    L = lib()
+    c2, j2 = _arr(problem.seg_cn2), _arr(problem.fbi_cn2)
+    t, nt = _tgs_rel(problem)
+    x = np.zeros(problem.n * (problem.n + 1), dtype=np.int32)
+    st = Stats()
+    rc = L.orc_solve(problem.n, c2.ctypes.data_as(I32P), j2.ctypes.data_as(I32P), problem.effective_loop_ub(), nt,
+                     t.ctypes.data_as(I32P), int(problem.junc_info), int(want_unique), x.ctypes.data_as(I32P), C.byref(st))
+    if rc != 0:
+        raise RuntimeError(f"orc_solve failed: {rc}")
+    return x, st
+
+
+def model_eval(problem, x) -> Tuple[bool, int]:
+    L = lib()
+    c2, j2 = _arr(problem.seg_cn2), _arr(problem.fbi_cn2)
+    t, nt = _tgs_rel(problem)
+    xx = _arr(x)
+    s = C.c_int64(0)
+    ok = L.orc_model_eval(problem.n, c2.ctypes.data_as(I32P), j2.ctypes.data_as(I32P), problem.effective_loop_ub(), nt,
+                          t.ctypes.data_as(I32P), int(problem.junc_info), xx.ctypes.data_as(I32P), C.byref(s))
+    return bool(ok), int(s.value)
+
+
+def bruteforce(problem, lmax: int = 3):
+    L = lib()
+    c2, j2 = _arr(problem.seg_cn2), _arr(problem.fbi_cn2)
+    t, nt = _tgs_rel(problem)
+    x = np.zeros(problem.n * (problem.n + 1), dtype=np.int32)
+    nopt = C.c_int64(0)
+    best = L.orc_bruteforce(problem.n, c2.ctypes.data_as(I32P), j2.ctypes.data_as(I32P), problem.effective_loop_ub(), nt,
+                            t.ctypes.data_as(I32P), int(problem.junc_info), lmax, x.ctypes.data_as(I32P), C.byref(nopt))
+    return int(best), x, int(nopt.value)
+
+
+def construct_dag(n: int, start_id: int, x) -> Dag:
+    d = Dag()
+    xx = _arr(x)
+    rc = lib().orc_construct_dag(n, start_id, xx.ctypes.data_as(I32P), C.byref(d))
+    if rc != 0:
+        raise RuntimeError("orc_construct_dag failed")
+    return d
+
+
+def first_valid_order(dag: Dag, reversed_: bool = False, naive_cap: Optional[int] = None):
+    """-> (found, used_flipped, order, bkp, n_tested)"""
+    order = (C.c_int32 * MAXK)()
+    bkp = (C.c_int32 * 4096)()
+    flipped, blen, tested = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+    if naive_cap is None:
+        ok = lib().orc_first_valid_order(C.byref(dag), int(reversed_), order, C.byref(flipped), bkp, C.byref(blen), C.byref(tested))
+    else:
+        ok = lib().orc_first_valid_order_naive(C.byref(dag), int(reversed_), C.c_int64(naive_cap), order, C.byref(flipped), bkp,
+                                               C.byref(blen), C.byref(tested))
+    return bool(ok), bool(flipped.value), list(order[:dag.k]), list(bkp[:blen.value]), int(tested.value)
+
+
+def count_valid_orders(dag: Dag, forward: bool = True, cap: int = 0) -> Tuple[int, int]:
+    n_orders = C.c_int64(0)
+    v = lib().orc_count_valid_orders(C.byref(dag), int(forward), C.c_int64(cap), C.byref(n_orders))
+    return int(v), int(n_orders.value)
+
+
+def expand_path(bkp: Sequence[int]) -> List[int]:
+    b = _arr(bkp)
+    out = np.zeros(16384, dtype=np.int32)
+    ln = lib().orc_expand_path(b.ctypes.data_as(I32P), len(b), out.ctypes.data_as(I32P), len(out))
+    return [int(v) for v in out[:ln]]
