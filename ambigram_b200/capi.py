@@ -48,6 +48,11 @@ class _Solution(C.Structure):
                 ("incumbent_score2", C.c_int32), ("seconds", C.c_double), ("seconds_to_best", C.c_double)]
 
 
+class _Profile(C.Structure):
+    _fields_ = [("expand_ms", C.c_double), ("expand_launches", C.c_uint64), ("total_ms", C.c_double),
+                ("incumbent_pass_ms", C.c_double), ("record_stride", C.c_uint64)]
+
+
 class _Dag(C.Structure):
     _fields_ = [("k", C.c_int32), ("kind", C.c_int8 * MAX_COMPONENTS), ("a", C.c_int16 * MAX_COMPONENTS),
                 ("b", C.c_int16 * MAX_COMPONENTS), ("cn", C.c_int16 * MAX_COMPONENTS),
@@ -65,7 +70,7 @@ EXPORTS = [
     "ambi_nccl_unique_id", "ambi_comm_init", "ambi_bfb_solve", "ambi_bfb_solve_batch", "ambi_bfb_solve_shard",
     "ambi_bfb_better", "ambi_bfb_construct_dag", "ambi_bfb_first_valid_order", "ambi_bfb_first_valid_order_batch",
     "ambi_bfb_expand_path", "ambi_batch_upload", "ambi_batch_run", "ambi_batch_fetch", "ambi_batch_free",
-    "ambi_ctx_stream", "ambi_ctx_sync", "ambi_ctx_launch_count",
+    "ambi_ctx_stream", "ambi_ctx_sync", "ambi_ctx_launch_count", "ambi_ctx_set_profile", "ambi_ctx_get_profile",
 ]
 
 _lib = None
@@ -109,6 +114,8 @@ def load_library(path: Optional[str] = None):
     lib.ambi_ctx_stream.argtypes = [vp]
     lib.ambi_ctx_stream.restype = vp
     lib.ambi_ctx_sync.argtypes = [vp]
+    lib.ambi_ctx_set_profile.argtypes = [vp, C.c_int]
+    lib.ambi_ctx_get_profile.argtypes = [vp, C.POINTER(_Profile)]
     lib.ambi_ctx_launch_count.argtypes = [vp]
     lib.ambi_ctx_launch_count.restype = C.c_uint64
     if path is None:
@@ -306,6 +313,15 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.ambi_ctx_launch_count(self.handle))
+
+    def set_profile(self, on: bool):
+        self._check(self.lib.ambi_ctx_set_profile(self.handle, int(on)))
+
+    def profile(self) -> dict:
+        p = _Profile()
+        self._check(self.lib.ambi_ctx_get_profile(self.handle, C.byref(p)))
+        return {"expand_ms": p.expand_ms, "expand_launches": int(p.expand_launches), "total_ms": p.total_ms,
+                "incumbent_pass_ms": p.incumbent_pass_ms, "record_stride": int(p.record_stride)}
 
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)

@@ -137,6 +137,21 @@ extern "C" int ambi_ctx_sync(ambi_ctx *ctx)
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     return e == cudaSuccess ? AMBI_OK : fail(ctx, AMBI_ERR_CUDA, cudaGetErrorString(e));
 }
+extern "C" int ambi_ctx_set_profile(ambi_ctx *ctx, int enable)
+{
+    if (!ctx) return AMBI_ERR_BAD_ARG;
+    ctx->sa.set_profile(enable != 0);
+    return AMBI_OK;
+}
+extern "C" int ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out)
+{
+    if (!ctx || !out) return AMBI_ERR_BAD_ARG;
+    unsigned long long l = 0;
+    ctx->sa.profile(&out->expand_ms, &l, &out->total_ms, &out->incumbent_pass_ms);
+    out->expand_launches = l;
+    out->record_stride = (uint64_t)ctx->sa.record_stride();
+    return AMBI_OK;
+}
 extern "C" uint64_t ambi_ctx_launch_count(const ambi_ctx *ctx) { return ctx ? ctx->sa.launches() + ctx->sb.launches() : 0; }
 
 extern "C" int ambi_nccl_unique_id(void *id128)

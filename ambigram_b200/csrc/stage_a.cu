@@ -570,6 +570,8 @@ void StageA::release()
     counters_ = nullptr; ptab_ = ltab_ = nullptr;
     free_problem_arrays();
     for (int i = 0; i < 4; ++i) if (ev_[i]) { cudaEventDestroy(ev_[i]); ev_[i] = nullptr; }
+    for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
+    prof_ev_.clear();
 }
 
 void StageA::free_problem_arrays()
@@ -658,7 +660,12 @@ int StageA::run_level(int level, int cur, bool beam, int shard_world)
     L.cand_count = d_cand_; L.node_count = d_node_; L.work_counter = c_work; L.overflow = c_over;
     L.ptab = ptab_; L.ltab = ltab_; L.level = level; L.stride = stride_; L.nmax = AMBI_MAXN;
     L.shard_world = shard_world; L.shard_rank = rank_; L.shard_level = shard_level_eff_;
+    if (profile_) {
+        if (prof_used_ + 2 > prof_ev_.size()) { cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); prof_ev_.push_back(e0); prof_ev_.push_back(e1); }
+        CK(cudaEventRecord(prof_ev_[prof_used_], stream_));
+    }
     k_expand<<<sms_ * 4, WPB * 32, 0, stream_>>>(L); ++launches_;
+    if (profile_) { CK(cudaEventRecord(prof_ev_[prof_used_ + 1], stream_)); prof_used_ += 2; }
     DedupArgs D;
     D.recs = buf_[cur ^ 1]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
     D.gen = ++gen_; D.dead = dead_; D.stride = stride_; D.level = level;
@@ -690,6 +697,7 @@ int StageA::run(bool sharded)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
     uint32_t *c_over = counters_ + 3;
+    prof_used_ = 0;
     CK(cudaEventRecord(ev_[0], stream_));
     CK(cudaMemsetAsync(counters_, 0, 64 * sizeof(uint32_t), stream_));
     CK(cudaMemsetAsync(d_cand_, 0, (size_t)count_ * 8, stream_));
@@ -738,6 +746,11 @@ int StageA::fetch(HostResult *out)
     float ms_beam = 0, ms_all = 0;
     cudaEventElapsedTime(&ms_beam, ev_[0], ev_[1]);
     cudaEventElapsedTime(&ms_all, ev_[0], ev_[2]);
+    prof_total_ms_ = ms_all; prof_beam_ms_ = ms_beam;
+    if (profile_) {
+        prof_expand_ms_ = 0; prof_expand_launches_ = prof_used_ / 2;
+        for (size_t i = 0; i + 1 < prof_used_; i += 2) { float m = 0; cudaEventElapsedTime(&m, prof_ev_[i], prof_ev_[i + 1]); prof_expand_ms_ += m; }
+    }
     const bool overflow = ctr[3] != 0;
     for (int p = 0; p < count_; ++p) {
         out[p].score2 = score[p]; out[p].incumbent = inc[p];

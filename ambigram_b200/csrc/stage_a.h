@@ -1,6 +1,7 @@
 // stage_a.h -- host driver of the Stage-A device search (see stage_a.cu).
 #pragma once
 #include "ambi_common.cuh"
+#include <vector>
 
 namespace ambi {
 
@@ -28,6 +29,13 @@ public:
     const char *error() const { return err_; }
     unsigned long long launches() const { return launches_; }
     int count() const { return count_; }
+    // per-kernel timing (CUDA events around every k_expand launch; adds launch gaps, so only
+    // enabled for the bench's roofline pass)
+    void set_profile(bool on) { profile_ = on; }
+    void profile(double *expand_ms, unsigned long long *expand_launches, double *total_ms, double *beam_ms) const {
+        *expand_ms = prof_expand_ms_; *expand_launches = prof_expand_launches_; *total_ms = prof_total_ms_; *beam_ms = prof_beam_ms_;
+    }
+    size_t record_stride() const { return (size_t)stride_; }
 
 private:
     int ensure_problem_arrays(int count);
@@ -52,6 +60,11 @@ private:
     unsigned long long *d_cand_ = nullptr, *d_node_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches_ = 0;
+    bool profile_ = false;
+    std::vector<cudaEvent_t> prof_ev_;
+    size_t prof_used_ = 0;
+    double prof_expand_ms_ = 0, prof_total_ms_ = 0, prof_beam_ms_ = 0;
+    unsigned long long prof_expand_launches_ = 0;
     char err_[256];
 };
 

@@ -1,0 +1,279 @@
+#!/usr/bin/env python3
+"""bench.py -- BFB candidates scored/sec on B200 (BASELINE.json metric), one JSON line.
+
+A "step" is one pass of the hot path (Stage-A fold-pattern search: incumbent pass + exact pass)
+over one batch of synthetic BFB partitions.  Workload at N=1 = BASELINE.json configs[1]:
+synthetic BFB .lh, 12 segments / 4 folds (seeded, ambigram_b200/synth.py), --batch of them per step.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, C ABI)
+    python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port on host cores
+
+value   = candidates scored per second, whole job, inputs resident in HBM (device-event timed)
+e2e     = the same through ambi_bfb_solve_batch with HOST buffers (H2D + D2H inside the timed region)
+roofline / cpu_baseline / clocks: see the task contract and DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "bfb_candidates_scored_per_sec"
+UNIT = "candidates/s"
+N_SEG, N_FOLDS = 12, 4
+
+
+def make_problems(count: int, seed0: int, n: int = N_SEG, folds: int = N_FOLDS):
+    from ambigram_b200 import lh, synth
+    return [lh.problem_from_lh(synth.generate(n, folds, seed0 + s).lh_text()) for s in range(count)]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.splitlines():
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(problems, budget_s: float = 15.0, threads: int = 0):
+    """oracle port (oracle/ambi_oracle.c, OpenMP over problems) on a bounded sample of the workload"""
+    from tests import oracle_lib as orc
+    th = threads or orc.max_threads()
+    sample = problems[:min(len(problems), 64)]
+    t0 = time.perf_counter()
+    _, _, cand = orc.solve_batch(sample, th)
+    dt = time.perf_counter() - t0
+    rate = cand.sum() / dt
+    # scale the sample so that it takes roughly budget_s
+    want = int(min(len(problems), max(len(sample), len(sample) * budget_s / max(dt, 1e-6))))
+    if want > len(sample):
+        sample = problems[:want]
+        t0 = time.perf_counter()
+        _, _, cand = orc.solve_batch(sample, th)
+        dt = time.perf_counter() - t0
+        rate = cand.sum() / dt
+    return {"value": float(rate), "unit": UNIT, "cores": int(th), "kind": "port",
+            "sample": f"first {len(sample)} of the step's {len(problems)} n={N_SEG}/{N_FOLDS}-fold partitions, "
+                      f"oracle/ambi_oracle.c orc_solve_batch, {dt:.2f} s wall",
+            "problems_per_s": len(sample) / dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for this metric = the oracle port (Cbc, the reference's
+    solver, is not in the image and does not count candidates; DESIGN.md 'Reference arm')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from tests import oracle_lib as orc
+    problems = make_problems(args.batch, 0)
+    th = orc.max_threads()
+    # bounded sample per step
+    probe = problems[:min(64, len(problems))]
+    t0 = time.perf_counter(); orc.solve_batch(probe, th); dt = time.perf_counter() - t0
+    per_step = int(min(len(problems), max(len(probe), len(probe) * 8.0 / max(dt, 1e-6))))
+    sample = problems[:per_step]
+    for _ in range(args.warmup):
+        orc.solve_batch(sample, th)
+    tot_c, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        _, _, cand = orc.solve_batch(sample, th)
+        tot_t += time.perf_counter() - t0
+        tot_c += int(cand.sum())
+    value = tot_c / tot_t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"synthetic BFB .lh, {N_SEG} segments / {N_FOLDS} folds, bounded sample of "
+                                   f"{per_step} of {args.batch} partitions per step", "batch": args.batch},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": th, "kind": "port",
+                             "sample": f"{per_step} partitions per step, oracle/ambi_oracle.c (OpenMP)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "problems_per_s": per_step * args.steps / tot_t}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=4096, help="partitions per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from ambigram_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # weak scaling: every rank owns its own --batch partitions (sample-sharded, no data-path collective)
+    problems = make_problems(args.batch, rank * args.batch)
+    ctx = capi.Context(device=local, rank=0, world=1)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
+
+    batch = ctx.upload(problems)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps -------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        batch.run(); ctx.sync()
+    sols = batch.fetch()
+    cand_per_step = sum(s.candidates_scored for s in sols)
+    nodes_per_step = sum(s.nodes_expanded for s in sols)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        ev[k][0].record(stream)
+        batch.run()
+        ev[k][1].record(stream)
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = ctx.launch_count() - launches0
+    sols = batch.fetch()
+    t_best = statistics.mean(s.seconds_to_best for s in sols)
+
+    # ---- end to end through the C ABI with host buffers --------------------------
+    for _ in range(2):
+        ctx.solve_batch(problems)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_sols = ctx.solve_batch(problems)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    e2e_cand = sum(s.candidates_scored for s in e2e_sols)
+
+    # ---- roofline pass: per-launch duration of the dominant kernel (k_expand) ----
+    ctx.set_profile(True)
+    batch.run(); ctx.sync(); batch.fetch()
+    prof = ctx.profile()
+    ctx.set_profile(False)
+
+    # max over ranks / sum over ranks
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    c = torch.tensor([float(cand_per_step), float(e2e_cand), float(launches)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
+    cand_all, e2e_cand_all, launches_all = float(c[0]), float(c[1]), int(c[2])
+
+    if rank == 0:
+        hbm_peak, peak_src, sm_max = measured_peaks()
+        ms_per_step = dev_ms_max / args.steps
+        value = cand_all / (ms_per_step * 1e-3)
+        e2e_value = e2e_cand_all * args.steps / e2e_s_max
+        # algorithmic work of the dominant kernel: per candidate 8n+16 INT32 ops;
+        # per record materialised in a frontier buffer (read or written) 4n+16 bytes
+        n = N_SEG
+        exp_s = prof["expand_ms"] * 1e-3
+        recs = 2 * nodes_per_step            # every expanded record was written once and read once
+        alg_bytes = recs * (4 * n + 16)
+        alg_ops = cand_per_step * (8 * n + 16)
+        int_peak = 148 * 128 * sm_max * 1e6  # nominal INT32 lanes x clock (no measured figure in MEASURED_PEAKS.json)
+        roof = {"bound": "hbm", "achieved": alg_bytes / exp_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg_bytes / exp_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "k_expand", "launches": prof["expand_launches"],
+                "avg_launch_us": 1e3 * prof["expand_ms"] / max(prof["expand_launches"], 1),
+                "share_of_step": prof["expand_ms"] / prof["total_ms"],
+                "note": "k_expand is INT32-issue bound, not HBM bound: see roofline_int32"}
+        roof_int = {"bound": "int32", "achieved": alg_ops / exp_s / 1e12, "peak": int_peak / 1e12, "unit": "Top/s",
+                    "frac": alg_ops / exp_s / int_peak, "ops_per_candidate": 8 * n + 16,
+                    "peak_source": "nominal 148 SM x 128 lanes x sm_max_mhz"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": f"synthetic BFB .lh, {N_SEG} segments / {N_FOLDS} folds (BASELINE configs[1]), "
+                                       f"{args.batch} partitions per step per GPU, seeds rank*batch..",
+                           "batch_per_gpu": args.batch, "l2": "256 MB buffer written between timed steps",
+                           "parallelism": f"sample-sharded x{world}"},
+                "e2e": {"value": e2e_value, "unit": UNIT,
+                        "h2d_bytes_per_step": args.batch * 416 * world, "d2h_bytes_per_step": args.batch * 156 * world},
+                "gpu_launches": launches_all,
+                "candidates_per_step": cand_all, "problems_per_s": args.batch * world / (ms_per_step * 1e-3),
+                "time_to_best_ms_per_lh": 1e3 * t_best,
+                "roofline": roof, "roofline_int32": roof_int, "clocks": clocks}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(problems)
+        print(json.dumps(line))
+    batch.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -192,6 +192,18 @@ int  ambi_batch_fetch(ambi_ctx *ctx, ambi_batch *batch, ambi_bfb_solution *solut
 void ambi_batch_free(ambi_ctx *ctx, ambi_batch *batch);
 void *ambi_ctx_stream(ambi_ctx *ctx);                                  /* cudaStream_t */
 int  ambi_ctx_sync(ambi_ctx *ctx);
+/* Per-kernel timing of the last ambi_batch_run/solve (CUDA events around every
+ * launch of the expansion+scoring kernel; only when enabled: it serialises
+ * launches and is meant for the bench's roofline pass).                      */
+typedef struct {
+    double expand_ms;          /* sum of k_expand launch durations              */
+    uint64_t expand_launches;
+    double total_ms;           /* whole search (incumbent + exact pass)         */
+    double incumbent_pass_ms;
+    uint64_t record_stride;    /* bytes per candidate record in HBM             */
+} ambi_profile;
+int  ambi_ctx_set_profile(ambi_ctx *ctx, int enable);
+int  ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out);
 /* kernels launched by the ctx since creation (bench "gpu_launches") */
 uint64_t ambi_ctx_launch_count(const ambi_ctx *ctx);
 

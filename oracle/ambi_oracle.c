@@ -782,3 +782,40 @@ int orc_expand_path(const int32_t *bkp, int32_t bkp_len, int32_t *path_out, int3
     }
     return len;
 }
+
+/* ------------------------------------------------------------------ */
+/* batch driver for the CPU baseline (bench.py): independent problems  */
+/* are solved in parallel with OpenMP, one problem per thread at a time */
+/* ------------------------------------------------------------------ */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* problems are packed: n[i], then c2/j2 at offsets off[i] (each n[i] ints);
+ * x_out at xoff[i]; no third-generation rows in the packed form. */
+int orc_solve_batch(int count, const int32_t *n, const int32_t *off, const int32_t *c2, const int32_t *j2,
+                    const int32_t *loop_ub, const int64_t *xoff, int32_t *x_out, int64_t *score2,
+                    int64_t *candidates, int threads)
+{
+    int bad = 0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : bad)
+    for (int i = 0; i < count; i++) {
+        orc_solve_stats st;
+        int rc = orc_solve(n[i], c2 + off[i], j2 + off[i], loop_ub[i], 0, NULL, 0, 0, x_out + xoff[i], &st);
+        if (rc) bad++;
+        score2[i] = st.score2; candidates[i] = st.candidates;
+    }
+    return bad;
+}

@@ -130,3 +130,35 @@ def expand_path(bkp: Sequence[int]) -> List[int]:
     out = np.zeros(16384, dtype=np.int32)
     ln = lib().orc_expand_path(b.ctypes.data_as(I32P), len(b), out.ctypes.data_as(I32P), len(out))
     return [int(v) for v in out[:ln]]
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
+def solve_batch(problems, threads: int = 0):
+    """OpenMP batch solve (no third-generation rows) -> (list of x, scores, candidates)"""
+    L = lib()
+    cnt = len(problems)
+    n = _arr([p.n for p in problems])
+    off = np.zeros(cnt, dtype=np.int32)
+    xoff = np.zeros(cnt, dtype=np.int64)
+    o = xo = 0
+    for i, p in enumerate(problems):
+        off[i], xoff[i] = o, xo
+        o += p.n
+        xo += p.n * (p.n + 1)
+    c2 = _arr(np.concatenate([np.asarray(p.seg_cn2) for p in problems]))
+    j2 = _arr(np.concatenate([np.asarray(p.fbi_cn2) for p in problems]))
+    ub = _arr([p.effective_loop_ub() for p in problems])
+    x = np.zeros(xo, dtype=np.int32)
+    score = np.zeros(cnt, dtype=np.int64)
+    cand = np.zeros(cnt, dtype=np.int64)
+    I64P = C.POINTER(C.c_int64)
+    bad = L.orc_solve_batch(cnt, n.ctypes.data_as(I32P), off.ctypes.data_as(I32P), c2.ctypes.data_as(I32P),
+                            j2.ctypes.data_as(I32P), ub.ctypes.data_as(I32P), xoff.ctypes.data_as(I64P),
+                            x.ctypes.data_as(I32P), score.ctypes.data_as(I64P), cand.ctypes.data_as(I64P), int(threads))
+    if bad:
+        raise RuntimeError(f"orc_solve_batch: {bad} problems failed")
+    xs = [x[xoff[i]:xoff[i] + problems[i].n * (problems[i].n + 1)] for i in range(cnt)]
+    return xs, score, cand

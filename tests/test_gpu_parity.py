@@ -1,0 +1,181 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the committed
+fixtures.  Bit-exact bar: same score2, same element_cn (search-order tie-break), same order and path."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from ambigram_b200 import capi, lh, synth
+from ambigram_b200.capi import Problem
+from tests import oracle_lib as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = json.load(open(os.path.join(ROOT, "tests", "golden", "cases.json")))["cases"]
+README_PATH = "1+2+3+4+5+6+|6-5-4-3-2-|2+3+4+|4-3-|3+4+|4-3-2-|2+3+4+5+6+|6-5-4-3-2-1-"
+
+
+def problem_of(case):
+    g = lh.parse_lh(case["lh"])
+    comps = lh.read_components(g, case["juncs"]) if case["juncs"] else []
+    return lh.flatten(g, comps, case["junc_info"])[0].problem
+
+
+def check_against_oracle(p, sol):
+    x, st = orc.solve(p, want_unique=False)
+    assert sol.status == 0
+    assert sol.score2 == st.score2
+    assert sol.objective2 == st.score2 - 2 * p.bias
+    assert np.array_equal(sol.element_cn, x)
+    ok, s2 = orc.model_eval(p, sol.element_cn)
+    assert ok and s2 == sol.score2
+    assert sol.incumbent_score2 >= sol.score2 and sol.candidates_scored > 0
+
+
+def test_readme_known_answer(ctx):
+    p = lh.problem_from_lh(open(os.path.join(ROOT, "tests", "golden", "readme6.lh")).read())
+    sol = ctx.solve(p)
+    assert sol.score2 == 2 and [int(i) for i in np.nonzero(sol.element_cn)[0]] == [26, 29, 31, 33]
+    dag = capi.construct_dag(p.n, p.start_id, sol.element_cn)
+    res = ctx.first_valid_order(dag, False)
+    assert res.found and not res.used_flipped and res.order == [0, 1, 2, 3]
+    assert capi.format_path(capi.expand_path(res.bkp)) == README_PATH
+    rev = ctx.first_valid_order(dag, True)
+    assert capi.format_path(capi.expand_path(rev.bkp)) == \
+        "6-5-4-3-2-1-|1+2+3+4+5+6+|6-5-4-3-2-|2+3+4+|4-3-|3+4+|4-3-2-|2+3+4+5+6+"
+
+
+def test_golden_cases_batch(ctx):
+    """every committed fixture (reference-generated) in one device batch"""
+    probs = [problem_of(c) for c in CASES]
+    sols = ctx.solve_batch(probs)
+    dags = []
+    for c, p, s in zip(CASES, probs, sols):
+        assert s.status == 0 and s.score2 == c["oracle_score2"], c["name"]
+        assert [[int(i), int(v)] for i, v in enumerate(s.element_cn) if v] == c["oracle_x_nz"], c["name"]
+        if c.get("ref_highs_objective") is not None:
+            assert abs(2 * (c["ref_highs_objective"] + c["bias"]) - s.score2) < 1e-6
+        dags.append(capi.construct_dag(p.n, p.start_id, s.element_cn))
+    for rev, key in ((False, "ref_inject_paths"), (True, "ref_inject_paths_rev")):
+        res = ctx.first_valid_order_batch(dags, [rev] * len(dags))
+        for c, d, r in zip(CASES, dags, res):
+            if d.k > 16 or not c[key]:
+                continue
+            assert r.found, c["name"]
+            assert capi.format_path(capi.expand_path(r.bkp)) == c[key][0], c["name"]
+
+
+@pytest.mark.parametrize("n,folds,noise,count", [(2, 2, 0.5, 12), (3, 2, 0.5, 16), (5, 3, 0.5, 24), (8, 3, 0.5, 24),
+                                                 (12, 4, 0.0, 32), (12, 4, 0.5, 32), (16, 5, 0.5, 8), (20, 6, 0.5, 4)])
+def test_seeded_synthetic_vs_oracle(ctx, n, folds, noise, count):
+    probs = [lh.problem_from_lh(synth.generate(n, folds, 100 + s, noise).lh_text()) for s in range(count)]
+    sols = ctx.solve_batch(probs)
+    for p, s in zip(probs, sols):
+        check_against_oracle(p, s)
+    # single-problem entry point agrees with the batched one
+    one = ctx.solve(probs[0])
+    assert one.score2 == sols[0].score2 and np.array_equal(one.element_cn, sols[0].element_cn)
+
+
+def test_random_profiles_ragged_batch(ctx):
+    """ragged batch: n from 1 to 10, arbitrary (non-BFB) profiles, zeros, third-generation rows"""
+    rng = random.Random(5)
+    probs = []
+    for _ in range(200):
+        n = rng.randint(1, 10)
+        tg = []
+        for _ in range(rng.choice([0, 0, 1, 3])):
+            a = rng.randrange(n); b = rng.randrange(a, n); tg += [a + 1, b + 1]
+        probs.append(Problem(n=n, seg_cn2=[rng.choice([0, 1, 2, 4, 6, 7, 12, 20]) for _ in range(n)],
+                             fbi_cn2=[rng.choice([0, 0, 1, 2, 4, 6]) for _ in range(n)], start_id=1,
+                             loop_ub=rng.choice([0, 1, 2, 9, 40]), bias=rng.choice([1, 2]), tgs_pairs=tg,
+                             junc_info=rng.choice([False, True])))
+    sols = ctx.solve_batch(probs)
+    for p, s in zip(probs, sols):
+        check_against_oracle(p, s)
+
+
+def test_small_n_vs_bruteforce(ctx):
+    rng = random.Random(9)
+    probs = [Problem(n=n, seg_cn2=[rng.randint(0, 12) for _ in range(n)], fbi_cn2=[rng.randint(0, 6) for _ in range(n)],
+                     loop_ub=rng.choice([1, 2, 3])) for n in [1, 2, 3] * 20]
+    sols = ctx.solve_batch(probs)
+    for p, s in zip(probs, sols):
+        best, xb, _ = orc.bruteforce(p, lmax=3)
+        assert s.score2 == best and np.array_equal(s.element_cn, xb)
+
+
+def test_results_do_not_depend_on_beam_or_batching():
+    probs = [lh.problem_from_lh(synth.generate(12, 4, 300 + s, 0.5).lh_text()) for s in range(24)]
+    ref = None
+    for beam in (1, 8, 64, 512):
+        with capi.Context(device=0, beam_width=beam) as c:
+            sols = c.solve_batch(probs)
+            got = [(s.score2, tuple(int(v) for v in s.element_cn)) for s in sols]
+            if ref is None:
+                ref = got
+            assert got == ref
+            shuffled = list(reversed(probs))
+            got2 = [(s.score2, tuple(int(v) for v in s.element_cn)) for s in c.solve_batch(shuffled)]
+            assert got2 == list(reversed(ref))
+
+
+def test_repeated_runs_are_identical(ctx):
+    probs = [lh.problem_from_lh(synth.generate(14, 4, 500 + s, 0.5).lh_text()) for s in range(16)]
+    a = ctx.solve_batch(probs)
+    b = ctx.solve_batch(probs)
+    for s, t in zip(a, b):
+        assert s.score2 == t.score2 and np.array_equal(s.element_cn, t.element_cn)
+
+
+def test_stage_b_vs_oracle_batch(ctx):
+    probs = [lh.problem_from_lh(synth.generate(n, f, 700 + s, 0.5).lh_text())
+             for (n, f) in [(6, 3), (10, 4), (12, 4), (16, 5)] for s in range(12)]
+    sols = ctx.solve_batch(probs)
+    dags = [capi.construct_dag(p.n, p.start_id, s.element_cn) for p, s in zip(probs, sols)]
+    for rev in (False, True):
+        res = ctx.first_valid_order_batch(dags, [rev] * len(dags))
+        for p, s, d, r in zip(probs, sols, dags, res):
+            od = orc.construct_dag(p.n, p.start_id, s.element_cn)
+            assert od.nodes() == d.nodes() and od.edges() == d.edges()
+            ok, flipped, order, bkp, _ = orc.first_valid_order(od, rev)
+            assert r.found == ok
+            if ok:
+                assert (r.used_flipped, r.order, r.bkp) == (flipped, order, bkp)
+                assert capi.expand_path(r.bkp) == orc.expand_path(bkp)
+
+
+def test_prefix_sharded_solve_combines_to_the_same_optimum():
+    """multi-GPU path on one device: every shard explores only the prefixes hashed to it; the arg-min
+    of the shard optima in (score, search order) must equal the unsharded answer"""
+    probs = [lh.problem_from_lh(synth.generate(n, f, 40 + s, 0.5).lh_text()) for (n, f, s) in
+             [(6, 3, 0), (10, 4, 1), (12, 4, 2), (12, 4, 3), (16, 5, 4)]]
+    with capi.Context(device=0) as c1:
+        want = [c1.solve(p) for p in probs]
+    for world in (2, 4):
+        shard_sols = []
+        for rank in range(world):
+            with capi.Context(device=0, rank=rank, world=world) as c:
+                shard_sols.append([c.solve_shard(p) for p in probs])
+        for i, p in enumerate(probs):
+            best = None
+            for rank in range(world):
+                s = shard_sols[rank][i]
+                if best is None or capi.better(p.n, s.score2, s.element_cn, best.score2, best.element_cn):
+                    best = s
+            assert best.score2 == want[i].score2 and np.array_equal(best.element_cn, want[i].element_cn)
+
+
+def test_overflow_is_reported_loudly():
+    p = lh.problem_from_lh(synth.generate(16, 5, 0, 0.5).lh_text())
+    with capi.Context(device=0, node_capacity=64) as c:
+        with pytest.raises(capi.AmbiError) as e:
+            c.solve(p)
+        assert e.value.status == -5
+
+
+def test_bad_arguments(ctx):
+    with pytest.raises(capi.AmbiError):
+        ctx.solve(Problem(n=33, seg_cn2=[2] * 33, fbi_cn2=[0] * 33))

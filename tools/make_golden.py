@@ -1,0 +1,182 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/cases.json by running the REFERENCE's own code (oracle/_ref/Ambigram_ref,
+built from /root/reference by `make -C oracle ref`) in this container.
+
+For every case we record
+  * the reference's printed BFB path with HiGHS standing in for cbc (mode highs) -- the whole
+    reference pipeline end to end,
+  * the optimal objective of the reference's own LP (the matrix its BFB_ILP emitted),
+  * (feasible, score2) of the reference's rows on a set of probe assignments -- pins
+    oracle/ambi_oracle.c orc_model_eval row for row,
+  * the path the reference prints when OUR oracle's Stage-A assignment is injected as the cbc
+    answer (mode inject) -- pins Stage B (constructDAG, allTopologicalOrders, getBFB, imperfectFBI,
+    expansion, printBFB) independently of solver tie-breaks; also with --reversed.
+The GPU box has no /root/reference: tests read only the JSON written here.
+"""
+import json
+import os
+import random
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+from ambigram_b200 import lh, synth  # noqa: E402
+from tests import oracle_lib as orc  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "Ambigram_ref")
+BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+PATH_RE = re.compile(r"^\d+[+-](\|{0,2}\d+[+-])*$")
+
+
+def run_ref(lh_text, juncs_text="", junc_info=False, reversed_=False, inject=None):
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "in.lh"), "w").write(lh_text)
+        cmd = [REF, "--op", "bfb", "--in_lh", "in.lh", "--lp_prefix", "p"]
+        if juncs_text:
+            open(os.path.join(d, "in.juncs"), "w").write(juncs_text)
+            cmd += ["--juncdb", "in.juncs"]
+        if junc_info:
+            cmd += ["--junc_info", "true"]
+        if reversed_:
+            cmd += ["--reversed"]
+        env = dict(os.environ, PATH=BIN + ":" + os.environ["PATH"])
+        if inject is not None:
+            with open(os.path.join(d, "inject.txt"), "w") as f:
+                for i, v in enumerate(inject):
+                    if v:
+                        f.write(f"{i} {int(v)}\n")
+            env["AMBI_CBC_MODE"] = "inject"
+            env["AMBI_CBC_SOL"] = os.path.join(d, "inject.txt")
+        r = subprocess.run(cmd, cwd=d, env=env, capture_output=True, text=True, timeout=3600)
+        paths = [ln.strip() for ln in r.stdout.splitlines() if PATH_RE.match(ln.strip())]
+        sol = open(os.path.join(d, "p.sol")).read() if os.path.exists(os.path.join(d, "p.sol")) else ""
+        lp = open(os.path.join(d, "p.lp")).read() if os.path.exists(os.path.join(d, "p.lp")) else ""
+        return r.returncode, paths, sol, lp, r.stdout
+
+
+def parse_sol(sol, nvars):
+    obj, x = None, [0] * nvars
+    toks = sol.split()
+    for i, t in enumerate(toks):
+        if t == "value":
+            obj = float(toks[i + 1])
+        if t.startswith("x") and t[1:].isdigit() and int(t[1:]) < nvars:
+            x[int(t[1:])] = int(round(float(toks[i + 1])))
+    return obj, x
+
+
+def lp_eval(lp, x, nvars):
+    """(feasible, score2) of the reference's dumped rows on integer x (eps optimal)."""
+    lines = lp.splitlines()
+    nrows, ncols = map(int, lines[1].split())
+    rows = []
+    for ln in lines[2:2 + nrows]:
+        t = ln.split()
+        rows.append((float(t[1]), float(t[2]), [(int(p.split(":")[0]), float(p.split(":")[1])) for p in t[4:]]))
+    cols = [ln.split() for ln in lines[2 + nrows:2 + nrows + ncols]]
+    ok = True
+    for i in range(nvars):
+        if x[i] < float(cols[i][1]) or x[i] > float(cols[i][2]):
+            ok = False
+    neps = ncols - 1 - nvars
+    score2 = 0.0
+    for k in range(neps):
+        lo, hi, r = rows[2 * k]
+        val = sum(c * x[i] for i, c in r if i < nvars)
+        score2 += 2 * abs(val - lo)
+    for (lo, hi, r) in rows[2 * neps + 1:]:
+        val = sum(c * x[i] for i, c in r if i < nvars)
+        if val < lo - 1e-9 or val > hi + 1e-9:
+            ok = False
+    return ok, int(round(score2))
+
+
+def probes(problem, xopt, rng, k=24):
+    n = problem.n
+    nv = n * (n + 1)
+    out = [list(map(int, xopt)), [0] * nv]
+    for _ in range(k):
+        x = list(map(int, xopt))
+        for _ in range(rng.randint(1, 3)):
+            i = rng.randrange(nv)
+            x[i] = max(0, x[i] + rng.choice([-1, 1]))
+        out.append(x)
+    for _ in range(k // 2):
+        x = [0] * nv
+        for _ in range(rng.randint(1, 4)):
+            x[rng.randrange(nv)] = rng.randint(1, 2)
+        out.append(x)
+    return out
+
+
+def make_case(name, lh_text, juncs_text="", junc_info=False, want_highs=True, rng=None):
+    rng = rng or random.Random(1)
+    g = lh.parse_lh(lh_text)
+    comps = lh.read_components(g, juncs_text) if juncs_text else []
+    parts = lh.flatten(g, comps, junc_info)
+    assert len(parts) == 1 and parts[0].problem is not None, name
+    p = parts[0].problem
+    nv = p.n * (p.n + 1)
+    case = {"name": name, "lh": lh_text, "juncs": juncs_text, "junc_info": junc_info,
+            "n": p.n, "seg_cn2": list(p.seg_cn2), "fbi_cn2": list(p.fbi_cn2), "loop_ub": p.effective_loop_ub(),
+            "bias": p.bias, "tgs_pairs": list(p.tgs_pairs), "start_id": p.start_id}
+    x, st = orc.solve(p, want_unique=True)
+    case["oracle_score2"] = int(st.score2)
+    case["oracle_unique"] = int(st.unique)
+    case["oracle_x_nz"] = [[int(i), int(v)] for i, v in enumerate(x) if v]
+    if want_highs:
+        rc, paths, sol, lpt, out = run_ref(lh_text, juncs_text, junc_info)
+        obj, xh = parse_sol(sol, nv)
+        case["ref_rc"] = rc
+        case["ref_highs_objective"] = obj
+        case["ref_highs_x_nz"] = [[i, v] for i, v in enumerate(xh) if v]
+        case["ref_highs_paths"] = paths
+    # inject our Stage-A answer into the reference -> its Stage B output
+    for rev in (False, True):
+        rc, paths, sol, lpt, out = run_ref(lh_text, juncs_text, junc_info, reversed_=rev, inject=x)
+        case["ref_inject_paths_rev" if rev else "ref_inject_paths"] = paths
+        case["ref_inject_rc_rev" if rev else "ref_inject_rc"] = rc
+    # LP stats + probe evaluations with the reference's own rows
+    lines = lpt.splitlines()
+    case["lp_rows"], case["lp_cols"] = map(int, lines[1].split())
+    pr = probes(p, x, rng)
+    case["probes"] = [{"x_nz": [[i, v] for i, v in enumerate(q) if v], "feasible": bool(f), "score2": s}
+                      for q in pr for (f, s) in [lp_eval(lpt, q, nv)]]
+    return case
+
+
+def main():
+    cases = []
+    rng = random.Random(7)
+    readme = open(os.path.join(ROOT, "tests", "golden", "readme6.lh")).read()
+    cases.append(make_case("readme6", readme, rng=rng))
+    readme_juncs = "6+ 6- 5- 4- 3- 2- 2+\n2- 2+ 3+ 4+ 5+ 6+ 6-\n6+ 6- 5- 4- 3-\n"
+    cases.append(make_case("readme6_juncs", readme, readme_juncs, True, rng=rng))
+    spec = [(2, 2, 0.0, 2), (3, 2, 0.5, 3), (4, 2, 0.5, 3), (5, 3, 0.5, 3), (6, 3, 0.0, 3), (6, 3, 0.5, 4),
+            (8, 3, 0.5, 4), (10, 4, 0.5, 4), (12, 4, 0.0, 4), (12, 4, 0.5, 4), (14, 4, 0.5, 2), (16, 5, 0.5, 2)]
+    for n, folds, noise, k in spec:
+        for seed in range(k):
+            s = synth.generate(n, folds, seed, noise)
+            cases.append(make_case(f"synth_n{n}_f{folds}_noise{noise}_s{seed}", s.lh_text(), rng=rng))
+            print(cases[-1]["name"], cases[-1]["oracle_score2"], cases[-1].get("ref_highs_objective"), flush=True)
+    for n, folds, seed in [(8, 3, 11), (12, 4, 12), (12, 4, 13)]:
+        s = synth.generate(n, folds, seed, 0.0, with_juncs=True)
+        cases.append(make_case(f"synth_juncs_n{n}_s{seed}", s.lh_text(), s.juncs_text(), True, rng=rng))
+        print(cases[-1]["name"], cases[-1]["oracle_score2"], cases[-1].get("ref_highs_objective"), flush=True)
+    # n = 20 : HiGHS is slow here, keep two
+    for seed in (2, 3):
+        s = synth.generate(20, 6, seed, 0.0)
+        cases.append(make_case(f"synth_n20_f6_s{seed}", s.lh_text(), want_highs=(seed == 2), rng=rng))
+        print(cases[-1]["name"], cases[-1]["oracle_score2"], cases[-1].get("ref_highs_objective"), flush=True)
+    out = os.path.join(ROOT, "tests", "golden", "cases.json")
+    json.dump({"generator": "tools/make_golden.py", "cases": cases}, open(out, "w"), indent=0)
+    print("wrote", out, len(cases), "cases")
+
+
+if __name__ == "__main__":
+    main()
