@@ -302,6 +302,15 @@ class Context:
         self._check(self.lib.ambi_bfb_solve_batch(self.handle, pk.count, pk.arr, pk.sol))
         return pk.solutions()
 
+    @staticmethod
+    def pack(problems: Sequence[Problem]) -> "_Packed":
+        """marshal once (host arrays of ambi_bfb_problem / ambi_bfb_solution) for repeated solve_packed calls"""
+        return _Packed(problems)
+
+    def solve_packed(self, pk: "_Packed") -> None:
+        """ambi_bfb_solve_batch on pre-marshalled host buffers; results land in pk (pk.solutions())"""
+        self._check(self.lib.ambi_bfb_solve_batch(self.handle, pk.count, pk.arr, pk.sol))
+
     def upload(self, problems: Sequence[Problem]) -> ResidentBatch:
         return ResidentBatch(self, _Packed(problems))
 

@@ -47,6 +47,7 @@ struct DevProblem {
     int32_t pad[3];
     int32_t c2[AMBI_MAXN];
     int32_t j2[AMBI_MAXN];
+    uint32_t cj[AMBI_MAXN];         // c2 | j2<<16 (both < 65536), what k_expand stages in shared memory
     uint32_t tgs_mask[AMBI_MAXN];   // row a: bit b set if (a,b) is a third-generation span
 };
 

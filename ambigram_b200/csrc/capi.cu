@@ -189,7 +189,9 @@ static int to_dev(const ambi_bfb_problem &p, DevProblem &d, std::string &why)
     long long z = 0;
     for (int i = 0; i < p.n; ++i) {
         if (p.seg_cn2[i] < 0 || p.fbi_cn2[i] < 0) { why = "negative copy number"; return AMBI_ERR_BAD_ARG; }
+        if (p.seg_cn2[i] > 65535 || p.fbi_cn2[i] > 65535) { why = "copy number above 32767"; return AMBI_ERR_BAD_ARG; }
         d.c2[i] = p.seg_cn2[i]; d.j2[i] = p.fbi_cn2[i];
+        d.cj[i] = (uint32_t)p.seg_cn2[i] | ((uint32_t)p.fbi_cn2[i] << 16);
         z += (long long)p.seg_cn2[i] + p.fbi_cn2[i];
     }
     if (z > 0x3fffffff) { why = "copy numbers too large"; return AMBI_ERR_BAD_ARG; }

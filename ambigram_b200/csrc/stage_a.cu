@@ -20,15 +20,18 @@
 #include "stage_a.h"
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 
 namespace ambi {
 
 constexpr int WPB = 8;              // warps per block in k_expand
-constexpr int PL_CAP = 544;         // >= AMBI_NP_CODES, multiple of 32
-constexpr int LL_CAP = 576;         // >= AMBI_NL_CODES, multiple of 32
+constexpr int GRP = 32;             // frontier records handled together by one warp
 constexpr int BEAM_BINS = 64;
+constexpr int CFG_NONE = 63;        // "no column" in a packed row configuration
+
+enum { EMIT_ALL = 0, EMIT_BEST = 1 };
 
 struct LevelArgs {
     const DevProblem *probs;
@@ -43,11 +46,10 @@ struct LevelArgs {
     unsigned long long *node_count;
     uint32_t *work_counter;
     uint32_t *overflow;
-    const uint8_t *ptab;            // [AMBI_NP_CODES][2] (q1,q2)
-    const uint8_t *ltab;            // [AMBI_NL_CODES][2]
     int level;
     int stride;
     int nmax;
+    int emit;                       // EMIT_ALL: every child within the limit; EMIT_BEST: arg-min child per record
     int shard_world, shard_rank, shard_level;
 };
 
@@ -58,288 +60,431 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     return x;
 }
 
-struct WarpShared {
-    uint16_t pl[PL_CAP];
-    uint16_t ll[LL_CAP];
-    int32_t c2[AMBI_MAXN];
-    int32_t j2[AMBI_MAXN];
-    uint32_t col[AMBI_MAXN];        // w | bP<<8 | bL<<16 | (nP+nL)<<24
-    uint32_t queue[64];
+// position of the k-th (0-based) set bit of m
+__device__ __forceinline__ int nth_bit(uint32_t m, int k) {
+    int pos = 0;                         // branch-free binary search on population counts
+#pragma unroll
+    for (int w = 16; w; w >>= 1) {
+        const int c = __popc(m & (((1u << w) - 1u) << pos));
+        const bool up = k >= c;
+        k -= up ? c : 0; pos += up ? w : 0;
+    }
+    return pos;
+}
+__device__ __forceinline__ uint32_t below(int b) { return (1u << b) - 1u; }
+
+// Per-warp staging of a group of GRP frontier records.  Column arrays are laid out
+// [column][slot] so that lanes working on different records hit different banks and
+// lanes working on the same record broadcast.
+struct GroupShared {
+    uint8_t  colb[AMBI_MAXN][GRP];      // nP | nL<<2 | bP<<4 | bL<<6 of column j of record slot
+    uint32_t cj[AMBI_MAXN][GRP];        // 2c_j | 2J_j << 16 of the record's problem
+    uint32_t okP[GRP], parP[GRP];       // column may take a pattern end / has a pattern parent (row 1)
+    uint32_t okL1[GRP], okL2[GRP];      // column may take one / two loop ends
+    uint32_t par1[GRP], par2[GRP];      // column already holds >= 1 / >= 2 parents for a loop (row 3)
+    uint32_t tmask[GRP];                // third-generation cells of this row
+    int32_t  score[GRP], slack[GRP], covC[GRP], fbC[GRP], ptgs[GRP], prob[GRP];
+    uint32_t pidx[GRP];
+    uint32_t nl0[GRP], nlall[GRP];      // loop multisets: parents satisfied already / all within budget
+    uint32_t cstart[GRP + 1];           // exclusive prefix of candidate counts
+    uint8_t  n[GRP];
+    uint32_t cnt[GRP];                  // candidates scored per record
+    unsigned long long best[GRP];       // EMIT_BEST: min (tot<<32 | cfg-order key)
+    uint32_t qh[64];                    // light-test survivors awaiting the bound: slot<<24 | cfg
+    uint32_t qw_cfg[64]; int32_t qw_err[64]; int32_t qw_tot[64];   // children awaiting the write
 };
 
-// Admissible bound on segments j > a for a child (ends p1<p2, l1<=l2; -1 = absent).
-// Mirrors oracle/ambi_oracle.c future_bound(): committed coverage / fold-back can
-// only grow; what can still be added is capped by column budgets and 6 per row.
-__device__ __forceinline__ int child_bound(const WarpShared &S, int n, int a,
-                                           int p1, int p2, int l1, int l2, int budget)
+// packed row configuration: p1 | p2<<6 | l1<<12 | l2<<18 (columns, CFG_NONE = absent; p1<p2, l1<=l2)
+__device__ __forceinline__ uint32_t pack_cfg(int p1, int p2, int l1, int l2) {
+    return (uint32_t)(p1 & 63) | ((uint32_t)(p2 & 63) << 6) | ((uint32_t)(l1 & 63) << 12) | ((uint32_t)(l2 & 63) << 18);
+}
+__device__ __forceinline__ void unpack_cfg(uint32_t c, int &p1, int &p2, int &l1, int &l2) {
+    p1 = c & 63; p2 = (c >> 6) & 63; l1 = (c >> 12) & 63; l2 = (c >> 18) & 63;
+    p1 = p1 == CFG_NONE ? -1 : p1; p2 = p2 == CFG_NONE ? -1 : p2;
+    l1 = l1 == CFG_NONE ? -1 : l1; l2 = l2 == CFG_NONE ? -1 : l2;
+}
+// search-order code of a configuration (see ambi_common.cuh)
+__device__ __forceinline__ uint32_t cfg_code(int n, int p1, int p2, int l1, int l2) {
+    int ip = p1 < 0 ? 0 : ambi_ip_code(n - 1 - p1, p2 < 0 ? -1 : n - 1 - p2);
+    int il = l1 < 0 ? 0 : ambi_il_code(n - 1 - l1, l2 < 0 ? -1 : n - 1 - l2);
+    return ((uint32_t)ip << 10) | (uint32_t)il;
+}
+
+// Admissible bound on segments j > a for a child of record `slot` (ends p1<p2, l1<=l2; -1 absent).
+// Mirrors oracle/ambi_oracle.c future_bound(): committed coverage / fold-back can only grow; what
+// can still be added is capped by the column budgets and by 6 per remaining row.
+// All lanes walk the same columns (jtop-1 .. a+1) so the shared-memory reads stay conflict free.
+__device__ __forceinline__ int child_bound(const GroupShared &S, int slot, int jtop, int a,
+                                           int p1, int p2, int l1, int l2, int budget, bool active)
 {
     int lb = 0, cov = 0, capsum = 0;
-    for (int j = n - 1; j > a; --j) {
-        uint32_t cw = S.col[j];
-        int w = cw & 0xff, bP = (cw >> 8) & 0xff, bL = (cw >> 16) & 0xff;
-        int pab = (j == p1) + (j == p2), lab = (j == l1) + (j == l2);
-        int rp = (p1 >= 0 && p1 < j) + (p2 >= 0 && p2 < j);
-        int rl = (l1 >= 0 && l1 < j) + (l2 >= 0 && l2 < j);
-        int kP = 2 - pab - max(rp, rl);
-        int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
-        int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
-        int cap = min(nbP, 2) + 2 * min(nbL, 2);
-        int wn = w + pab + 2 * lab;
+#pragma unroll 2
+    for (int j = jtop - 1; j > a; --j) {
+        const uint32_t cb = S.colb[j][slot];
+        const uint32_t cjw = S.cj[j][slot];
+        const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = (cb >> 6) & 3;
+        const int pab = (j == p1) + (j == p2), lab = (j == l1) + (j == l2);
+        const int rp = (p1 >= 0 && p1 < j) + (p2 >= 0 && p2 < j);
+        const int rl = (l1 >= 0 && l1 < j) + (l2 >= 0 && l2 < j);
+        const int kP = 2 - pab - max(rp, rl);
+        const int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
+        const int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
+        const int cap = min(nbP, 2) + 2 * min(nbL, 2);
+        const int wn = nP + 2 * nL + pab + 2 * lab;
         cov += wn; capsum += cap;
-        int fmax = min(6 * (j - a), capsum);
-        int d = 2 * cov - S.c2[j];
+        const int fmax = min(6 * (j - a), capsum);
+        const int d = 2 * cov - (int)(cjw & 0xffff);
         lb += d > 0 ? d : max(0, -d - 2 * fmax);
-        int gmax = cap + min(capsum, 6);
-        int f = wn - S.j2[j];
+        const int gmax = cap + min(capsum, 6);
+        const int f = wn - (int)(cjw >> 16);
         lb += f > 0 ? f : max(0, -f - gmax);
-        if (lb > budget) break;
+        if ((j & 3) == 0 && __ballot_sync(0xffffffffu, active && lb <= budget) == 0) break;
     }
     return lb;
 }
 
-__global__ void __launch_bounds__(WPB * 32)
-k_expand(LevelArgs A)
+// One batch of light-test survivors through the O(n) bound; survivors are queued for the write
+// (EMIT_ALL) or folded into the per-record arg-min (EMIT_BEST).  Returns the new write-queue fill.
+__device__ __noinline__ int heavy_batch(GroupShared &S, const LevelArgs &A, int count, int jtop, int qw)
 {
-    __shared__ uint8_t s_ptab[AMBI_NP_CODES * 2 + 6];
-    __shared__ uint8_t s_ltab[AMBI_NL_CODES * 2 + 6];
-    __shared__ WarpShared s_w[WPB];
-
-    for (int i = threadIdx.x; i < AMBI_NP_CODES * 2; i += blockDim.x) s_ptab[i] = A.ptab[i];
-    for (int i = threadIdx.x; i < AMBI_NL_CODES * 2; i += blockDim.x) s_ltab[i] = A.ltab[i];
-    __syncthreads();
-
     const int lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
-    WarpShared &S = s_w[threadIdx.x >> 5];
+    const int a = A.level;
+    const bool act = lane < count;
+    const uint32_t e = act ? S.qh[lane] : 0u;
+    const int slot = e >> 24;
+    const uint32_t cfg = e & 0xffffffu;
+    int p1, p2, l1, l2; unpack_cfg(cfg, p1, p2, l1, l2);
+    int err = 0, tot = 0; bool keep = false;
+    const int slack = S.slack[slot];
+    if (act) {
+        const int w = (p1 >= 0) + (p2 >= 0) + 2 * ((l1 >= 0) + (l2 >= 0));
+        const uint32_t cja = S.cj[a][slot];
+        err = abs(2 * (S.covC[slot] + w) - (int)(cja & 0xffff)) + abs(S.fbC[slot] + w - (int)(cja >> 16));
+    }
+    const int lb = child_bound(S, slot, jtop, a, p1, p2, l1, l2, slack - err, act);
+    if (act) { tot = err + lb; keep = tot <= slack; }
+    if (A.emit == EMIT_BEST) {
+        if (keep) atomicMin(&S.best[slot], ((unsigned long long)(uint32_t)tot << 32) | cfg_code(S.n[slot], p1, p2, l1, l2));
+        return qw;
+    }
+    const uint32_t km = __ballot_sync(0xffffffffu, keep);
+    if (keep) { const int pos = qw + __popc(km & lt_mask); S.qw_cfg[pos] = e; S.qw_err[pos] = err; S.qw_tot[pos] = tot; }
+    return qw + __popc(km);
+}
+
+// Children are written by one thread each (`count` queued entries from the head of the queue).
+__device__ __noinline__ void write_batch(GroupShared &S, const LevelArgs &A, int count)
+{
+    const int lane = lane_id();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int a = A.level;
+    const bool act = lane < count;
+    uint32_t cfg = 0; int err = 0, tot = 0, slot = 0;
+    if (act) { const uint32_t e = S.qw_cfg[lane]; slot = e >> 24; cfg = e & 0xffffffu; err = S.qw_err[lane]; tot = S.qw_tot[lane]; }
+    int p1, p2, l1, l2; unpack_cfg(cfg, p1, p2, l1, l2);
+    const int n = S.n[slot];
+    bool wr = act;
+    const uint32_t code = cfg_code(n, p1, p2, l1, l2);
+    const uint8_t *prec = A.parents + (size_t)S.pidx[slot] * A.stride;
+    if (A.shard_world > 1 && a == A.shard_level && wr) {
+        const uint32_t *prow = reinterpret_cast<const uint32_t *>(prec + sizeof(NodeHdr));
+        uint32_t h = 0;
+#pragma unroll 1
+        for (int k = 0; k < 32; ++k) {
+            const uint32_t v = k < a ? prow[k] : (k == a ? code : 0u);
+            h ^= mix32(v + 0x9e3779b9u * (uint32_t)(k + 1));
+        }
+        wr = (int)(mix32(h) % (uint32_t)A.shard_world) == A.shard_rank;
+    }
+    const uint32_t wm = __ballot_sync(0xffffffffu, wr);
+    uint32_t cbase = 0;
+    if (lane == 0 && wm) cbase = atomicAdd(A.ccount, (uint32_t)__popc(wm));
+    cbase = __shfl_sync(0xffffffffu, cbase, 0);
+    if (!wr) return;
+    const uint32_t cslot = cbase + __popc(wm & lt_mask);
+    if (cslot >= A.cap) { atomicExch(A.overflow, 1u); return; }
+    uint8_t *crec = A.children + (size_t)cslot * A.stride;
+    reinterpret_cast<uint4 *>(crec)[0] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4 *>(crec)[1] = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+    for (int j = a + 1; j < n; ++j) {
+        const uint32_t cb = S.colb[j][slot];
+        const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = (cb >> 6) & 3;
+        const int pab = (j == p1) + (j == p2), lab = (j == l1) + (j == l2);
+        const int rp = (p1 >= 0 && p1 < j) + (p2 >= 0 && p2 < j);
+        const int rl = (l1 >= 0 && l1 < j) + (l2 >= 0 && l2 < j);
+        const int kP = 2 - pab - max(rp, rl);
+        const int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
+        const int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
+        crec[j] = (uint8_t)((nP + pab) | ((nL + lab) << 2) | (nbP << 4) | (nbL << 6));
+    }
+    const uint32_t tm = S.tmask[slot];
+    int hits = 0;
+    if (tm) hits = (p1 >= 0 && ((tm >> p1) & 1)) + (p2 >= 0 && ((tm >> p2) & 1)) +
+                   (l1 >= 0 && ((tm >> l1) & 1)) + (l2 >= 0 && ((tm >> l2) & 1));
+    const int sc = S.score[slot];
+    // completed assignments all share one (empty) state: drop the running third-generation count
+    reinterpret_cast<int4 *>(crec)[2] = make_int4(sc + err, sc + tot, S.prob[slot], (n == a + 1) ? 0 : S.ptgs[slot] + hits);
+    const uint4 *src = reinterpret_cast<const uint4 *>(prec + sizeof(NodeHdr));
+    uint4 *dst = reinterpret_cast<uint4 *>(crec + sizeof(NodeHdr));
+    const int nq = (A.nmax + 3) >> 2;
+#pragma unroll 1
+    for (int q = 0; q < nq; ++q) {
+        uint4 v = src[q];
+        if ((a >> 2) == q) { const int r = a & 3; if (r == 0) v.x = code; else if (r == 1) v.y = code; else if (r == 2) v.z = code; else v.w = code; }
+        dst[q] = v;
+    }
+}
+
+// Decode candidate number r of record `slot` into a row configuration and run the light test
+// (loop parents row 3, rows 2/4/5 inside the row, third-generation row, exact deviation of segment a).
+// Returns the queue entry (slot<<24 | cfg) or 0 if structurally infeasible; *pass = within the limit.
+__device__ __forceinline__ uint32_t light_test(const GroupShared &S, int a, int slot, uint32_t r, bool *pass)
+{
+    const uint32_t okP = S.okP[slot], okL1 = S.okL1[slot], okL2 = S.okL2[slot];
+    const uint32_t nl0 = S.nl0[slot];
+    int p1 = -1, p2 = -1, l1 = -1, l2 = -1;
+    bool class0 = true;
+    uint32_t li;
+    if (r < nl0) li = r;
+    else {
+        class0 = false;
+        r -= nl0;
+        const uint32_t nlall = S.nlall[slot];
+        uint32_t pi = r / nlall;           // 0-based index among the non-empty pattern sets
+        li = r - pi * nlall;
+        const uint32_t S1 = okP & S.parP[slot];
+        const uint32_t ns = __popc(S1);
+        if (pi < ns) p1 = nth_bit(S1, pi);
+        else {
+            pi -= ns;
+            for (uint32_t m = S1; m; m &= m - 1) {
+                const int hi = __ffs(m) - 1;
+                const uint32_t lows = okP & below(hi);
+                const uint32_t k = __popc(lows);
+                if (pi < k) { p2 = hi; p1 = nth_bit(lows, pi); break; }
+                pi -= k;
+            }
+        }
+    }
+    if (li > 0) {
+        --li;
+        // class 0 enumerates only multisets whose loop parents already exist; otherwise every
+        // multiset within the column budgets (parents may come from the pattern ends of this row)
+        const uint32_t M1 = class0 ? (okL1 & S.par1[slot]) : okL1;
+        const uint32_t M2 = class0 ? (okL2 & S.par2[slot]) : okL2;
+        const uint32_t n1 = __popc(M1), n2 = __popc(M2);
+        if (li < n1) l1 = nth_bit(M1, li);
+        else if (li < n1 + n2) l1 = l2 = nth_bit(M2, li - n1);
+        else {
+            li -= n1 + n2;                 // pairs: high end in M1, low end any budgeted column below it
+            for (uint32_t m = M1; m; m &= m - 1) {
+                const int hi = __ffs(m) - 1;
+                const uint32_t lows = okL1 & below(hi);
+                const uint32_t k = __popc(lows);
+                if (li < k) { l2 = hi; l1 = nth_bit(lows, li); break; }
+                li -= k;
+            }
+        }
+    }
+    bool feas = true;
+    const int nl = (l1 >= 0) + (l2 >= 0);
+    const int lhi = l2 >= 0 ? l2 : l1;
+    if (!class0 && nl) {
+        const int need = (l2 == l1) ? 2 : 1;
+        const uint32_t cbh = S.colb[lhi][slot];
+        const bool root = (a == 0 && lhi == (int)S.n[slot] - 1);
+        const int par = (int)(cbh & 3) + (int)((cbh >> 2) & 3) + (p1 > lhi) + (p2 > lhi);
+        feas = root || par >= need;
+    }
+    const int pmax = p2 >= 0 ? p2 : p1;
+    if (nl == 2 && pmax > lhi) feas = false;     // a pattern end right of both loop entries
+    const uint32_t tm = S.tmask[slot];
+    if (feas && tm) {
+        const int hits = (p1 >= 0 && ((tm >> p1) & 1)) + (p2 >= 0 && ((tm >> p2) & 1)) +
+                         (l1 >= 0 && ((tm >> l1) & 1)) + (l2 >= 0 && ((tm >> l2) & 1));
+        if (S.ptgs[slot] + hits > 5) feas = false;
+    }
+    if (!feas) { *pass = false; return 0u; }
+    const int w = (p1 >= 0) + (p2 >= 0) + 2 * nl;
+    const uint32_t cja = S.cj[a][slot];
+    const int err = abs(2 * (S.covC[slot] + w) - (int)(cja & 0xffff)) + abs(S.fbC[slot] + w - (int)(cja >> 16));
+    *pass = err <= S.slack[slot];
+    return ((uint32_t)slot << 24) | pack_cfg(p1, p2, l1, l2);
+}
+
+__global__ void __launch_bounds__(WPB * 32)
+k_expand(LevelArgs A_param)
+{
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ LevelArgs s_args;            // the stage functions take the arguments by reference
+    if (threadIdx.x == 0) s_args = A_param;
+    __syncthreads();
+    const LevelArgs &A = s_args;
+    GroupShared &S = reinterpret_cast<GroupShared *>(s_raw)[threadIdx.x >> 5];
+    const int lane = lane_id();
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const int a = A.level;
     const uint32_t pcount = *A.pcount;
+    // records per warp group: spread a small frontier over all resident warps
+    const uint32_t nwarps = gridDim.x * WPB;
+    const uint32_t grp_n = min((uint32_t)GRP, max(1u, (pcount + 4 * nwarps - 1) / (4 * nwarps)));   // >= 4 groups per warp when possible
 
     for (;;) {
-        uint32_t wi = 0;
-        if (lane == 0) wi = atomicAdd(A.work_counter, 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= pcount) break;
-
-        const uint32_t pidx = A.plist[wi];
-        const uint8_t *prec = A.parents + (size_t)pidx * A.stride;
-        const NodeHdr *ph = reinterpret_cast<const NodeHdr *>(prec);
-        const uint32_t *prow = reinterpret_cast<const uint32_t *>(prec + sizeof(NodeHdr));
-        const int score = ph->score, prob = ph->prob, ptgs = ph->tgs;
-        const DevProblem &P = A.probs[prob];
-        const int n = P.n;
-        const int slack = A.limit[prob] - score;
-        if (n <= a || slack < 0) continue;
-        const int lmax = P.lmax;
-        const uint32_t tmask = P.has_tgs ? P.tgs_mask[a] : 0u;
-
-        // ---- stage the parent's column state in shared memory (lane j = column j)
-        const uint32_t cb = ph->col[lane];
-        const bool incol = lane >= a && lane < n;
-        const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = (cb >> 6) & 3;
-        const int wj = incol ? nP + 2 * nL : 0;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(A.work_counter, grp_n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= pcount) break;
         __syncwarp();
-        S.col[lane] = incol ? (uint32_t)(wj | (bP << 8) | (bL << 16) | ((nP + nL) << 24)) : 0u;
-        S.c2[lane] = lane < n ? P.c2[lane] : 0;
-        S.j2[lane] = lane < n ? P.j2[lane] : 0;
-        int covC = wj;
+
+        // ---- phase 1: lane = record slot; stage column state and problem data, count candidates
+        const bool have = (uint32_t)lane < grp_n && base + lane < pcount;
+        const uint8_t *prec = nullptr;
+        const DevProblem *P = nullptr;
+        int my_n = 0, slack = -1, lmax = 0;
+        S.best[lane] = ~0ull; S.cnt[lane] = 0;
+        if (have) {
+            const uint32_t pidx = A.plist[base + lane];
+            prec = A.parents + (size_t)pidx * A.stride;
+            const int4 hd = reinterpret_cast<const int4 *>(prec)[2];       // score, f, prob, tgs
+            P = &A.probs[hd.z];
+            my_n = P->n; lmax = P->lmax;
+            slack = A.limit[hd.z] - hd.x;
+            S.pidx[lane] = pidx; S.score[lane] = hd.x; S.prob[lane] = hd.z; S.ptgs[lane] = hd.w;
+            S.slack[lane] = slack; S.n[lane] = (uint8_t)my_n;
+            S.tmask[lane] = P->has_tgs ? P->tgs_mask[a] : 0u;
+        }
+        int jtop = my_n;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) covC += __shfl_xor_sync(0xffffffffu, covC, o);
-        const int fbC = __shfl_sync(0xffffffffu, wj, a);
-        const bool rootcol = (a == 0 && lane == n - 1);
-        const uint32_t okP = __ballot_sync(0xffffffffu, incol && bP >= 1);
-        const uint32_t parP = __ballot_sync(0xffffffffu, incol && (nP >= 1 || rootcol));
-        const uint32_t okL1 = __ballot_sync(0xffffffffu, incol && bL >= 1 && lmax >= 1);
-        const uint32_t okL2 = __ballot_sync(0xffffffffu, incol && bL >= 2 && lmax >= 2);
-        __syncwarp();
-
-        const int m = n - a;
-        // ---- feasible pattern sets (column budget, parent row ①)
-        int npl = 0;
-        {
-            const int NPm = ambi_np_for(m);
-            for (int base = 0; base < NPm; base += 32) {
-                int ip = base + lane;
-                bool ok = false;
-                if (ip < NPm) {
-                    if (ip == 0) ok = true;
-                    else {
-                        int q1 = s_ptab[2 * ip], q2 = s_ptab[2 * ip + 1];
-                        int b1 = n - 1 - q1;
-                        if (q2 == AMBI_NONE) ok = ((okP >> b1) & 1) && ((parP >> b1) & 1);
-                        else { int b2 = n - 1 - q2; ok = ((okP >> b1) & 1) && ((okP >> b2) & 1) && ((parP >> b2) & 1); }
-                    }
-                }
-                uint32_t bal = __ballot_sync(0xffffffffu, ok);
-                if (ok) S.pl[npl + __popc(bal & lt_mask)] = (uint16_t)ip;
-                npl += __popc(bal);
+        for (int o = 16; o; o >>= 1) jtop = max(jtop, __shfl_xor_sync(0xffffffffu, jtop, o));
+        uint32_t okP = 0, parP = 0, okL1 = 0, okL2 = 0, par1 = 0, par2 = 0;
+        int covC = 0, fbC = 0;
+#pragma unroll 1
+        for (int j = a; j < jtop; ++j) {
+            uint32_t b = 0, cjv = 0;
+            if (have && j < my_n) { b = prec[j]; cjv = P->cj[j]; }
+            S.colb[j][lane] = (uint8_t)b;
+            S.cj[j][lane] = cjv;
+            const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
+            if (have && j < my_n) {
+                const bool root = (a == 0 && j == my_n - 1);
+                covC += nP + 2 * nL;
+                if (j == a) fbC = nP + 2 * nL;
+                okP |= (uint32_t)(bP >= 1) << j;
+                parP |= (uint32_t)(nP >= 1 || root) << j;
+                okL1 |= (uint32_t)(bL >= 1 && lmax >= 1) << j;
+                okL2 |= (uint32_t)(bL >= 2 && lmax >= 2) << j;
+                par1 |= (uint32_t)(nP + nL >= 1 || root) << j;
+                par2 |= (uint32_t)(nP + nL >= 2 || root) << j;
             }
         }
-        // ---- feasible loop multisets (column budget); class 0 = parent row ③ already
-        //      satisfied by earlier rows, class 1 = needs pattern ends to its right
-        int nl0 = 0, nll = 0;
-        {
-            const int NLm = ambi_nl_for(m);
-            for (int cls = 0; cls < 2; ++cls) {
-                for (int base = 0; base < NLm; base += 32) {
-                    int il = base + lane;
-                    bool ok = false;
-                    if (il < NLm) {
-                        if (il == 0) ok = (cls == 0);
-                        else {
-                            int q1 = s_ltab[2 * il], q2 = s_ltab[2 * il + 1];
-                            int l1 = n - 1 - q1, hi, need;
-                            bool bud;
-                            if (q2 == AMBI_NONE) { hi = l1; need = 1; bud = (okL1 >> l1) & 1; }
-                            else if (q2 == q1) { hi = l1; need = 2; bud = (okL2 >> l1) & 1; }
-                            else { hi = n - 1 - q2; need = 1; bud = ((okL1 >> l1) & 1) && ((okL1 >> hi) & 1); }
-                            int par = (S.col[hi] >> 24);
-                            bool c0 = (a == 0 && hi == n - 1) || par >= need;
-                            ok = bud && (c0 == (cls == 0));
-                        }
-                    }
-                    uint32_t bal = __ballot_sync(0xffffffffu, ok);
-                    if (ok) S.ll[nll + __popc(bal & lt_mask)] = (uint16_t)il;
-                    nll += __popc(bal);
-                }
-                if (cls == 0) nl0 = nll;
-            }
+        uint32_t total = 0;
+        if (have && my_n > a && slack >= 0) {
+            // pattern sets: {} + singles in S1 + pairs (hi in S1, lo any okP column below hi)
+            const uint32_t S1 = okP & parP;
+            uint32_t nps = 1 + __popc(S1);
+            for (uint32_t m = S1; m; m &= m - 1) nps += __popc(okP & below(__ffs(m) - 1));
+            // loop multisets whose parents already exist (class 0)
+            const uint32_t A1 = okL1 & par1, A2 = okL2 & par2;
+            uint32_t nl0 = 1 + __popc(A1) + __popc(A2);
+            for (uint32_t m = A1; m; m &= m - 1) nl0 += __popc(okL1 & below(__ffs(m) - 1));
+            // every multiset within budget: singles, doubles, pairs
+            uint32_t nlall = 1 + __popc(okL1) + __popc(okL2);
+            for (uint32_t m = okL1; m; m &= m - 1) nlall += __popc(okL1 & below(__ffs(m) - 1));
+            S.nl0[lane] = nl0; S.nlall[lane] = nlall;
+            total = nl0 + (nps - 1) * nlall;
         }
+        S.okP[lane] = okP; S.parP[lane] = parP; S.okL1[lane] = okL1; S.okL2[lane] = okL2;
+        S.par1[lane] = par1; S.par2[lane] = par2; S.covC[lane] = covC; S.fbC[lane] = fbC;
+        // exclusive prefix of candidate counts
+        uint32_t incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        S.cstart[lane + 1] = incl;
+        if (lane == 0) S.cstart[0] = 0;
+        const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
         __syncwarp();
 
-        // ---- enumerate the product, light test per lane, heavy test from a queue
-        int qn = 0;                       // queue fill (warp-uniform)
-        unsigned long long ncand = 0;     // per-lane count
-
-        auto heavy = [&](uint32_t code, bool active) {
-            // code = ip<<10 | il ; all lanes call, inactive lanes idle
-            int p1 = -1, p2 = -1, l1 = -1, l2 = -1, err = 0, tot = 0;
-            bool keep = false;
-            if (active) {
-                int ip = code >> 10, il = code & 1023;
-                if (ip) { int q1 = s_ptab[2 * ip], q2 = s_ptab[2 * ip + 1];
-                          p1 = n - 1 - q1; if (q2 != AMBI_NONE) p2 = n - 1 - q2; }
-                if (il) { int q1 = s_ltab[2 * il], q2 = s_ltab[2 * il + 1];
-                          l1 = n - 1 - q1; if (q2 != AMBI_NONE) l2 = n - 1 - q2; }
-                int w = (p1 >= 0) + (p2 >= 0) + 2 * ((l1 >= 0) + (l2 >= 0));
-                err = abs(2 * (covC + w) - S.c2[a]) + abs(fbC + w - S.j2[a]);
-                int lb = child_bound(S, n, a, p1, p2, l1, l2, slack - err);
-                tot = err + lb;
-                keep = tot <= slack;
-            }
-            // ---- survivors are written one at a time by the whole warp
-            uint32_t km = __ballot_sync(0xffffffffu, keep);
-            while (km) {
-                int src = __ffs(km) - 1; km &= km - 1;
-                uint32_t ccode = __shfl_sync(0xffffffffu, code, src);
-                int cp1 = __shfl_sync(0xffffffffu, p1, src), cp2 = __shfl_sync(0xffffffffu, p2, src);
-                int cl1 = __shfl_sync(0xffffffffu, l1, src), cl2 = __shfl_sync(0xffffffffu, l2, src);
-                int cerr = __shfl_sync(0xffffffffu, err, src), ctot = __shfl_sync(0xffffffffu, tot, src);
-                // prefix value for this lane (row code of row `lane`)
-                uint32_t myrow = lane < a ? prow[lane] : (lane == a ? ccode : 0u);
-                if (A.shard_world > 1 && a == A.shard_level) {
-                    uint32_t h = mix32(myrow + 0x9e3779b9u * (lane + 1));
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, o);
-                    if ((int)(mix32(h) % (uint32_t)A.shard_world) != A.shard_rank) continue;
-                }
-                uint32_t slot = 0;
-                if (lane == 0) slot = atomicAdd(A.ccount, 1u);
-                slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (slot >= A.cap) { if (lane == 0) atomicExch(A.overflow, 1u); continue; }
-                uint8_t *crec = A.children + (size_t)slot * A.stride;
-                // column byte of lane's column
-                uint32_t nb = 0;
-                if (lane > a && lane < n) {
-                    int j = lane;
-                    int pab = (j == cp1) + (j == cp2), lab = (j == cl1) + (j == cl2);
-                    int rp = (cp1 >= 0 && cp1 < j) + (cp2 >= 0 && cp2 < j);
-                    int rl = (cl1 >= 0 && cl1 < j) + (cl2 >= 0 && cl2 < j);
-                    int kP = 2 - pab - max(rp, rl);
-                    int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
-                    int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
-                    nb = (uint32_t)((nP + pab) | ((nL + lab) << 2) | (nbP << 4) | (nbL << 6));
-                }
-                crec[lane] = (uint8_t)nb;
-                if (lane == 0) {
-                    NodeHdr *ch = reinterpret_cast<NodeHdr *>(crec);
-                    int hits = 0;
-                    if (tmask) hits = (cp1 >= 0 && ((tmask >> cp1) & 1)) + (cp2 >= 0 && ((tmask >> cp2) & 1)) +
-                                      (cl1 >= 0 && ((tmask >> cl1) & 1)) + (cl2 >= 0 && ((tmask >> cl2) & 1));
-                    ch->score = score + cerr; ch->f = score + ctot; ch->prob = prob; ch->tgs = ptgs + hits;
-                }
-                uint32_t *crow = reinterpret_cast<uint32_t *>(crec + sizeof(NodeHdr));
-                if (lane < A.nmax) crow[lane] = myrow;
-            }
-        };
-
-        for (int pi = 0; pi < npl; ++pi) {
-            const int ip = S.pl[pi];
-            int p1 = -1, p2 = -1;
-            if (ip) { int q1 = s_ptab[2 * ip], q2 = s_ptab[2 * ip + 1];
-                      p1 = n - 1 - q1; if (q2 != AMBI_NONE) p2 = n - 1 - q2; }
-            const int pmax = p2 >= 0 ? p2 : p1;           // highest pattern end
-            const int np = (p1 >= 0) + (p2 >= 0);
-            const int range = ip ? nll : nl0;
-            const int phits = tmask ? ((p1 >= 0 && ((tmask >> p1) & 1)) + (p2 >= 0 && ((tmask >> p2) & 1))) : 0;
-            for (int base = 0; base < range; base += 32) {
-                const int li = base + lane;
-                bool pass = false;
-                uint32_t code = 0;
-                if (li < range) {
-                    const int il = S.ll[li];
-                    int l1 = -1, l2 = -1;            // l1 = lowest column, l2 = highest (or == l1 for mult 2)
-                    if (il) { int q1 = s_ltab[2 * il], q2 = s_ltab[2 * il + 1];
-                              l1 = n - 1 - q1; if (q2 != AMBI_NONE) l2 = n - 1 - q2; }
-                    bool feas = true;
-                    if (li >= nl0) {                 // class 1: parents must come from pattern ends to the right
-                        int hi = l2 >= 0 ? l2 : l1;
-                        int need = (l2 == l1) ? 2 : 1;
-                        int par = (int)(S.col[hi] >> 24) + (p1 > hi) + (p2 > hi);
-                        feas = par >= need;
-                    }
-                    // rows ②④⑤ inside the row: a pattern end strictly right of both loop entries
-                    const int nl = (l1 >= 0) + (l2 >= 0);
-                    const int lhi = l2 >= 0 ? l2 : l1;
-                    if (nl == 2 && pmax > lhi) feas = false;
-                    if (feas && tmask) {
-                        int hits = phits + (l1 >= 0 && ((tmask >> l1) & 1)) + (l2 >= 0 && ((tmask >> l2) & 1));
-                        if (ptgs + hits > 5) feas = false;
-                    }
-                    if (feas) {
-                        ++ncand;
-                        int w = np + 2 * nl;
-                        int err = abs(2 * (covC + w) - S.c2[a]) + abs(fbC + w - S.j2[a]);
-                        pass = err <= slack;
-                        code = ((uint32_t)ip << 10) | (uint32_t)il;
-                    }
-                }
-                uint32_t bal = __ballot_sync(0xffffffffu, pass);
-                if (pass) S.queue[qn + __popc(bal & lt_mask)] = code;
-                qn += __popc(bal);
+        // ---- phase 2: lane = candidate (flattened over the group's records); three stages fed
+        //      through two shared-memory queues so that each stage runs with full lanes
+        int qh = 0, qw = 0;                 // queue fills (warp-uniform)
+        uint32_t cb0 = 0;
+        for (;;) {
+            if (qw >= 32 || (cb0 >= T && qh == 0 && qw > 0)) {
+                const int cnt = min(qw, 32);
+                write_batch(S, A, cnt);
                 __syncwarp();
-                if (qn >= 32) {
-                    uint32_t c = S.queue[lane];
-                    __syncwarp();
-                    heavy(c, true);
-                    qn -= 32;
-                    uint32_t mv = (lane < qn) ? S.queue[32 + lane] : 0u;
-                    __syncwarp();
-                    if (lane < qn) S.queue[lane] = mv;
-                    __syncwarp();
-                }
+                qw -= cnt;
+                uint32_t m0 = 0; int m1 = 0, m2 = 0;
+                if (lane < qw) { m0 = S.qw_cfg[32 + lane]; m1 = S.qw_err[32 + lane]; m2 = S.qw_tot[32 + lane]; }
+                __syncwarp();
+                if (lane < qw) { S.qw_cfg[lane] = m0; S.qw_err[lane] = m1; S.qw_tot[lane] = m2; }
+                __syncwarp();
+                continue;
             }
-        }
-        if (qn > 0) {
-            uint32_t c = lane < qn ? S.queue[lane] : 0u;
-            __syncwarp();
-            heavy(c, lane < qn);
-        }
-        // ---- statistics
+            if (qh >= 32 || (cb0 >= T && qh > 0)) {
+                const int cnt = min(qh, 32);
+                qw = heavy_batch(S, A, cnt, jtop, qw);
+                __syncwarp();
+                qh -= cnt;
+                const uint32_t mv = lane < qh ? S.qh[32 + lane] : 0u;
+                __syncwarp();
+                if (lane < qh) S.qh[lane] = mv;
+                __syncwarp();
+                continue;
+            }
+            if (cb0 >= T) break;
+            const uint32_t c = cb0 + lane;
+            cb0 += 32;
+            bool pass = false;
+            uint32_t entry = 0;
+            if (c < T) {
+                int slot = 0;                // owning record: largest slot with cstart[slot] <= c
 #pragma unroll
-        for (int o = 16; o; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
-        if (lane == 0) {
-            atomicAdd(&A.cand_count[prob], ncand);
-            atomicAdd(&A.node_count[prob], 1ull);
+                for (int o = 16; o; o >>= 1) if (S.cstart[slot + o] <= c) slot += o;
+                entry = light_test(S, a, slot, c - S.cstart[slot], &pass);
+            }
+            {   // candidates scored, per record (lanes of one record are contiguous)
+                const int key = entry ? (int)(entry >> 24) : -1;
+                const uint32_t grp = __match_any_sync(0xffffffffu, key);
+                if (key >= 0 && (grp & lt_mask) == 0) S.cnt[key] += __popc(grp);
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+            if (pass) S.qh[qh + __popc(bal & lt_mask)] = entry;
+            qh += __popc(bal);
+            __syncwarp();
+        }
+        if (A.emit == EMIT_BEST) {
+            // every record emits its arg-min child (tot, then search order)
+            __syncwarp();
+            const unsigned long long bk = S.best[lane];
+            const bool has = bk != ~0ull;
+            const uint32_t hm = __ballot_sync(0xffffffffu, has);
+            if (has) {
+                const int n = S.n[lane];
+                const uint32_t code = (uint32_t)bk;       // recover the configuration from its search-order code
+                const int ip = code >> 10, il = code & 1023;
+                int p1 = -1, p2 = -1, l1 = -1, l2 = -1;
+                if (ip) { int q1 = 0; while (ambi_ip_code(q1 + 1, -1) <= ip) ++q1; const int off = ip - ambi_ip_code(q1, -1);
+                          p1 = n - 1 - q1; if (off > 0) p2 = n - 1 - (off - 1); }
+                if (il) { int q1 = 0; while (ambi_il_code(q1 + 1, -1) <= il) ++q1; const int off = il - ambi_il_code(q1, -1);
+                          l1 = n - 1 - q1; if (off > 0) l2 = (off - 1 == q1) ? l1 : n - 1 - (off - 1); }
+                const int tot = (int)(bk >> 32);
+                const int w = (p1 >= 0) + (p2 >= 0) + 2 * ((l1 >= 0) + (l2 >= 0));
+                const uint32_t cja = S.cj[a][lane];
+                const int err = abs(2 * (S.covC[lane] + w) - (int)(cja & 0xffff)) + abs(S.fbC[lane] + w - (int)(cja >> 16));
+                const int pos = __popc(hm & lt_mask);
+                S.qw_cfg[pos] = ((uint32_t)lane << 24) | pack_cfg(p1, p2, l1, l2); S.qw_err[pos] = err; S.qw_tot[pos] = tot;
+            }
+            __syncwarp();
+            if (hm) { write_batch(S, A, __popc(hm)); __syncwarp(); }
+        }
+        // ---- statistics (per problem of each record)
+        __syncwarp();
+        if (have && S.cstart[lane + 1] - S.cstart[lane] > 0) {
+            atomicAdd(&A.cand_count[S.prob[lane]], (unsigned long long)S.cnt[lane]);
+            atomicAdd(&A.node_count[S.prob[lane]], 1ull);
         }
         __syncwarp();
     }
@@ -347,21 +492,31 @@ k_expand(LevelArgs A)
 
 // ---------------------------------------------------------------------------
 // K3a: merge records that reached the same column state.
+// A dropped record is flagged in its own header (bit 31 of the tgs word), so no
+// per-level flag array has to be cleared.
 // ---------------------------------------------------------------------------
+constexpr uint32_t DEAD_BIT = 0x80000000u;
+
 struct DedupArgs {
     uint8_t *recs;
     const uint32_t *count;
     uint32_t cap;
     unsigned long long *table;
     uint32_t tmask;
-    uint32_t gen;
-    uint8_t *dead;
+    const uint32_t *gen_base;   // bumped once per run, so a replayed graph never sees stale slots
+    uint32_t gen_off;
     int stride;
     int level;          // rows 0..level are fixed in these records
 };
 
+__device__ __forceinline__ uint32_t hdr_tgs(const NodeHdr *h) {
+    return *reinterpret_cast<const volatile uint32_t *>(&h->tgs) & ~DEAD_BIT;
+}
+__device__ __forceinline__ bool hdr_dead(const NodeHdr *h) { return (uint32_t)h->tgs & DEAD_BIT; }
+__device__ __forceinline__ void hdr_kill(NodeHdr *h) { atomicOr(reinterpret_cast<unsigned int *>(&h->tgs), DEAD_BIT); }
+
 __device__ __forceinline__ bool same_state(const NodeHdr *x, const NodeHdr *y) {
-    if (x->prob != y->prob || x->tgs != y->tgs) return false;
+    if (x->prob != y->prob || hdr_tgs(x) != hdr_tgs(y)) return false;
     const uint4 *a = reinterpret_cast<const uint4 *>(x->col), *b = reinterpret_cast<const uint4 *>(y->col);
     uint4 a0 = a[0], b0 = b[0], a1 = a[1], b1 = b[1];
     return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w &&
@@ -381,30 +536,31 @@ __device__ __forceinline__ bool rec_better(const uint8_t *x, const uint8_t *y, i
 __global__ void k_dedup(DedupArgs A)
 {
     uint32_t cnt = min(*A.count, A.cap);
+    const uint32_t gen = *A.gen_base + A.gen_off;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const uint8_t *rec = A.recs + (size_t)i * A.stride;
-        const NodeHdr *h = reinterpret_cast<const NodeHdr *>(rec);
+        uint8_t *rec = A.recs + (size_t)i * A.stride;
+        NodeHdr *h = reinterpret_cast<NodeHdr *>(rec);
         const uint32_t *cw = reinterpret_cast<const uint32_t *>(h->col);
-        uint32_t hv = mix32((uint32_t)h->prob * 0x9e3779b9u + (uint32_t)h->tgs);
+        uint32_t hv = mix32((uint32_t)h->prob * 0x9e3779b9u + hdr_tgs(h));
 #pragma unroll
         for (int k = 0; k < 8; ++k) hv = mix32(hv ^ cw[k]) + 0x85ebca6bu * (k + 1);
         uint32_t slot = hv & A.tmask;
-        const unsigned long long mine = ((unsigned long long)A.gen << 32) | i;
+        const unsigned long long mine = ((unsigned long long)gen << 32) | i;
         for (;;) {
             unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&A.table[slot]);
-            if ((uint32_t)(cur >> 32) != A.gen) {
+            if ((uint32_t)(cur >> 32) != gen) {
                 unsigned long long old = atomicCAS(&A.table[slot], cur, mine);
                 if (old == cur) break;
                 continue;                              // re-read the same slot
             }
             uint32_t o = (uint32_t)cur;
-            const uint8_t *orec = A.recs + (size_t)o * A.stride;
+            uint8_t *orec = A.recs + (size_t)o * A.stride;
             if (same_state(h, reinterpret_cast<const NodeHdr *>(orec))) {
                 if (rec_better(rec, orec, A.level + 1)) {
                     unsigned long long old = atomicCAS(&A.table[slot], cur, mine);
-                    if (old == cur) { A.dead[o] = 1; break; }
+                    if (old == cur) { hdr_kill(reinterpret_cast<NodeHdr *>(orec)); break; }
                     continue;
-                } else { A.dead[i] = 1; break; }
+                } else { hdr_kill(h); break; }
             }
             slot = (slot + 1) & A.tmask;
         }
@@ -419,12 +575,11 @@ struct FinalizeArgs {
     const uint8_t *recs;
     const uint32_t *count;
     uint32_t cap;
-    const uint8_t *dead;
     uint32_t *next_list;
     uint32_t *next_count;
     int32_t *best_score;        // [prob]
     uint32_t *best_rows;        // [prob][AMBI_MAXN]
-    int32_t *fmin;              // beam: per-problem min f (or nullptr)
+    int32_t *fmin;              // beam: per-problem min f of this level (or nullptr)
     int stride;
     int level;
 };
@@ -433,9 +588,9 @@ __global__ void k_finalize(FinalizeArgs A)
 {
     uint32_t cnt = min(*A.count, A.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        if (A.dead[i]) continue;
         const uint8_t *rec = A.recs + (size_t)i * A.stride;
         const NodeHdr *h = reinterpret_cast<const NodeHdr *>(rec);
+        if (hdr_dead(h)) continue;
         const int n = A.probs[h->prob].n;
         if (n == A.level + 1) {
             // all completed assignments of a problem share the empty column state, so the
@@ -459,7 +614,6 @@ struct BeamArgs {
     const uint8_t *recs;
     const uint32_t *count;
     uint32_t cap;
-    const uint8_t *dead;
     const int32_t *fmin;
     uint32_t *hist;             // [prob][BEAM_BINS]
     uint32_t *ticket;           // [prob]
@@ -474,9 +628,8 @@ __global__ void k_beam_hist(BeamArgs A)
 {
     uint32_t cnt = min(*A.count, A.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        if (A.dead[i]) continue;
         const NodeHdr *h = reinterpret_cast<const NodeHdr *>(A.recs + (size_t)i * A.stride);
-        if (A.probs[h->prob].n == A.level + 1) continue;
+        if (hdr_dead(h) || A.probs[h->prob].n == A.level + 1) continue;
         int bin = min(h->f - A.fmin[h->prob], BEAM_BINS - 1);
         atomicAdd(&A.hist[(size_t)h->prob * BEAM_BINS + bin], 1u);
     }
@@ -486,9 +639,8 @@ __global__ void k_beam_select(BeamArgs A)
 {
     uint32_t cnt = min(*A.count, A.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        if (A.dead[i]) continue;
         const NodeHdr *h = reinterpret_cast<const NodeHdr *>(A.recs + (size_t)i * A.stride);
-        if (A.probs[h->prob].n == A.level + 1) continue;
+        if (hdr_dead(h) || A.probs[h->prob].n == A.level + 1) continue;
         int bin = min(h->f - A.fmin[h->prob], BEAM_BINS - 1);
         const uint32_t *hs = A.hist + (size_t)h->prob * BEAM_BINS;
         uint32_t below = 0;
@@ -541,12 +693,14 @@ __global__ void k_solve_n1(const DevProblem *probs, int count, int32_t *best_sco
     cand_count[p] += 2ull * (unsigned long long)(P.loop_ub + 1);
 }
 
+__global__ void k_bump_gen(uint32_t *gen) { *gen += 128u; }
+
 __global__ void k_set_limit(const DevProblem *probs, int count, int32_t *limit, const int32_t *best_score,
                             int32_t *incumbent)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= count) return;
-    int z = probs[p].zero_score, b = best_score[p];
+    int z = limit[p], b = best_score[p];       // limit starts at the all-zero score (k_init_roots)
     int l = b < z ? b : z;
     limit[p] = l; incumbent[p] = l;
 }
@@ -559,19 +713,23 @@ __global__ void k_set_limit(const DevProblem *probs, int count, int32_t *limit, 
 
 static uint32_t next_pow2(uint64_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
+// device counters: one set per level so that a whole pass needs a single clear
+enum { CTR_OVERFLOW = 0, CTR_GEN = 1, CTR_WORK = 8, CTR_CHILD = 8 + 40, CTR_FRONT = 8 + 80, CTR_TOTAL = 8 + 128 };
+
 StageA::StageA() { err_[0] = 0; }
 StageA::~StageA() { release(); }
 
 void StageA::release()
 {
-    cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]); cudaFree(dead_);
-    cudaFree(table_); cudaFree(counters_); cudaFree(ptab_); cudaFree(ltab_);
-    buf_[0] = buf_[1] = nullptr; list_[0] = list_[1] = nullptr; dead_ = nullptr; table_ = nullptr;
-    counters_ = nullptr; ptab_ = ltab_ = nullptr;
+    cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]);
+    cudaFree(table_); cudaFree(counters_);
+    buf_[0] = buf_[1] = nullptr; list_[0] = list_[1] = nullptr; table_ = nullptr;
+    counters_ = nullptr;
     free_problem_arrays();
     for (int i = 0; i < 4; ++i) if (ev_[i]) { cudaEventDestroy(ev_[i]); ev_[i] = nullptr; }
     for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
     prof_ev_.clear();
+    if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
 }
 
 void StageA::free_problem_arrays()
@@ -587,35 +745,41 @@ void StageA::free_problem_arrays()
 int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int rank, int world, int shard_level)
 {
     stream_ = stream;
-    cap_ = node_capacity > 0 ? (uint32_t)std::min<int64_t>(node_capacity, 1ll << 30) : (4u << 20);
-    beam_ = beam_width > 0 ? beam_width : 64;
-    rank_ = rank; world_ = world > 0 ? world : 1; shard_level_ = shard_level;
     stride_ = (int)ambi_node_stride(AMBI_MAXN);
-    CK(cudaMalloc(&buf_[0], (size_t)cap_ * stride_));
-    CK(cudaMalloc(&buf_[1], (size_t)cap_ * stride_));
-    CK(cudaMalloc(&list_[0], (size_t)cap_ * 4));
-    CK(cudaMalloc(&list_[1], (size_t)cap_ * 4));
-    CK(cudaMalloc(&dead_, (size_t)cap_));
-    tsize_ = next_pow2((uint64_t)cap_ * 2);
+    if (node_capacity > 0) cap_base_ = (uint32_t)std::min<int64_t>(node_capacity, 1ll << 28);
+    else {
+        // size the two candidate buffers for the 180 GB part: a fifth of what is free, at most 64 M records each
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        uint64_t recs = (free_b / 5) / (2ull * stride_ + 64);
+        cap_base_ = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(recs, 64ull << 20));
+    }
+    cap_ = cap_base_;
+    beam_ = beam_width > 0 ? beam_width : 16;
+    if (const char *e = getenv("AMBI_BEAM_WIDTH")) { int v = atoi(e); if (v > 0) beam_ = v; }   // tuning knob; results do not depend on it
+    rank_ = rank; world_ = world > 0 ? world : 1; shard_level_ = shard_level;
+    // buffers are sized in bytes for the widest record (n = 32); narrower batches fit more records
+    buf_bytes_ = (size_t)cap_base_ * stride_;
+    cap_max_ = (uint32_t)std::min<uint64_t>(2ull * cap_base_, buf_bytes_ / ambi_node_stride(2));
+    CK(cudaMalloc(&buf_[0], buf_bytes_));
+    CK(cudaMalloc(&buf_[1], buf_bytes_));
+    CK(cudaMalloc(&list_[0], (size_t)cap_max_ * 4));
+    CK(cudaMalloc(&list_[1], (size_t)cap_max_ * 4));
+    tsize_ = next_pow2((uint64_t)cap_max_ * 2);
     CK(cudaMalloc(&table_, (size_t)tsize_ * 8));
     CK(cudaMemsetAsync(table_, 0, (size_t)tsize_ * 8, stream_));
-    CK(cudaMalloc(&counters_, 64 * sizeof(uint32_t)));
-    // decode tables
-    std::vector<uint8_t> pt(AMBI_NP_CODES * 2, AMBI_NONE), lt(AMBI_NL_CODES * 2, AMBI_NONE);
-    for (int q1 = 0; q1 < AMBI_MAXN; ++q1) {
-        int ip = ambi_ip_code(q1, -1); pt[2 * ip] = q1; pt[2 * ip + 1] = AMBI_NONE;
-        for (int q2 = 0; q2 < q1; ++q2) { ip = ambi_ip_code(q1, q2); pt[2 * ip] = q1; pt[2 * ip + 1] = q2; }
-        int il = ambi_il_code(q1, -1); lt[2 * il] = q1; lt[2 * il + 1] = AMBI_NONE;
-        for (int q2 = 0; q2 <= q1; ++q2) { il = ambi_il_code(q1, q2); lt[2 * il] = q1; lt[2 * il + 1] = q2; }
-    }
-    CK(cudaMalloc(&ptab_, pt.size())); CK(cudaMalloc(&ltab_, lt.size()));
-    CK(cudaMemcpyAsync(ptab_, pt.data(), pt.size(), cudaMemcpyHostToDevice, stream_));
-    CK(cudaMemcpyAsync(ltab_, lt.data(), lt.size(), cudaMemcpyHostToDevice, stream_));
+    CK(cudaMalloc(&counters_, CTR_TOTAL * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(counters_, 0, CTR_TOTAL * sizeof(uint32_t), stream_));
     CK(cudaStreamSynchronize(stream_));
     for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&ev_[i]));
     int dev = 0; CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev));
     gen_ = 1;
+    expand_smem_ = sizeof(GroupShared) * WPB;
+    CK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand, WPB * 32, expand_smem_));
+    expand_blocks_ = sms_ * (per_sm > 0 ? per_sm : 1);
     return 0;
 }
 
@@ -629,8 +793,9 @@ int StageA::ensure_problem_arrays(int count)
     CK(cudaMalloc(&d_best_score_, (size_t)c * 4)); CK(cudaMalloc(&d_beam_score_, (size_t)c * 4));
     CK(cudaMalloc(&d_best_rows_, (size_t)c * AMBI_MAXN * 4)); CK(cudaMalloc(&d_beam_rows_, (size_t)c * AMBI_MAXN * 4));
     CK(cudaMalloc(&d_cand_, (size_t)c * 8)); CK(cudaMalloc(&d_node_, (size_t)c * 8));
-    CK(cudaMalloc(&d_fmin_, (size_t)c * 4)); CK(cudaMalloc(&d_hist_, (size_t)c * BEAM_BINS * 4));
-    CK(cudaMalloc(&d_ticket_, (size_t)c * 4));
+    // beam statistics: one slice per level, cleared once per pass
+    CK(cudaMalloc(&d_fmin_, (size_t)c * 4 * AMBI_MAXN)); CK(cudaMalloc(&d_hist_, (size_t)c * BEAM_BINS * 4 * AMBI_MAXN));
+    CK(cudaMalloc(&d_ticket_, (size_t)c * 4 * AMBI_MAXN));
     prob_cap_ = c;
     return 0;
 }
@@ -638,54 +803,60 @@ int StageA::ensure_problem_arrays(int count)
 int StageA::upload(const DevProblem *host_probs, int count)
 {
     if (int rc = ensure_problem_arrays(count)) return rc;
-    count_ = count; nmax_ = 0;
-    for (int i = 0; i < count; ++i) nmax_ = std::max(nmax_, (int)host_probs[i].n);
+    if (count != count_ && graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    count_ = count;
+    int nmax = 0;
+    for (int i = 0; i < count; ++i) nmax = std::max(nmax, (int)host_probs[i].n);
+    if (nmax != nmax_ && graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    nmax_ = nmax;
+    stride_ = (int)ambi_node_stride(nmax_);
+    cap_ = (uint32_t)std::min<uint64_t>(cap_max_, buf_bytes_ / stride_);
+    if ((uint64_t)count > cap_) { snprintf(err_, sizeof err_, "batch of %d partitions exceeds node capacity %u", count, cap_); return -5; }
     CK(cudaMemcpyAsync(d_probs_, host_probs, (size_t)count * sizeof(DevProblem), cudaMemcpyHostToDevice, stream_));
     return 0;
 }
 
-// One level: expand -> merge -> finalize (-> beam selection).
-int StageA::run_level(int level, int cur, bool beam, int shard_world)
+// One level: expand -> (merge) -> finalize (-> beam selection).
+//   mode 0: greedy incumbent (every record emits its arg-min child)
+//   mode 1: beam incumbent (children within the limit, top-W per problem kept)
+//   mode 2: exact (children within the limit, merged by column state)
+int StageA::run_level(int level, int cur, int mode, int shard_world)
 {
-    uint32_t *c_work = counters_ + 0, *c_child = counters_ + 1, *c_next = counters_ + 2, *c_over = counters_ + 3;
-    uint32_t *c_cur = counters_ + 4 + (level & 1);      // frontier count of this level
-    uint32_t *c_nxt = counters_ + 4 + ((level + 1) & 1);
-    (void)c_next;
-    CK(cudaMemsetAsync(c_work, 0, 8, stream_));         // work + child counters
-    CK(cudaMemsetAsync(c_nxt, 0, 4, stream_));
-    CK(cudaMemsetAsync(dead_, 0, cap_, stream_));
+    uint32_t *c_over = counters_ + CTR_OVERFLOW;
+    uint32_t *c_work = counters_ + CTR_WORK + level, *c_child = counters_ + CTR_CHILD + level;
+    uint32_t *c_cur = counters_ + CTR_FRONT + level, *c_nxt = counters_ + CTR_FRONT + level + 1;
+    const bool merge = mode != 0;
     LevelArgs L;
     L.probs = d_probs_; L.parents = buf_[cur]; L.plist = list_[cur]; L.pcount = c_cur;
     L.children = buf_[cur ^ 1]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
     L.cand_count = d_cand_; L.node_count = d_node_; L.work_counter = c_work; L.overflow = c_over;
-    L.ptab = ptab_; L.ltab = ltab_; L.level = level; L.stride = stride_; L.nmax = AMBI_MAXN;
+    L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = mode == 0 ? EMIT_BEST : EMIT_ALL;
     L.shard_world = shard_world; L.shard_rank = rank_; L.shard_level = shard_level_eff_;
-    if (profile_) {
+    const bool prof = profile_ && !capturing_;
+    if (prof) {
         if (prof_used_ + 2 > prof_ev_.size()) { cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); prof_ev_.push_back(e0); prof_ev_.push_back(e1); }
         CK(cudaEventRecord(prof_ev_[prof_used_], stream_));
     }
-    k_expand<<<sms_ * 4, WPB * 32, 0, stream_>>>(L); ++launches_;
-    if (profile_) { CK(cudaEventRecord(prof_ev_[prof_used_ + 1], stream_)); prof_used_ += 2; }
-    DedupArgs D;
-    D.recs = buf_[cur ^ 1]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
-    D.gen = ++gen_; D.dead = dead_; D.stride = stride_; D.level = level;
-    k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
-    FinalizeArgs F;
-    F.probs = d_probs_; F.recs = buf_[cur ^ 1]; F.count = c_child; F.cap = cap_; F.dead = dead_;
-    F.next_list = list_[cur ^ 1]; F.next_count = c_nxt;
-    F.best_score = beam ? d_beam_score_ : d_best_score_; F.best_rows = beam ? d_beam_rows_ : d_best_rows_;
-    F.fmin = nullptr; F.stride = stride_; F.level = level;
-    if (beam) {
-        CK(cudaMemsetAsync(d_fmin_, 0x7f, (size_t)count_ * 4, stream_));
-        CK(cudaMemsetAsync(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4, stream_));
-        CK(cudaMemsetAsync(d_ticket_, 0, (size_t)count_ * 4, stream_));
-        F.fmin = d_fmin_;
+    k_expand<<<expand_blocks_, WPB * 32, expand_smem_, stream_>>>(L); ++launches_;
+    if (prof) { CK(cudaEventRecord(prof_ev_[prof_used_ + 1], stream_)); prof_used_ += 2; }
+    if (merge) {
+        DedupArgs D;
+        D.recs = buf_[cur ^ 1]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
+        D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = stride_; D.level = level;
+        k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
     }
+    const bool beam = mode == 1;
+    FinalizeArgs F;
+    F.probs = d_probs_; F.recs = buf_[cur ^ 1]; F.count = c_child; F.cap = cap_;
+    F.next_list = list_[cur ^ 1]; F.next_count = c_nxt;
+    F.best_score = mode == 2 ? d_best_score_ : d_beam_score_; F.best_rows = mode == 2 ? d_best_rows_ : d_beam_rows_;
+    F.fmin = beam ? d_fmin_ + (size_t)level * count_ : nullptr; F.stride = stride_; F.level = level;
     k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_;
     if (beam) {
         BeamArgs B;
-        B.probs = d_probs_; B.recs = buf_[cur ^ 1]; B.count = c_child; B.cap = cap_; B.dead = dead_;
-        B.fmin = d_fmin_; B.hist = d_hist_; B.ticket = d_ticket_; B.next_list = list_[cur ^ 1];
+        B.probs = d_probs_; B.recs = buf_[cur ^ 1]; B.count = c_child; B.cap = cap_;
+        B.fmin = d_fmin_ + (size_t)level * count_; B.hist = d_hist_ + (size_t)level * count_ * BEAM_BINS;
+        B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = list_[cur ^ 1];
         B.next_count = c_nxt; B.width = beam_; B.stride = stride_; B.level = level;
         k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
         k_beam_select<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
@@ -693,40 +864,87 @@ int StageA::run_level(int level, int cur, bool beam, int shard_world)
     return 0;
 }
 
-int StageA::run(bool sharded)
+int StageA::run_pass(int mode, int shard_world, bool first)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
-    uint32_t *c_over = counters_ + 3;
-    prof_used_ = 0;
-    CK(cudaEventRecord(ev_[0], stream_));
-    CK(cudaMemsetAsync(counters_, 0, 64 * sizeof(uint32_t), stream_));
+    // everything but the overflow flag
+    CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
+    if (mode == 1) {
+        CK(cudaMemsetAsync(d_fmin_, 0x7f, (size_t)count_ * 4 * nmax_, stream_));
+        CK(cudaMemsetAsync(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4 * nmax_, stream_));
+        CK(cudaMemsetAsync(d_ticket_, 0, (size_t)count_ * 4 * nmax_, stream_));
+    }
+    k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, buf_[0], stride_, nmax_, list_[0],
+                                              counters_ + CTR_FRONT, d_limit_, d_best_score_, first ? 1 : 0); ++launches_;
+    int cur = 0;
+    for (int a = 0; a < nmax_; ++a) { if (int rc = run_level(a, cur, mode, shard_world)) return rc; cur ^= 1; }
+    return 0;
+}
+
+int StageA::enqueue(bool sharded)
+{
+    const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
+    CK(cudaMemsetAsync(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t), stream_));
+    k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
     CK(cudaMemsetAsync(d_cand_, 0, (size_t)count_ * 8, stream_));
     CK(cudaMemsetAsync(d_node_, 0, (size_t)count_ * 8, stream_));
     CK(cudaMemsetAsync(d_beam_score_, 0x7f, (size_t)count_ * 4, stream_));
-    // ---- pass 1: incumbent (beam) ------------------------------------------
-    k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, buf_[0], stride_, AMBI_MAXN, list_[0],
-                                              counters_ + 4, d_limit_, d_best_score_, 1); ++launches_;
+    shard_level_eff_ = -1;
+    // ---- pass 0: greedy dive -> first incumbent (limit starts at the all-zero score)
+    if (int rc = run_pass(0, 1, true)) return rc;
     k_solve_n1<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_best_score_, d_best_rows_, d_cand_); ++launches_;
-    shard_level_eff_ = -1;
-    int cur = 0;
-    for (int a = 0; a < nmax_; ++a) { if (int rc = run_level(a, cur, true, 1)) return rc; cur ^= 1; }
     k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_); ++launches_;
-    CK(cudaEventRecord(ev_[1], stream_));
-    // ---- pass 2: exact ------------------------------------------------------
-    // roots again (buffer 0 head was overwritten by children of later levels)
-    CK(cudaMemsetAsync(counters_ + 4, 0, 8, stream_));
-    k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, buf_[0], stride_, AMBI_MAXN, list_[0],
-                                              counters_ + 4, d_limit_, d_best_score_, 0); ++launches_;
+    // ---- pass 1: beam of width W inside that limit -> tighter incumbent
+    if (beam_ > 1) {
+        CK(cudaMemsetAsync(d_beam_score_, 0x7f, (size_t)count_ * 4, stream_));
+        if (int rc = run_pass(1, 1, false)) return rc;
+        k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_); ++launches_;
+    }
+    if (!capturing_) CK(cudaEventRecord(ev_[1], stream_));
+    // ---- pass 2: exact
     int sw = sharded ? world_ : 1;
-    shard_level_eff_ = -1;
     if (sw > 1) {
         int sl = shard_level_ > 0 ? shard_level_ : 2;
         shard_level_eff_ = std::min(sl, std::max(0, nmax_ - 2));
     }
-    cur = 0;
-    for (int a = 0; a < nmax_; ++a) { if (int rc = run_level(a, cur, false, sw)) return rc; cur ^= 1; }
+    if (int rc = run_pass(2, sw, false)) return rc;
+    return 0;
+}
+
+// The launch sequence depends only on (count, nmax, sharding): every size that matters lives in
+// device counters.  It is captured once into a CUDA graph and replayed, so a step costs one
+// graph launch instead of ~150 kernel launches; the profiling pass uses plain launches.
+int StageA::run(bool sharded)
+{
+    prof_used_ = 0;
+    CK(cudaEventRecord(ev_[0], stream_));
+    const bool use_graph = !profile_ && getenv("AMBI_NO_GRAPH") == nullptr;
+    if (!use_graph) {
+        if (int rc = enqueue(sharded)) return rc;
+        used_graph_ = false;
+    } else {
+        if (graph_exec_ && graph_sharded_ != sharded) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+        if (!graph_exec_) {
+            cudaGraph_t g = nullptr;
+            const unsigned long long l0 = launches_;
+            CK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+            capturing_ = true;
+            int rc = enqueue(sharded);
+            capturing_ = false;
+            cudaError_t e = cudaStreamEndCapture(stream_, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            CK(e);
+            CK(cudaGraphInstantiate(&graph_exec_, g, 0));
+            cudaGraphDestroy(g);
+            graph_sharded_ = sharded;
+            graph_launches_ = launches_ - l0;
+            launches_ = l0;
+        }
+        CK(cudaGraphLaunch(graph_exec_, stream_));
+        launches_ += graph_launches_;
+        used_graph_ = true;
+    }
     CK(cudaEventRecord(ev_[2], stream_));
-    (void)c_over;
     return 0;
 }
 
@@ -735,7 +953,7 @@ int StageA::fetch(HostResult *out)
     std::vector<int32_t> score(count_), inc(count_);
     std::vector<uint32_t> rows((size_t)count_ * AMBI_MAXN);
     std::vector<unsigned long long> cand(count_), node(count_);
-    uint32_t ctr[8];
+    uint32_t ctr[8];   // CTR_OVERFLOW is word 0
     CK(cudaMemcpyAsync(score.data(), d_best_score_, (size_t)count_ * 4, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(inc.data(), d_incumbent_, (size_t)count_ * 4, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(rows.data(), d_best_rows_, rows.size() * 4, cudaMemcpyDeviceToHost, stream_));
@@ -744,19 +962,19 @@ int StageA::fetch(HostResult *out)
     CK(cudaMemcpyAsync(ctr, counters_, sizeof ctr, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     float ms_beam = 0, ms_all = 0;
-    cudaEventElapsedTime(&ms_beam, ev_[0], ev_[1]);
+    if (!used_graph_) cudaEventElapsedTime(&ms_beam, ev_[0], ev_[1]);
     cudaEventElapsedTime(&ms_all, ev_[0], ev_[2]);
     prof_total_ms_ = ms_all; prof_beam_ms_ = ms_beam;
     if (profile_) {
         prof_expand_ms_ = 0; prof_expand_launches_ = prof_used_ / 2;
         for (size_t i = 0; i + 1 < prof_used_; i += 2) { float m = 0; cudaEventElapsedTime(&m, prof_ev_[i], prof_ev_[i + 1]); prof_expand_ms_ += m; }
     }
-    const bool overflow = ctr[3] != 0;
+    const bool overflow = ctr[CTR_OVERFLOW] != 0;
     for (int p = 0; p < count_; ++p) {
         out[p].score2 = score[p]; out[p].incumbent = inc[p];
         out[p].candidates = cand[p]; out[p].nodes = node[p];
         memcpy(out[p].rows, &rows[(size_t)p * AMBI_MAXN], AMBI_MAXN * 4);
-        out[p].seconds = ms_all * 1e-3; out[p].seconds_to_best = (inc[p] == score[p] ? ms_beam : ms_all) * 1e-3;
+        out[p].seconds = ms_all * 1e-3; out[p].seconds_to_best = ((inc[p] == score[p] && !used_graph_) ? ms_beam : ms_all) * 1e-3;
         out[p].status = overflow ? -5 : (score[p] == 0x7fffffff ? -4 : 0);
     }
     if (overflow) snprintf(err_, sizeof err_, "frontier overflow: more than %u candidate records in one level", cap_);

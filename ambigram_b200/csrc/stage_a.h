@@ -40,18 +40,21 @@ public:
 private:
     int ensure_problem_arrays(int count);
     void free_problem_arrays();
-    int run_level(int level, int cur, bool beam, int shard_world);
+    int run_level(int level, int cur, int mode, int shard_world);
+    int run_pass(int mode, int shard_world, bool first);
+    int enqueue(bool sharded);
 
     cudaStream_t stream_ = nullptr;
-    uint32_t cap_ = 0, tsize_ = 0, gen_ = 1;
+    uint32_t cap_ = 0, cap_base_ = 0, cap_max_ = 0, tsize_ = 0, gen_ = 1;
+    size_t buf_bytes_ = 0;
     int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
     int stride_ = 0, sms_ = 148;
     uint8_t *buf_[2] = {nullptr, nullptr};
     uint32_t *list_[2] = {nullptr, nullptr};
-    uint8_t *dead_ = nullptr;
     unsigned long long *table_ = nullptr;
     uint32_t *counters_ = nullptr;
-    uint8_t *ptab_ = nullptr, *ltab_ = nullptr;
+    size_t expand_smem_ = 0;
+    int expand_blocks_ = 148;
     // per-problem arrays
     int prob_cap_ = 0, count_ = 0, nmax_ = 0;
     DevProblem *d_probs_ = nullptr;
@@ -60,7 +63,10 @@ private:
     unsigned long long *d_cand_ = nullptr, *d_node_ = nullptr;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches_ = 0;
-    bool profile_ = false;
+    bool profile_ = false, capturing_ = false, used_graph_ = false, graph_sharded_ = false;
+    cudaGraphExec_t graph_exec_ = nullptr;
+    uint32_t graph_gens_ = 0;
+    unsigned long long graph_launches_ = 0;
     std::vector<cudaEvent_t> prof_ev_;
     size_t prof_used_ = 0;
     double prof_expand_ms_ = 0, prof_total_ms_ = 0, prof_beam_ms_ = 0;

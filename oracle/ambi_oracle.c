@@ -232,7 +232,36 @@ typedef struct {
     int64_t best_score;
     int64_t cands, nodes;
     memo_ent *memo; size_t memo_cap, memo_cnt;
+    int shard_world, shard_rank, shard_level;   /* prefix sharding (multi-GPU emulation) */
 } srch_t;
+
+/* row-configuration codes, identical to ambigram_b200/csrc/ambi_common.cuh: ends numbered from the
+ * right (q = n-1-b) so that integer order of (ip<<10|il) is the search order */
+static int ip_code(int q1, int q2) { if (q1 < 0) return 0; int base = 1 + q1 * (q1 + 1) / 2; return q2 < 0 ? base : base + 1 + q2; }
+static int il_code(int q1, int q2)
+{
+    if (q1 < 0) return 0;
+    int base = 1 + 2 * q1 + q1 * (q1 - 1) / 2;
+    if (q2 < 0) return base;
+    return q2 == q1 ? base + 1 + q1 : base + 1 + q2;
+}
+static uint32_t row_code(int n, const int8_t r[4])
+{
+    int ip = r[0] < 0 ? 0 : ip_code(n - 1 - r[0], r[1] < 0 ? -1 : n - 1 - r[1]);
+    int il = r[2] < 0 ? 0 : il_code(n - 1 - r[2], r[3] < 0 ? -1 : n - 1 - r[3]);
+    return ((uint32_t)ip << 10) | (uint32_t)il;
+}
+static uint32_t mix32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
+/* which shard owns the prefix rows[0..level] (same hash as k_expand) */
+static int prefix_shard(int n, int8_t rows[][4], int level, int world)
+{
+    uint32_t h = 0;
+    for (int lane = 0; lane < 32; lane++) {
+        uint32_t v = lane <= level ? row_code(n, rows[lane]) : 0u;
+        h ^= mix32(v + 0x9e3779b9u * (uint32_t)(lane + 1));
+    }
+    return (int)(mix32(h) % (uint32_t)world);
+}
 
 #define BUD_INF 3
 
@@ -433,7 +462,11 @@ static void dfs(srch_t *S, int a, const st_t *st, int score)
         }
         return;
     }
-    if (memo_visit(S, a, st, score)) return;
+    if (S->shard_world > 1) {
+        if (a == S->shard_level + 1 && prefix_shard(n, S->cur, S->shard_level, S->shard_world) != S->shard_rank) return;
+        /* merging states across prefixes is only valid once the prefix is owned by one shard */
+        if (a > S->shard_level && memo_visit(S, a, st, score)) return;
+    } else if (memo_visit(S, a, st, score)) return;
     S->nodes++;
     child_t *ch = NULL; size_t cnt = 0, cap = 0;
     expand_row(S, a, st, (int)(S->limit - score), &ch, &cnt, &cap);
@@ -464,6 +497,13 @@ int orc_solve(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub,
               int n_tgs, const int32_t *tgs_pairs, int junc_info,
               int want_unique, int32_t *x_out, orc_solve_stats *stats)
 {
+    return orc_solve_shard(n, c2, j2, loop_ub, n_tgs, tgs_pairs, junc_info, want_unique, 1, 0, -1, x_out, stats);
+}
+
+int orc_solve_shard(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub,
+                    int n_tgs, const int32_t *tgs_pairs, int junc_info, int want_unique,
+                    int world, int rank, int shard_level, int32_t *x_out, orc_solve_stats *stats)
+{
     orc_solve_stats dummy;
     if (!stats) stats = &dummy;
     memset(stats, 0, sizeof *stats);
@@ -489,6 +529,8 @@ int orc_solve(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub,
     }
     srch_t *S = calloc(1, sizeof *S);
     S->n = n; S->loop_ub = loop_ub;
+    S->shard_world = world > 1 ? world : 1; S->shard_rank = rank;
+    S->shard_level = shard_level < 0 ? 0 : (shard_level > n - 2 ? n - 2 : shard_level);
     for (int i = 0; i < n; i++) { S->c2[i] = c2[i]; S->j2[i] = j2[i]; }
     if (n_tgs > 0 && junc_info)
         for (int t = 0; t < n_tgs; t++) {
@@ -507,11 +549,17 @@ int orc_solve(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub,
     memo_reset(S);
     dfs(S, 0, &root, 0);
     int64_t vstar = S->best_score;
+    if (vstar > zero) vstar = zero;      /* shard without an improving assignment: bound by all-zero */
     /* phase 2: first optimum in search order */
     S->mode = 1; S->found = 0; S->limit = vstar;
     memo_reset(S);
     dfs(S, 0, &root, 0);
-    if (!S->found) { stats->status = -2; free(S->memo); free(S); return -2; }
+    if (!S->found) {                 /* only possible for a shard that owns no completed assignment */
+        stats->status = S->shard_world > 1 ? 1 : -2; stats->score2 = 0x7fffffff;
+        memset(x_out, 0, 2 * H * sizeof(int32_t));
+        int rc = S->shard_world > 1 ? 0 : -2;
+        free(S->memo); free(S); return rc;
+    }
     rows_to_x(n, S->best, x_out);
     stats->score2 = vstar;
     if (want_unique) {

@@ -75,6 +75,21 @@ def solve(problem, want_unique: bool = True):
     return x, st
 
 
+def solve_shard(problem, world: int, rank: int, shard_level: int = 2):
+    """shard-local optimum: -> (x, Stats); Stats.score2 == 2**31-1 when the shard owns no assignment"""
+    L = lib()
+    c2, j2 = _arr(problem.seg_cn2), _arr(problem.fbi_cn2)
+    t, nt = _tgs_rel(problem)
+    x = np.zeros(problem.n * (problem.n + 1), dtype=np.int32)
+    st = Stats()
+    rc = L.orc_solve_shard(problem.n, c2.ctypes.data_as(I32P), j2.ctypes.data_as(I32P), problem.effective_loop_ub(), nt,
+                           t.ctypes.data_as(I32P), int(problem.junc_info), 0, world, rank, shard_level,
+                           x.ctypes.data_as(I32P), C.byref(st))
+    if rc != 0:
+        raise RuntimeError(f"orc_solve_shard failed: {rc}")
+    return x, st
+
+
 def model_eval(problem, x) -> Tuple[bool, int]:
     L = lib()
     c2, j2 = _arr(problem.seg_cn2), _arr(problem.fbi_cn2)
