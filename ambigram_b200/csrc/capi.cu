@@ -196,6 +196,16 @@ static int to_dev(const ambi_bfb_problem &p, DevProblem &d, std::string &why)
     }
     if (z > 0x3fffffff) { why = "copy numbers too large"; return AMBI_ERR_BAD_ARG; }
     d.zero_score = (int32_t)z;
+    {   // bound before any row is fixed: every column may still take 2 patterns + 2 loops (cap 6),
+        // every row adds at most 6 (child_bound() with a = -1 and an empty state)
+        long long lb = 0;
+        for (int j = 0; j < p.n; ++j) {
+            int fmax = std::min(6 * (j + 1), 6 * (p.n - j));
+            lb += std::max(0, p.seg_cn2[j] - 2 * fmax);
+            lb += std::max(0, p.fbi_cn2[j] - (6 + std::min(6 * (p.n - j), 6)));
+        }
+        d.root_lb = (int32_t)std::min<long long>(lb, z);
+    }
     if (p.n_tgs > 0 && (p.flags & AMBI_FLAG_JUNC_INFO) && p.tgs_pairs) {
         for (int t = 0; t < p.n_tgs; ++t) {
             int s = p.tgs_pairs[2 * t] - p.start_id, e = p.tgs_pairs[2 * t + 1] - p.start_id;

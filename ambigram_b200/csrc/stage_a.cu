@@ -50,6 +50,7 @@ struct LevelArgs {
     int stride;
     int nmax;
     int emit;                       // EMIT_ALL: every child within the limit; EMIT_BEST: arg-min child per record
+    int beam_delta;                 // >= 0 (incumbent beam only): also drop children whose f exceeds the parent's by more
     int shard_world, shard_rank, shard_level;
 };
 
@@ -249,6 +250,7 @@ __device__ __forceinline__ uint32_t light_test(const GroupShared &S, int a, int 
     uint32_t li;
     if (r < nl0) li = r;
     else {
+        // non-empty pattern set: singles in S1, then pairs (high end in S1, low end any budgeted column below)
         class0 = false;
         r -= nl0;
         const uint32_t nlall = S.nlall[slot];
@@ -256,17 +258,18 @@ __device__ __forceinline__ uint32_t light_test(const GroupShared &S, int a, int 
         li = r - pi * nlall;
         const uint32_t S1 = okP & S.parP[slot];
         const uint32_t ns = __popc(S1);
-        if (pi < ns) p1 = nth_bit(S1, pi);
-        else {
+        uint32_t pm = S1;
+        if (pi >= ns) {
             pi -= ns;
             for (uint32_t m = S1; m; m &= m - 1) {
                 const int hi = __ffs(m) - 1;
-                const uint32_t lows = okP & below(hi);
-                const uint32_t k = __popc(lows);
-                if (pi < k) { p2 = hi; p1 = nth_bit(lows, pi); break; }
+                pm = okP & below(hi);
+                const uint32_t k = __popc(pm);
+                if (pi < k) { p2 = hi; break; }
                 pi -= k;
             }
         }
+        p1 = nth_bit(pm, pi);
     }
     if (li > 0) {
         --li;
@@ -275,18 +278,24 @@ __device__ __forceinline__ uint32_t light_test(const GroupShared &S, int a, int 
         const uint32_t M1 = class0 ? (okL1 & S.par1[slot]) : okL1;
         const uint32_t M2 = class0 ? (okL2 & S.par2[slot]) : okL2;
         const uint32_t n1 = __popc(M1), n2 = __popc(M2);
-        if (li < n1) l1 = nth_bit(M1, li);
-        else if (li < n1 + n2) l1 = l2 = nth_bit(M2, li - n1);
-        else {
-            li -= n1 + n2;                 // pairs: high end in M1, low end any budgeted column below it
-            for (uint32_t m = M1; m; m &= m - 1) {
-                const int hi = __ffs(m) - 1;
-                const uint32_t lows = okL1 & below(hi);
-                const uint32_t k = __popc(lows);
-                if (li < k) { l2 = hi; l1 = nth_bit(lows, li); break; }
-                li -= k;
+        uint32_t lm = M1;                  // mask the low (or only) end is drawn from, and its rank in it
+        bool dbl = false;
+        if (li >= n1) {
+            li -= n1;
+            if (li < n2) { lm = M2; dbl = true; }
+            else {
+                li -= n2;                  // pairs: high end in M1, low end any budgeted column below it
+                for (uint32_t m = M1; m; m &= m - 1) {
+                    const int hi = __ffs(m) - 1;
+                    lm = okL1 & below(hi);
+                    const uint32_t k = __popc(lm);
+                    if (li < k) { l2 = hi; break; }
+                    li -= k;
+                }
             }
         }
+        l1 = nth_bit(lm, li);
+        if (dbl) l2 = l1;
     }
     bool feas = true;
     const int nl = (l1 >= 0) + (l2 >= 0);
@@ -351,6 +360,9 @@ k_expand(LevelArgs A_param)
             P = &A.probs[hd.z];
             my_n = P->n; lmax = P->lmax;
             slack = A.limit[hd.z] - hd.x;
+            // heuristic band (the beam only feeds the incumbent): a child may exceed its parent's f by
+            // beam_delta, or by half of what is left up to the current limit if that is more
+            if (A.beam_delta >= 0) slack = min(slack, hd.y - hd.x + max(A.beam_delta, (A.limit[hd.z] - hd.y) >> 1));
             S.pidx[lane] = pidx; S.score[lane] = hd.x; S.prob[lane] = hd.z; S.ptgs[lane] = hd.w;
             S.slack[lane] = slack; S.n[lane] = (uint8_t)my_n;
             S.tmask[lane] = P->has_tgs ? P->tgs_mask[a] : 0u;
@@ -668,7 +680,7 @@ __global__ void k_init_roots(const DevProblem *probs, int count, uint8_t *recs, 
     uint8_t *rec = recs + (size_t)s * stride;
     NodeHdr *h = reinterpret_cast<NodeHdr *>(rec);
     for (int b = 0; b < AMBI_MAXN; ++b) h->col[b] = b < P.n ? (uint8_t)((AMBI_BUD_INF << 4) | (AMBI_BUD_INF << 6)) : 0;
-    h->score = 0; h->f = 0; h->prob = p; h->tgs = 0;
+    h->score = 0; h->f = P.root_lb; h->prob = p; h->tgs = 0;
     uint32_t *r = reinterpret_cast<uint32_t *>(rec + sizeof(NodeHdr));
     for (int k = 0; k < nmax; ++k) r[k] = 0;
     list[s] = s;
@@ -755,8 +767,9 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
         cap_base_ = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(recs, 64ull << 20));
     }
     cap_ = cap_base_;
-    beam_ = beam_width > 0 ? beam_width : 16;
-    if (const char *e = getenv("AMBI_BEAM_WIDTH")) { int v = atoi(e); if (v > 0) beam_ = v; }   // tuning knob; results do not depend on it
+    beam_ = beam_width > 0 ? beam_width : 8;
+    if (const char *e = getenv("AMBI_BEAM_WIDTH")) { int v = atoi(e); if (v > 0) beam_ = v; }   // tuning knobs; results do not depend on them
+    if (const char *e = getenv("AMBI_BEAM_DELTA")) beam_delta_ = atoi(e);
     rank_ = rank; world_ = world > 0 ? world : 1; shard_level_ = shard_level;
     // buffers are sized in bytes for the widest record (n = 32); narrower batches fit more records
     buf_bytes_ = (size_t)cap_base_ * stride_;
@@ -831,6 +844,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     L.children = buf_[cur ^ 1]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
     L.cand_count = d_cand_; L.node_count = d_node_; L.work_counter = c_work; L.overflow = c_over;
     L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = mode == 0 ? EMIT_BEST : EMIT_ALL;
+    L.beam_delta = mode == 1 ? beam_delta_ : -1;
     L.shard_world = shard_world; L.shard_rank = rank_; L.shard_level = shard_level_eff_;
     const bool prof = profile_ && !capturing_;
     if (prof) {

@@ -47,6 +47,7 @@ private:
     cudaStream_t stream_ = nullptr;
     uint32_t cap_ = 0, cap_base_ = 0, cap_max_ = 0, tsize_ = 0, gen_ = 1;
     size_t buf_bytes_ = 0;
+    int beam_delta_ = 8;          // heuristic band of the incumbent beam (see k_expand)
     int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
     int stride_ = 0, sms_ = 148;
     uint8_t *buf_[2] = {nullptr, nullptr};

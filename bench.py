@@ -264,7 +264,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         "h2d_bytes_per_step": args.batch * 416 * world, "d2h_bytes_per_step": args.batch * 156 * world},
                 "gpu_launches": launches_all,
-                "candidates_per_step": cand_all, "problems_per_s": args.batch * world / (ms_per_step * 1e-3),
+                "candidates_per_step": cand_all, "records_expanded_per_step": nodes_per_step, "problems_per_s": args.batch * world / (ms_per_step * 1e-3),
                 "time_to_best_ms_per_lh": 1e3 * t_best,
                 "roofline": roof, "roofline_int32": roof_int, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
