@@ -592,8 +592,10 @@ struct FinalizeArgs {
     int32_t *best_score;        // [prob]
     uint32_t *best_rows;        // [prob][AMBI_MAXN]
     int32_t *fmin;              // beam: per-problem min f of this level (or nullptr)
+    int32_t *limit;             // chunked mode: tighten the pruning limit as completed assignments arrive
     int stride;
     int level;
+    int merge_best;             // chunked mode: keep the better of (stored best, this chunk's best)
 };
 
 __global__ void k_finalize(FinalizeArgs A)
@@ -607,10 +609,22 @@ __global__ void k_finalize(FinalizeArgs A)
         if (n == A.level + 1) {
             // all completed assignments of a problem share the empty column state, so the
             // merge above left exactly one alive: the arg-min in (score, search order)
-            A.best_score[h->prob] = h->score;
             const uint32_t *r = reinterpret_cast<const uint32_t *>(rec + sizeof(NodeHdr));
             uint32_t *o = A.best_rows + (size_t)h->prob * AMBI_MAXN;
-            for (int k = 0; k < n; ++k) o[k] = r[k];
+            bool take = true;
+            if (A.merge_best) {     // one alive completed record per problem and launch: no race
+                const int old = A.best_score[h->prob];
+                if (old < h->score) take = false;
+                else if (old == h->score) {
+                    take = false;
+                    for (int k = 0; k < n; ++k) if (r[k] != o[k]) { take = r[k] < o[k]; break; }
+                }
+            }
+            if (take) {
+                A.best_score[h->prob] = h->score;
+                for (int k = 0; k < n; ++k) o[k] = r[k];
+                if (A.limit && h->score < A.limit[h->prob]) A.limit[h->prob] = h->score;
+            }
         } else {
             if (A.fmin) atomicMin(&A.fmin[h->prob], h->f);
             else { uint32_t s = atomicAdd(A.next_count, 1u); A.next_list[s] = i; }
@@ -734,7 +748,7 @@ StageA::~StageA() { release(); }
 void StageA::release()
 {
     cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]);
-    cudaFree(table_); cudaFree(counters_);
+    cudaFree(table_); cudaFree(counters_); cudaFree(pool_); pool_ = nullptr;
     buf_[0] = buf_[1] = nullptr; list_[0] = list_[1] = nullptr; table_ = nullptr;
     counters_ = nullptr;
     free_problem_arrays();
@@ -865,13 +879,15 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     F.next_list = list_[cur ^ 1]; F.next_count = c_nxt;
     F.best_score = mode == 2 ? d_best_score_ : d_beam_score_; F.best_rows = mode == 2 ? d_best_rows_ : d_beam_rows_;
     F.fmin = beam ? d_fmin_ + (size_t)level * count_ : nullptr; F.stride = stride_; F.level = level;
+    F.limit = nullptr; F.merge_best = 0;
     k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_;
     if (beam) {
         BeamArgs B;
         B.probs = d_probs_; B.recs = buf_[cur ^ 1]; B.count = c_child; B.cap = cap_;
         B.fmin = d_fmin_ + (size_t)level * count_; B.hist = d_hist_ + (size_t)level * count_ * BEAM_BINS;
         B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = list_[cur ^ 1];
-        B.next_count = c_nxt; B.width = beam_; B.stride = stride_; B.level = level;
+        // a fixed budget of beam records per batch: few large partitions get a wide beam
+        B.next_count = c_nxt; B.width = std::min(8192, std::max(beam_, beam_ * 4096 / std::max(count_, 1))); B.stride = stride_; B.level = level;
         k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
         k_beam_select<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
     }
@@ -931,6 +947,7 @@ int StageA::enqueue(bool sharded)
 int StageA::run(bool sharded)
 {
     prof_used_ = 0;
+    last_sharded_ = sharded;
     CK(cudaEventRecord(ev_[0], stream_));
     const bool use_graph = !profile_ && getenv("AMBI_NO_GRAPH") == nullptr;
     if (!use_graph) {
@@ -962,8 +979,134 @@ int StageA::run(bool sharded)
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// chunked (depth-first) exact pass: the fallback when one level of the breadth-first
+// pass does not fit the candidate buffers.  Frontiers live in a pool used as a stack of
+// levels; each level is expanded a chunk at a time, all the way down before the next
+// chunk, so completed assignments arrive early and tighten the limit for what is left.
+// ---------------------------------------------------------------------------
+__global__ void k_iota(uint32_t *list, uint32_t start, uint32_t m, uint32_t *count)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) list[i] = start + i;
+    if (i == 0) *count = m;
+}
+
+__global__ void k_gather(const uint8_t *recs, const uint32_t *list, uint32_t m, uint8_t *dst, int stride)
+{
+    const uint32_t words = (uint32_t)stride / 16;
+    const uint64_t total = (uint64_t)m * words;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(t / words), w = (uint32_t)(t % words);
+        reinterpret_cast<uint4 *>(dst + (size_t)r * stride)[w] =
+            reinterpret_cast<const uint4 *>(recs + (size_t)list[r] * stride)[w];
+    }
+}
+
+int StageA::run_chunked(bool sharded)
+{
+    const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
+    if (!pool_) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        pool_bytes_ = std::min<size_t>(free_b / 2, 8 * buf_bytes_);
+        CK(cudaMalloc(&pool_, pool_bytes_));
+    }
+    int sw = sharded ? world_ : 1;
+    shard_level_eff_ = -1;
+    if (sw > 1) { int sl = shard_level_ > 0 ? shard_level_ : 2; shard_level_eff_ = std::min(sl, std::max(0, nmax_ - 2)); }
+    // the limit (incumbent from passes 0/1) and the n==1 results of the failed run are still valid
+    CK(cudaMemsetAsync(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t), stream_));
+    struct Seg { int level; size_t off; uint32_t cnt, pos; };
+    std::vector<Seg> stack;
+    // roots -> pool
+    CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
+    k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, pool_, stride_, nmax_, list_[0],
+                                              counters_ + CTR_FRONT, d_limit_, d_best_score_, 0); ++launches_;
+    uint32_t nroots = 0;
+    CK(cudaMemcpyAsync(&nroots, counters_ + CTR_FRONT, 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    if (nroots == 0) return 0;
+    stack.push_back({0, 0, nroots, 0});
+    size_t pool_top = (size_t)nroots * stride_;
+    std::vector<uint32_t> chunk(AMBI_MAXN + 1, cap_ / 16 ? cap_ / 16 : 1);   // parents per chunk, per level (adaptive)
+    uint32_t *c_over = counters_ + CTR_OVERFLOW;
+    uint32_t *c_work = counters_ + CTR_WORK, *c_child = counters_ + CTR_CHILD;
+    uint32_t *c_par = counters_ + CTR_FRONT, *c_next = counters_ + CTR_FRONT + 1;
+    unsigned long long chunks = 0;
+    while (!stack.empty()) {
+        Seg &sg = stack.back();
+        if (sg.pos >= sg.cnt) { pool_top = sg.off; stack.pop_back(); continue; }
+        const int level = sg.level;
+        const uint32_t m = std::min<uint32_t>(chunk[level], sg.cnt - sg.pos);
+        CK(cudaMemsetAsync(c_work, 0, 4, stream_)); CK(cudaMemsetAsync(c_child, 0, 4, stream_));
+        CK(cudaMemsetAsync(c_next, 0, 4, stream_)); CK(cudaMemsetAsync(c_over, 0, 4, stream_));
+        k_iota<<<(m + 255) / 256, 256, 0, stream_>>>(list_[0], sg.pos, m, c_par); ++launches_;
+        LevelArgs L;
+        L.probs = d_probs_; L.parents = pool_ + sg.off; L.plist = list_[0]; L.pcount = c_par;
+        L.children = buf_[0]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
+        L.cand_count = d_cand_; L.node_count = d_node_; L.work_counter = c_work; L.overflow = c_over;
+        L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = EMIT_ALL; L.beam_delta = -1;
+        L.shard_world = sw; L.shard_rank = rank_; L.shard_level = shard_level_eff_;
+        k_expand<<<expand_blocks_, WPB * 32, expand_smem_, stream_>>>(L); ++launches_;
+        uint32_t ctr[2] = {0, 0};
+        CK(cudaMemcpyAsync(&ctr[0], c_over, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpyAsync(&ctr[1], c_child, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        if (ctr[0]) {                               // this chunk's children do not fit: halve and retry
+            if (m == 1) { snprintf(err_, sizeof err_, "chunked pass: one record's children exceed the buffer (%u)", cap_); return -5; }
+            chunk[level] = std::max<uint32_t>(1, m / 2);
+            // candidates of the aborted attempt were scored; they stay in the statistics
+            continue;
+        }
+        if (ctr[1] * 4ull < cap_ && chunk[level] < cap_) chunk[level] = std::min<uint64_t>(cap_, 2ull * chunk[level]);
+        sg.pos += m;
+        ++chunks;
+        DedupArgs D;
+        D.recs = buf_[0]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
+        D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = stride_; D.level = level;
+        k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
+        k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
+        FinalizeArgs F;
+        F.probs = d_probs_; F.recs = buf_[0]; F.count = c_child; F.cap = cap_;
+        F.next_list = list_[1]; F.next_count = c_next; F.best_score = d_best_score_; F.best_rows = d_best_rows_;
+        F.fmin = nullptr; F.limit = d_limit_; F.stride = stride_; F.level = level; F.merge_best = 1;
+        k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_;
+        uint32_t nnext = 0;
+        CK(cudaMemcpyAsync(&nnext, c_next, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        if (nnext) {
+            const size_t need = (size_t)nnext * stride_;
+            if (pool_top + need > pool_bytes_) { snprintf(err_, sizeof err_, "chunked pass: frontier pool exhausted (%zu bytes)", pool_bytes_); return -5; }
+            k_gather<<<sms_ * 8, 256, 0, stream_>>>(buf_[0], list_[1], nnext, pool_ + pool_top, stride_); ++launches_;
+            stack.push_back({level + 1, pool_top, nnext, 0});
+            pool_top += need;
+        }
+    }
+    chunked_runs_++;
+    (void)chunks;
+    CK(cudaEventRecord(ev_[2], stream_));
+    return 0;
+}
+
+__global__ void k_reset_best(const DevProblem *probs, int count, int32_t *best_score)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < count && probs[p].n >= 2) best_score[p] = 0x7fffffff;
+}
+
 int StageA::fetch(HostResult *out)
 {
+    {   // a level of the breadth-first exact pass did not fit: redo the exact pass depth-first in chunks
+        uint32_t over = 0;
+        CK(cudaMemcpyAsync(&over, counters_ + CTR_OVERFLOW, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        if (over && getenv("AMBI_NO_CHUNKED") == nullptr) {
+            k_reset_best<<<(count_ + 127) / 128, 128, 0, stream_>>>(d_probs_, count_, d_best_score_); ++launches_;
+            if (int rc = run_chunked(last_sharded_)) { if (rc != -5) return rc; }
+        }
+    }
     std::vector<int32_t> score(count_), inc(count_);
     std::vector<uint32_t> rows((size_t)count_ * AMBI_MAXN);
     std::vector<unsigned long long> cand(count_), node(count_);

@@ -29,6 +29,7 @@ public:
     const char *error() const { return err_; }
     unsigned long long launches() const { return launches_; }
     int count() const { return count_; }
+    unsigned long long chunked_runs() const { return chunked_runs_; }
     // per-kernel timing (CUDA events around every k_expand launch; adds launch gaps, so only
     // enabled for the bench's roofline pass)
     void set_profile(bool on) { profile_ = on; }
@@ -43,10 +44,14 @@ private:
     int run_level(int level, int cur, int mode, int shard_world);
     int run_pass(int mode, int shard_world, bool first);
     int enqueue(bool sharded);
+    int run_chunked(bool sharded);
 
     cudaStream_t stream_ = nullptr;
     uint32_t cap_ = 0, cap_base_ = 0, cap_max_ = 0, tsize_ = 0, gen_ = 1;
-    size_t buf_bytes_ = 0;
+    size_t buf_bytes_ = 0, pool_bytes_ = 0;
+    uint8_t *pool_ = nullptr;
+    bool last_sharded_ = false;
+    unsigned long long chunked_runs_ = 0;
     int beam_delta_ = 8;          // heuristic band of the incumbent beam (see k_expand)
     int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
     int stride_ = 0, sms_ = 148;

@@ -35,6 +35,13 @@ def make_problems(count: int, seed0: int, n: int = N_SEG, folds: int = N_FOLDS):
     return [lh.problem_from_lh(synth.generate(n, folds, seed0 + s).lh_text()) for s in range(count)]
 
 
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -86,7 +93,7 @@ class ClockSampler:
 def cpu_baseline(problems, budget_s: float = 15.0, threads: int = 0):
     """oracle port (oracle/ambi_oracle.c, OpenMP over problems) on a bounded sample of the workload"""
     from tests import oracle_lib as orc
-    th = threads or orc.max_threads()
+    th = threads or host_threads()
     sample = problems[:min(len(problems), 64)]
     t0 = time.perf_counter()
     _, _, cand = orc.solve_batch(sample, th)
@@ -114,7 +121,7 @@ def run_reference(args):
         return 0
     from tests import oracle_lib as orc
     problems = make_problems(args.batch, 0)
-    th = orc.max_threads()
+    th = host_threads()         # torchrun exports OMP_NUM_THREADS=1; the arm uses every host core it is allowed
     # bounded sample per step
     probe = problems[:min(64, len(problems))]
     t0 = time.perf_counter(); orc.solve_batch(probe, th); dt = time.perf_counter() - t0

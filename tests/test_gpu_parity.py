@@ -168,7 +168,20 @@ def test_prefix_sharded_solve_combines_to_the_same_optimum():
             assert best.score2 == want[i].score2 and np.array_equal(best.element_cn, want[i].element_cn)
 
 
-def test_overflow_is_reported_loudly():
+def test_small_buffers_fall_back_to_chunked_depth_first_pass():
+    """when a level does not fit the candidate buffers the exact pass is redone depth-first in chunks:
+    same answer, bit for bit"""
+    probs = [lh.problem_from_lh(synth.generate(n, f, s, 0.5).lh_text()) for (n, f, s) in
+             [(12, 4, 1), (16, 5, 0), (16, 5, 3), (20, 6, 1)]]
+    with capi.Context(device=0, node_capacity=4096) as c:
+        for p in probs:
+            check_against_oracle(p, c.solve(p))
+        for p, s in zip(probs, c.solve_batch(probs)):
+            check_against_oracle(p, s)
+
+
+def test_overflow_is_reported_loudly(monkeypatch):
+    monkeypatch.setenv("AMBI_NO_CHUNKED", "1")
     p = lh.problem_from_lh(synth.generate(16, 5, 0, 0.5).lh_text())
     with capi.Context(device=0, node_capacity=64) as c:
         with pytest.raises(capi.AmbiError) as e:
