@@ -50,6 +50,7 @@ struct LevelArgs {
     int stride;
     int nmax;
     int emit;                       // EMIT_ALL: every child within the limit; EMIT_BEST: arg-min child per record
+    int beam_shift;
     int beam_delta;                 // >= 0 (incumbent beam only): also drop children whose f exceeds the parent's by more
     int shard_world, shard_rank, shard_level;
 };
@@ -86,7 +87,7 @@ struct GroupShared {
     uint32_t tmask[GRP];                // third-generation cells of this row
     int32_t  score[GRP], slack[GRP], covC[GRP], fbC[GRP], ptgs[GRP], prob[GRP];
     uint32_t pidx[GRP];
-    uint32_t nl0[GRP], nlall[GRP];      // loop multisets: parents satisfied already / all within budget
+    uint32_t nl0[GRP];                  // loop multisets whose parents already exist (class 0)
     uint32_t cstart[GRP + 1];           // exclusive prefix of candidate counts
     uint8_t  n[GRP];
     uint32_t cnt[GRP];                  // candidates scored per record
@@ -239,44 +240,48 @@ __device__ __noinline__ void write_batch(GroupShared &S, const LevelArgs &A, int
 }
 
 // Decode candidate number r of record `slot` into a row configuration and run the light test
-// (loop parents row 3, rows 2/4/5 inside the row, third-generation row, exact deviation of segment a).
+// (rows 2/4/5 inside the row, third-generation row, exact deviation of segment a).
+//
+// Enumeration of a record's row configurations (every one satisfies budgets and parent rows 1/3):
+//   [0, nl0)            empty pattern set x class-0 loop multisets (parents already in the column:
+//                       {}, singles in A1, doubles in A2, pairs with the high end in A1)
+//   then, for each pattern high end hi in S1 = okP & parP, a block of (1 + k_hi) x (nl0 + e_hi):
+//       pattern sets {hi} and {lo, hi}, lo any budgeted column below hi (hi is lo's parent), times
+//       class-0 multisets plus the singles at E(hi) = okL1 & ~par1 & below(hi), whose only parent
+//       is a pattern end of this row.  (A multiset of two entries below hi is cut by rows 4/5
+//       anyway, so nothing else can use the row's pattern ends as parents.)
 // Returns the queue entry (slot<<24 | cfg) or 0 if structurally infeasible; *pass = within the limit.
 __device__ __forceinline__ uint32_t light_test(const GroupShared &S, int a, int slot, uint32_t r, bool *pass)
 {
-    const uint32_t okP = S.okP[slot], okL1 = S.okL1[slot], okL2 = S.okL2[slot];
+    const uint32_t okP = S.okP[slot], okL1 = S.okL1[slot];
+    const uint32_t par1 = S.par1[slot];
     const uint32_t nl0 = S.nl0[slot];
     int p1 = -1, p2 = -1, l1 = -1, l2 = -1;
-    bool class0 = true;
-    uint32_t li;
-    if (r < nl0) li = r;
-    else {
-        // non-empty pattern set: singles in S1, then pairs (high end in S1, low end any budgeted column below)
-        class0 = false;
+    uint32_t li = r;
+    uint32_t extra = 0;                    // E(hi) of the chosen pattern high end
+    if (r >= nl0) {
         r -= nl0;
-        const uint32_t nlall = S.nlall[slot];
-        uint32_t pi = r / nlall;           // 0-based index among the non-empty pattern sets
-        li = r - pi * nlall;
-        const uint32_t S1 = okP & S.parP[slot];
-        const uint32_t ns = __popc(S1);
-        uint32_t pm = S1;
-        if (pi >= ns) {
-            pi -= ns;
-            for (uint32_t m = S1; m; m &= m - 1) {
-                const int hi = __ffs(m) - 1;
-                pm = okP & below(hi);
-                const uint32_t k = __popc(pm);
-                if (pi < k) { p2 = hi; break; }
-                pi -= k;
-            }
+        int hi = 0;
+        uint32_t lows = 0, width = 1;
+        for (uint32_t m = okP & S.parP[slot]; m; m &= m - 1) {
+            hi = __ffs(m) - 1;
+            lows = okP & below(hi);
+            extra = okL1 & ~par1 & below(hi);
+            width = nl0 + __popc(extra);
+            const uint32_t blk = (1u + __popc(lows)) * width;
+            if (r < blk) break;
+            r -= blk;
         }
-        p1 = nth_bit(pm, pi);
+        const uint32_t pi = r / width;
+        li = r - pi * width;
+        if (pi == 0) p1 = hi;
+        else { p2 = hi; p1 = nth_bit(lows, pi - 1); }
     }
-    if (li > 0) {
+    if (li >= nl0) l1 = nth_bit(extra, li - nl0);
+    else if (li > 0) {
         --li;
-        // class 0 enumerates only multisets whose loop parents already exist; otherwise every
-        // multiset within the column budgets (parents may come from the pattern ends of this row)
-        const uint32_t M1 = class0 ? (okL1 & S.par1[slot]) : okL1;
-        const uint32_t M2 = class0 ? (okL2 & S.par2[slot]) : okL2;
+        const uint32_t M1 = okL1 & par1;
+        const uint32_t M2 = S.okL2[slot] & S.par2[slot];
         const uint32_t n1 = __popc(M1), n2 = __popc(M2);
         uint32_t lm = M1;                  // mask the low (or only) end is drawn from, and its rank in it
         bool dbl = false;
@@ -300,15 +305,8 @@ __device__ __forceinline__ uint32_t light_test(const GroupShared &S, int a, int 
     bool feas = true;
     const int nl = (l1 >= 0) + (l2 >= 0);
     const int lhi = l2 >= 0 ? l2 : l1;
-    if (!class0 && nl) {
-        const int need = (l2 == l1) ? 2 : 1;
-        const uint32_t cbh = S.colb[lhi][slot];
-        const bool root = (a == 0 && lhi == (int)S.n[slot] - 1);
-        const int par = (int)(cbh & 3) + (int)((cbh >> 2) & 3) + (p1 > lhi) + (p2 > lhi);
-        feas = root || par >= need;
-    }
     const int pmax = p2 >= 0 ? p2 : p1;
-    if (nl == 2 && pmax > lhi) feas = false;     // a pattern end right of both loop entries
+    if (nl == 2 && pmax > lhi) feas = false;     // a pattern end right of both loop entries (rows 4/5)
     const uint32_t tm = S.tmask[slot];
     if (feas && tm) {
         const int hits = (p1 >= 0 && ((tm >> p1) & 1)) + (p2 >= 0 && ((tm >> p2) & 1)) +
@@ -362,7 +360,7 @@ k_expand(LevelArgs A_param)
             slack = A.limit[hd.z] - hd.x;
             // heuristic band (the beam only feeds the incumbent): a child may exceed its parent's f by
             // beam_delta, or by half of what is left up to the current limit if that is more
-            if (A.beam_delta >= 0) slack = min(slack, hd.y - hd.x + max(A.beam_delta, (A.limit[hd.z] - hd.y) >> 1));
+            if (A.beam_delta >= 0) slack = min(slack, hd.y - hd.x + max(A.beam_delta, (A.limit[hd.z] - hd.y) >> A.beam_shift));
             S.pidx[lane] = pidx; S.score[lane] = hd.x; S.prob[lane] = hd.z; S.ptgs[lane] = hd.w;
             S.slack[lane] = slack; S.n[lane] = (uint8_t)my_n;
             S.tmask[lane] = P->has_tgs ? P->tgs_mask[a] : 0u;
@@ -393,19 +391,17 @@ k_expand(LevelArgs A_param)
         }
         uint32_t total = 0;
         if (have && my_n > a && slack >= 0) {
-            // pattern sets: {} + singles in S1 + pairs (hi in S1, lo any okP column below hi)
-            const uint32_t S1 = okP & parP;
-            uint32_t nps = 1 + __popc(S1);
-            for (uint32_t m = S1; m; m &= m - 1) nps += __popc(okP & below(__ffs(m) - 1));
-            // loop multisets whose parents already exist (class 0)
+            // class-0 loop multisets (parents already exist): {}, singles, doubles, pairs
             const uint32_t A1 = okL1 & par1, A2 = okL2 & par2;
             uint32_t nl0 = 1 + __popc(A1) + __popc(A2);
             for (uint32_t m = A1; m; m &= m - 1) nl0 += __popc(okL1 & below(__ffs(m) - 1));
-            // every multiset within budget: singles, doubles, pairs
-            uint32_t nlall = 1 + __popc(okL1) + __popc(okL2);
-            for (uint32_t m = okL1; m; m &= m - 1) nlall += __popc(okL1 & below(__ffs(m) - 1));
-            S.nl0[lane] = nl0; S.nlall[lane] = nlall;
-            total = nl0 + (nps - 1) * nlall;
+            S.nl0[lane] = nl0;
+            total = nl0;
+            // one block per pattern high end (see light_test)
+            for (uint32_t m = okP & parP; m; m &= m - 1) {
+                const int hi = __ffs(m) - 1;
+                total += (1u + __popc(okP & below(hi))) * (nl0 + __popc(okL1 & ~par1 & below(hi)));
+            }
         }
         S.okP[lane] = okP; S.parP[lane] = parP; S.okL1[lane] = okL1; S.okL2[lane] = okL2;
         S.par1[lane] = par1; S.par2[lane] = par2; S.covC[lane] = covC; S.fbC[lane] = fbC;
@@ -549,6 +545,11 @@ __global__ void k_dedup(DedupArgs A)
 {
     uint32_t cnt = min(*A.count, A.cap);
     const uint32_t gen = *A.gen_base + A.gen_off;
+    // use only as much of the table as this level needs (>= 4 slots per record), so that small
+    // levels stay L2 resident; generation stamps make whatever is left there harmless
+    uint32_t tmask = 1023u;
+    while (tmask < A.tmask && (tmask >> 2) < cnt) tmask = (tmask << 1) | 1u;
+    tmask = min(tmask, A.tmask);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         uint8_t *rec = A.recs + (size_t)i * A.stride;
         NodeHdr *h = reinterpret_cast<NodeHdr *>(rec);
@@ -556,7 +557,7 @@ __global__ void k_dedup(DedupArgs A)
         uint32_t hv = mix32((uint32_t)h->prob * 0x9e3779b9u + hdr_tgs(h));
 #pragma unroll
         for (int k = 0; k < 8; ++k) hv = mix32(hv ^ cw[k]) + 0x85ebca6bu * (k + 1);
-        uint32_t slot = hv & A.tmask;
+        uint32_t slot = hv & tmask;
         const unsigned long long mine = ((unsigned long long)gen << 32) | i;
         for (;;) {
             unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&A.table[slot]);
@@ -574,7 +575,7 @@ __global__ void k_dedup(DedupArgs A)
                     continue;
                 } else { hdr_kill(h); break; }
             }
-            slot = (slot + 1) & A.tmask;
+            slot = (slot + 1) & tmask;
         }
     }
 }
@@ -784,6 +785,7 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     beam_ = beam_width > 0 ? beam_width : 8;
     if (const char *e = getenv("AMBI_BEAM_WIDTH")) { int v = atoi(e); if (v > 0) beam_ = v; }   // tuning knobs; results do not depend on them
     if (const char *e = getenv("AMBI_BEAM_DELTA")) beam_delta_ = atoi(e);
+    if (const char *e = getenv("AMBI_BEAM_SHIFT")) beam_shift_ = std::max(0, std::min(8, atoi(e)));
     rank_ = rank; world_ = world > 0 ? world : 1; shard_level_ = shard_level;
     // buffers are sized in bytes for the widest record (n = 32); narrower batches fit more records
     buf_bytes_ = (size_t)cap_base_ * stride_;
@@ -858,7 +860,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     L.children = buf_[cur ^ 1]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
     L.cand_count = d_cand_; L.node_count = d_node_; L.work_counter = c_work; L.overflow = c_over;
     L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = mode == 0 ? EMIT_BEST : EMIT_ALL;
-    L.beam_delta = mode == 1 ? beam_delta_ : -1;
+    L.beam_delta = mode == 1 ? beam_delta_ : -1; L.beam_shift = beam_shift_;
     L.shard_world = shard_world; L.shard_rank = rank_; L.shard_level = shard_level_eff_;
     const bool prof = profile_ && !capturing_;
     if (prof) {
@@ -1047,7 +1049,7 @@ int StageA::run_chunked(bool sharded)
         L.probs = d_probs_; L.parents = pool_ + sg.off; L.plist = list_[0]; L.pcount = c_par;
         L.children = buf_[0]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
         L.cand_count = d_cand_; L.node_count = d_node_; L.work_counter = c_work; L.overflow = c_over;
-        L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = EMIT_ALL; L.beam_delta = -1;
+        L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = EMIT_ALL; L.beam_delta = -1; L.beam_shift = 1;
         L.shard_world = sw; L.shard_rank = rank_; L.shard_level = shard_level_eff_;
         k_expand<<<expand_blocks_, WPB * 32, expand_smem_, stream_>>>(L); ++launches_;
         uint32_t ctr[2] = {0, 0};

@@ -52,6 +52,7 @@ private:
     uint8_t *pool_ = nullptr;
     bool last_sharded_ = false;
     unsigned long long chunked_runs_ = 0;
+    int beam_shift_ = 2;
     int beam_delta_ = 8;          // heuristic band of the incumbent beam (see k_expand)
     int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
     int stride_ = 0, sms_ = 148;
