@@ -69,7 +69,7 @@ EXPORTS = [
     "ambi_abi_version", "ambi_init", "ambi_destroy", "ambi_last_error", "ambi_status_string",
     "ambi_nccl_unique_id", "ambi_comm_init", "ambi_bfb_solve", "ambi_bfb_solve_batch", "ambi_bfb_solve_shard",
     "ambi_bfb_better", "ambi_bfb_construct_dag", "ambi_bfb_first_valid_order", "ambi_bfb_first_valid_order_batch",
-    "ambi_bfb_expand_path", "ambi_batch_upload", "ambi_batch_run", "ambi_batch_fetch", "ambi_batch_free",
+    "ambi_bfb_expand_path", "ambi_bfb_imperfect_fbi", "ambi_batch_upload", "ambi_batch_run", "ambi_batch_fetch", "ambi_batch_free",
     "ambi_ctx_stream", "ambi_ctx_sync", "ambi_ctx_launch_count", "ambi_ctx_set_profile", "ambi_ctx_get_profile",
 ]
 
@@ -105,6 +105,8 @@ def load_library(path: Optional[str] = None):
     lib.ambi_bfb_first_valid_order.argtypes = [vp, C.POINTER(_Dag), C.c_int32, C.POINTER(_OrderResult)]
     lib.ambi_bfb_first_valid_order_batch.argtypes = [vp, C.c_int32, C.POINTER(_Dag), C.POINTER(C.c_int32),
                                                      C.POINTER(_OrderResult)]
+    lib.ambi_bfb_imperfect_fbi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                           C.c_int32]
     lib.ambi_bfb_expand_path.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32]
     lib.ambi_batch_upload.argtypes = [vp, C.c_int32, C.POINTER(_Problem), C.POINTER(vp)]
     lib.ambi_batch_run.argtypes = [vp, vp]
@@ -379,6 +381,22 @@ def expand_path(bkp: Sequence[int], lib_path: Optional[str] = None) -> List[int]
     out = np.zeros(8192, dtype=np.int32)
     ln = lib.ambi_bfb_expand_path(b.ctypes.data_as(C.POINTER(C.c_int32)), len(b), out.ctypes.data_as(C.POINTER(C.c_int32)), len(out))
     return [int(v) for v in out[:ln]]
+
+
+def imperfect_fbi(bkp: Sequence[int], inversions: dict, lib_path: Optional[str] = None) -> List[int]:
+    """imperfectFBI (LGM:3431-3512) on a breakpoint path; inversions: segment id -> (source id, target id)"""
+    lib = load_library(lib_path)
+    b = np.ascontiguousarray(bkp, dtype=np.int32).copy()
+    mx = max([1] + [abs(int(v)) for v in bkp] + [int(k) for k in inversions.keys()])
+    src = np.zeros(mx + 2, dtype=np.int32)
+    tgt = np.zeros(mx + 2, dtype=np.int32)
+    for k, (s_, t_) in inversions.items():
+        src[int(k)], tgt[int(k)] = s_, t_
+    rc = lib.ambi_bfb_imperfect_fbi(b.ctypes.data_as(C.POINTER(C.c_int32)), len(b), src.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    tgt.ctypes.data_as(C.POINTER(C.c_int32)), mx)
+    if rc != 0:
+        raise AmbiError(rc, "ambi_bfb_imperfect_fbi failed")
+    return [int(v) for v in b]
 
 
 def better(n: int, score_a: int, x_a, score_b: int, x_b, lib_path: Optional[str] = None) -> bool:

@@ -494,3 +494,53 @@ extern "C" int ambi_bfb_expand_path(const int32_t *bkp, int32_t bkp_len, int32_t
     }
     return len;
 }
+
+// imperfectFBI (LGM:3431-3512), host side of Seam B: rewrite fold vertices whose fold-back junction
+// joins two different segments.  inv_src/inv_tgt are indexed by absolute segment id (0 = none) and
+// carry the endpoints of inversions[id] as getJuncCN recorded them (LGM:4014-4048).
+extern "C" int ambi_bfb_imperfect_fbi(int32_t *bkp, int32_t len, const int32_t *inv_src, const int32_t *inv_tgt, int32_t max_id)
+{
+    if (!bkp || len < 0 || (len & 1) || !inv_src || !inv_tgt) return AMBI_ERR_BAD_ARG;
+    auto has = [&](int id) { return id >= 1 && id <= max_id && inv_src[id] != 0; };
+    auto mag = [](int v) { return v < 0 ? -v : v; };
+    int pos = 0;
+    while (pos < len) {
+        int r = len;                                   // first q >= pos+3 holding the complement of bkp[pos]
+        for (int q = pos + 3; q < len; ++q) if (bkp[q] == -bkp[pos]) { r = q; break; }
+        const int l = r - 1;
+        if (r == len || bkp[l] != -bkp[pos + 1]) {     // not the outer pair of a palindrome (LGM:3442-3472)
+            int id = mag(bkp[pos + 1]);
+            if (has(id)) {
+                const int lo = std::min(inv_src[id], inv_tgt[id]), hi = std::max(inv_src[id], inv_tgt[id]);
+                bkp[pos + 1] = bkp[pos + 1] > 0 ? lo : -hi;
+            }
+            if (pos > 0) {
+                id = mag(bkp[pos]);
+                if (has(id) && mag(bkp[pos - 1]) == id) {
+                    const int other = inv_src[id] == id ? inv_tgt[id] : inv_src[id];
+                    bkp[pos] = bkp[pos] > 0 ? other : -other;
+                }
+            }
+            if (bkp[pos] > 0 && mag(bkp[pos]) > mag(bkp[pos + 1])) bkp[pos + 1] = bkp[pos];
+            if (bkp[pos] < 0 && mag(bkp[pos]) < mag(bkp[pos + 1])) bkp[pos + 1] = bkp[pos];
+            pos += 2;
+        } else {                                       // palindrome: walk outwards from its centre (LGM:3473-3509)
+            int p1 = pos + (l - pos) / 2, p2 = p1 + 1;
+            while (p1 >= pos - 1 && p1 > 0) {
+                const int id = mag(bkp[p1]);
+                if (has(id)) {
+                    const int lo = std::min(inv_src[id], inv_tgt[id]), hi = std::max(inv_src[id], inv_tgt[id]);
+                    if (bkp[p1] > 0) { bkp[p1] = lo; bkp[p1 + 1] = -hi; }
+                    else { bkp[p1] = -hi; bkp[p1 + 1] = lo; }
+                    if (p2 != p1 + 1) {
+                        if (p1 > pos - 1) bkp[p2] = -bkp[p1];
+                        bkp[p2 - 1] = -bkp[p1 + 1];
+                    }
+                }
+                p1 -= 2; p2 += 2;
+            }
+            pos = r + 1;
+        }
+    }
+    return AMBI_OK;
+}

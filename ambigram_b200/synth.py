@@ -38,7 +38,8 @@ class SynthSample:
         return "\n".join(" ".join(f"{i}{'+' if d > 0 else '-'}" for (i, d) in comp) for comp in self.juncs_file) + "\n"
 
 
-def generate(n: int, folds: int, seed: int, noise: float = 0.0, with_juncs: bool = False) -> SynthSample:
+def generate(n: int, folds: int, seed: int, noise: float = 0.0, with_juncs: bool = False,
+             imperfect: float = 0.0) -> SynthSample:
     """S = [1+..n+]; each fold appends a prefix of the reverse complement (one breakage-fusion-bridge
     cycle).  Segment CN = occurrences; every adjacent opposite-strand repeat (i,d)->(i,-d) is one copy of a
     fold-back junction.  `noise`: each segment CN +/-1 with that probability (min 1)."""
@@ -58,7 +59,16 @@ def generate(n: int, folds: int, seed: int, noise: float = 0.0, with_juncs: bool
     seg_cn = cn[1:]
     if noise > 0:
         seg_cn = [max(1, x + (rng.choice([-1, 1]) if rng.random() < noise else 0)) for x in seg_cn]
-    juncs = [(i, d, i, -d, v) for (i, d), v in sorted(fb.items())]
+    juncs = []
+    for (i, d), v in sorted(fb.items()):
+        # `imperfect`: with that probability the fold-back junction is reported between two adjacent
+        # segments (what getJuncCN accepts as a fold-back "with error of 2 segments", LGM:4012)
+        if imperfect > 0 and rng.random() < imperfect:
+            if d > 0 and i < n:
+                juncs.append((i, 1, i + 1, -1, v)); continue
+            if d < 0 and i > 1:
+                juncs.append((i, -1, i - 1, 1, v)); continue
+        juncs.append((i, d, i, -d, v))
     jf = None
     if with_juncs:
         jf = []

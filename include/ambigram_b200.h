@@ -179,6 +179,12 @@ int ambi_bfb_first_valid_order(ambi_ctx *ctx, const ambi_dag *dag, int32_t rever
 int ambi_bfb_first_valid_order_batch(ambi_ctx *ctx, int32_t count, const ambi_dag *dags,
                                      const int32_t *reversed, ambi_order_result *results);
 
+/* imperfectFBI (LGM:3431-3512), host bookkeeping for the winning order only: fold
+ * vertices whose junction joins two different segments are rewritten in place.
+ * inv_src/inv_tgt[id] = endpoints of inversions[id] (0 = none), id <= max_id.  */
+int ambi_bfb_imperfect_fbi(int32_t *bkp, int32_t bkp_len, const int32_t *inv_src,
+                           const int32_t *inv_tgt, int32_t max_id);
+
 /* Expand breakpoint pairs to the vertex path (LGM:3661-3670); returns length. */
 int ambi_bfb_expand_path(const int32_t *bkp, int32_t bkp_len, int32_t *path_out, int32_t cap);
 

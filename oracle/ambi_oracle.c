@@ -867,3 +867,61 @@ int orc_solve_batch(int count, const int32_t *n, const int32_t *off, const int32
     }
     return bad;
 }
+
+/* ------------------------------------------------------------------ */
+/* imperfectFBI (LGM:3431-3512)                                        */
+/* ------------------------------------------------------------------ */
+/* A fold-back junction may join two different (adjacent) segments; after the
+ * breakpoint path is assembled the reference rewrites the fold vertices to the
+ * junction's real endpoints.  bkp holds signed ids; inversions[id] is given as
+ * inv_src[id] / inv_tgt[id] (source / target segment id of that junction, 0 if
+ * the segment has none), as recorded by getJuncCN (LGM:4014-4048).             */
+void orc_imperfect_fbi(int32_t *B, int32_t len, const int32_t *inv_src, const int32_t *inv_tgt, int32_t max_id)
+{
+#define HAS(id) ((id) >= 1 && (id) <= max_id && inv_src[(id)] != 0)
+    int pos = 0;
+    while (pos < len) {
+        /* r = find(pos+3, end, complement(*pos)), LGM:3439 (guarded: pos+3 may pass the end) */
+        int r = len;
+        for (int q = pos + 3; q < len; q++) if (B[q] == -B[pos]) { r = q; break; }
+        int l = r - 1;
+        if (r == len || B[l] != -B[pos + 1]) {                     /* LGM:3442-3472 */
+            int id = abs(B[pos + 1]);
+            if (HAS(id)) {
+                int s = inv_src[id], t = inv_tgt[id];
+                if (B[pos + 1] > 0) B[pos + 1] = s < t ? s : t;     /* smaller id, '+' */
+                else B[pos + 1] = -(s < t ? t : s);                 /* larger id, '-'  */
+            }
+            if (pos > 0) {
+                id = abs(B[pos]);
+                if (HAS(id) && abs(B[pos - 1]) == id) {
+                    int other = inv_src[id] == id ? inv_tgt[id] : inv_src[id];
+                    B[pos] = B[pos] > 0 ? other : -other;
+                }
+            }
+            if (B[pos] > 0 && abs(B[pos]) > abs(B[pos + 1])) B[pos + 1] = B[pos];   /* adjustment */
+            if (B[pos] < 0 && abs(B[pos]) < abs(B[pos + 1])) B[pos + 1] = B[pos];
+            pos += 2;
+        } else {                                                   /* LGM:3473-3509 */
+            int p1 = pos + (l - pos) / 2, p2 = p1 + 1;
+            while (p1 >= pos - 1 && p1 > 0) {
+                int id = abs(B[p1]);
+                if (HAS(id)) {
+                    int s = inv_src[id], t = inv_tgt[id];
+                    if (B[p1] > 0) {
+                        if (s < t) { B[p1] = s; B[p1 + 1] = -t; } else { B[p1] = t; B[p1 + 1] = -s; }
+                    } else {
+                        if (s < t) { B[p1] = -t; B[p1 + 1] = s; } else { B[p1] = -s; B[p1 + 1] = t; }
+                    }
+                    if (p2 != p1 + 1) {
+                        if (p1 > pos - 1) B[p2] = -B[p1];
+                        B[p2 - 1] = -B[p1 + 1];
+                    }
+                }
+                p1 -= 2; p2 += 2;
+            }
+            pos = r + 1;
+        }
+    }
+#undef HAS
+}

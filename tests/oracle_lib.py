@@ -177,3 +177,16 @@ def solve_batch(problems, threads: int = 0):
         raise RuntimeError(f"orc_solve_batch: {bad} problems failed")
     xs = [x[xoff[i]:xoff[i] + problems[i].n * (problems[i].n + 1)] for i in range(cnt)]
     return xs, score, cand
+
+
+def imperfect_fbi(bkp: Sequence[int], inversions: dict) -> List[int]:
+    """imperfectFBI (LGM:3431-3512); inversions: segment id -> (source id, target id)"""
+    b = _arr(bkp).copy()
+    mx = max([1] + [abs(int(v)) for v in bkp] + list(inversions.keys()))
+    src = np.zeros(mx + 2, dtype=np.int32)
+    tgt = np.zeros(mx + 2, dtype=np.int32)
+    for k, (s_, t_) in inversions.items():
+        src[k], tgt[k] = s_, t_
+    lib().orc_imperfect_fbi.restype = None
+    lib().orc_imperfect_fbi(b.ctypes.data_as(I32P), len(b), src.ctypes.data_as(I32P), tgt.ctypes.data_as(I32P), mx)
+    return [int(v) for v in b]

@@ -90,3 +90,25 @@ def test_synth_generator_is_seeded_and_parses():
     assert s1.lh_text() == s2.lh_text()
     p = lh.problem_from_lh(s1.lh_text())
     assert p.n == 12 and sum(p.seg_cn2) // 2 == len(s1.string)
+
+
+def test_imperfect_fbi_matches_oracle_on_golden_cases():
+    import json
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "cases.json")))["cases"]
+    seen = 0
+    for c in cases:
+        g = lh.parse_lh(c["lh"])
+        part = lh.flatten(g, lh.read_components(g, c["juncs"]) if c["juncs"] else [], c["junc_info"])[0]
+        x = np.zeros(c["n"] * (c["n"] + 1), dtype=np.int32)
+        for i, v in c["oracle_x_nz"]:
+            x[i] = v
+        d = orc.construct_dag(c["n"], c["start_id"], x)
+        ok, _, _, bkp, _ = orc.first_valid_order(d, False)
+        if not ok:
+            continue
+        a, b = capi.imperfect_fbi(bkp, part.inversions), orc.imperfect_fbi(bkp, part.inversions)
+        assert a == b
+        seen += a != list(bkp)
+        if d.k <= 16 and c["ref_inject_paths"]:
+            assert capi.format_path(capi.expand_path(a)) == c["ref_inject_paths"][0]
+    assert seen >= 5        # the imperfect_* fixtures really exercise the rewrite

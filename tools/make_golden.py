@@ -122,7 +122,7 @@ def make_case(name, lh_text, juncs_text="", junc_info=False, want_highs=True, rn
     assert len(parts) == 1 and parts[0].problem is not None, name
     p = parts[0].problem
     nv = p.n * (p.n + 1)
-    case = {"name": name, "lh": lh_text, "juncs": juncs_text, "junc_info": junc_info,
+    case = {"name": name, "inversions": {str(k): list(v) for k, v in parts[0].inversions.items()}, "lh": lh_text, "juncs": juncs_text, "junc_info": junc_info,
             "n": p.n, "seg_cn2": list(p.seg_cn2), "fbi_cn2": list(p.fbi_cn2), "loop_ub": p.effective_loop_ub(),
             "bias": p.bias, "tgs_pairs": list(p.tgs_pairs), "start_id": p.start_id}
     x, st = orc.solve(p, want_unique=True)
@@ -150,7 +150,26 @@ def make_case(name, lh_text, juncs_text="", junc_info=False, want_highs=True, rn
     return case
 
 
+def extra_imperfect():
+    """cases whose fold-back junctions join two adjacent segments (imperfectFBI, bias > 1); appended to
+    an existing cases.json"""
+    out = os.path.join(ROOT, "tests", "golden", "cases.json")
+    doc = json.load(open(out))
+    doc["cases"] = [c for c in doc["cases"] if not c["name"].startswith("imperfect_")]
+    rng = random.Random(11)
+    for n, folds, k in [(5, 3, 4), (6, 3, 4), (8, 3, 4), (10, 4, 3), (12, 4, 3)]:
+        for seed in range(k):
+            s = synth.generate(n, folds, 50 + seed, 0.0, imperfect=0.6)
+            c = make_case(f"imperfect_n{n}_f{folds}_s{seed}", s.lh_text(), rng=rng)
+            doc["cases"].append(c)
+            print(c["name"], c["oracle_score2"], c.get("ref_highs_objective"), c["bias"], c["ref_inject_paths"][:1], flush=True)
+    json.dump(doc, open(out, "w"), indent=0)
+    print("wrote", out, len(doc["cases"]), "cases")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "imperfect":
+        return extra_imperfect()
     cases = []
     rng = random.Random(7)
     readme = open(os.path.join(ROOT, "tests", "golden", "readme6.lh")).read()
