@@ -167,9 +167,30 @@ def extra_imperfect():
     print("wrote", out, len(doc["cases"]), "cases")
 
 
+def extra_indel():
+    """cases with a deletion / duplication junction inside the partition (getIndelBias before the
+    search, indelBFB after it): the reference prints a second path line"""
+    out = os.path.join(ROOT, "tests", "golden", "cases.json")
+    doc = json.load(open(out))
+    doc["cases"] = [c for c in doc["cases"] if not c["name"].startswith("indel_")]
+    rng = random.Random(13)
+    for n, folds, seed, extra in [(6, 3, 0, "JUNC H:2:+ H:4:+ 15.0 1.0 U B"), (8, 3, 1, "JUNC H:3:+ H:5:+ 15.0 1.0 U B"),
+                                  (8, 3, 2, "JUNC H:6:- H:4:- 15.0 1.0 U B"), (10, 4, 3, "JUNC H:5:+ H:4:+ 15.0 1.0 U B"),
+                                  (12, 4, 5, "JUNC H:7:+ H:9:+ 15.0 1.0 U B"), (12, 4, 6, "JUNC H:4:+ H:3:+ 15.0 1.0 U B")]:
+        s = synth.generate(n, folds, seed, 0.0)
+        text = s.lh_text() + extra + "\n"
+        c = make_case(f"indel_n{n}_s{seed}", text, rng=rng)
+        doc["cases"].append(c)
+        print(c["name"], c["oracle_score2"], c.get("ref_highs_objective"), c["seg_cn2"], c["ref_inject_paths"], flush=True)
+    json.dump(doc, open(out, "w"), indent=0)
+    print("wrote", out, len(doc["cases"]), "cases")
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "imperfect":
         return extra_imperfect()
+    if len(sys.argv) > 1 and sys.argv[1] == "indel":
+        return extra_indel()
     cases = []
     rng = random.Random(7)
     readme = open(os.path.join(ROOT, "tests", "golden", "readme6.lh")).read()
