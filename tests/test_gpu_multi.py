@@ -40,6 +40,12 @@ def _worker(rank, world, port, out_dir):
         s = ctx.solve(p)
         x, st = orc.solve(p, want_unique=False)
         ok &= s.status == 0 and s.score2 == st.score2 and np.array_equal(s.element_cn, x)
+    # BASELINE config 3: n=20 / 6 folds with .juncs and --junc_info true, prefix-sharded
+    sm = synth.generate(20, 6, 3, 0.0, with_juncs=True)
+    p = lh.problem_from_lh(sm.lh_text(), sm.juncs_text(), True)
+    s = ctx.solve(p)
+    x, st = orc.solve(p, want_unique=False)
+    ok &= s.status == 0 and s.score2 == st.score2 and np.array_equal(s.element_cn, x)
     open(os.path.join(out_dir, f"rank{rank}.ok"), "w").write("1" if ok else "0")
     ctx.close()
     dist.destroy_process_group()

@@ -197,3 +197,45 @@ def test_overflow_is_reported_loudly(monkeypatch):
 def test_bad_arguments(ctx):
     with pytest.raises(capi.AmbiError):
         ctx.solve(Problem(n=33, seg_cn2=[2] * 33, fbi_cn2=[0] * 33))
+
+
+def test_config3_n20_with_juncs_vs_oracle(ctx):
+    """BASELINE config 3: n=20 / 6 folds with a .juncs file and --junc_info true (third-generation row)"""
+    for seed in (3, 5, 8):
+        sm = synth.generate(20, 6, seed, 0.0, with_juncs=True)
+        p = lh.problem_from_lh(sm.lh_text(), sm.juncs_text(), True)
+        assert p.junc_info and len(p.tgs_pairs) > 0
+        check_against_oracle(p, ctx.solve(p))
+
+
+def test_config4_n30_noisy_vs_oracle(ctx):
+    """BASELINE config 4: n=30 / 8 folds, CN noise +-1 w.p. 0.5 (two seeds the oracle finishes in seconds)"""
+    for seed in (0, 1):
+        p = lh.problem_from_lh(synth.generate(30, 8, seed, 0.5).lh_text())
+        check_against_oracle(p, ctx.solve(p))
+
+
+def test_config5_sweep_properties():
+    """BASELINE config 5 at full segment counts (n in 10..25, folds = ceil(n/3.5)): size-independent
+    properties instead of the oracle -- the returned assignment satisfies every row of the reference
+    model with exactly the reported score, never exceeds the incumbent, and is identical
+    under a different beam width and under tiny buffers (chunked depth-first pass)."""
+    rng = random.Random(21)
+    probs = []
+    for s in range(96):
+        n = rng.randint(10, 25)
+        probs.append(lh.problem_from_lh(synth.generate(n, synth.folds_for(n), 9000 + s, 0.0).lh_text()))
+    with capi.Context(device=0) as c:
+        a = c.solve_batch(probs)
+    for p, s in zip(probs, a):
+        ok, s2 = orc.model_eval(p, s.element_cn)
+        assert s.status == 0 and ok and s2 == s.score2 and s.score2 <= s.incumbent_score2
+        assert s.score2 <= sum(p.seg_cn2) + sum(p.fbi_cn2)
+    with capi.Context(device=0, beam_width=64, node_capacity=200000) as c:
+        b = c.solve_batch(probs)
+    for s, t in zip(a, b):
+        assert s.score2 == t.score2 and np.array_equal(s.element_cn, t.element_cn)
+    # the small ones also against the oracle
+    for p, s in zip(probs, a):
+        if p.n <= 16:
+            check_against_oracle(p, s)
