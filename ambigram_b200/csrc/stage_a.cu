@@ -120,18 +120,20 @@ __device__ __forceinline__ int child_bound(const GroupShared &S, int slot, int j
                                            int p1, int p2, int l1, int l2, int budget, bool active)
 {
     int lb = 0, cov = 0, capsum = 0;
+    // ends at or below the current column (the walk goes right to left, every end is < jtop)
+    int rp_le = (p1 >= 0) + (p2 >= 0), rl_le = (l1 >= 0) + (l2 >= 0);
 #pragma unroll 2
     for (int j = jtop - 1; j > a; --j) {
         const uint32_t cb = S.colb[j][slot];
         const uint32_t cjw = S.cj[j][slot];
         const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = (cb >> 6) & 3;
         const int pab = (j == p1) + (j == p2), lab = (j == l1) + (j == l2);
-        const int rp = (p1 >= 0 && p1 < j) + (p2 >= 0 && p2 < j);
-        const int rl = (l1 >= 0 && l1 < j) + (l2 >= 0 && l2 < j);
-        const int kP = 2 - pab - max(rp, rl);
-        const int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
+        const int rp = rp_le - pab, rl = rl_le - lab;          // ends strictly below column j
+        rp_le = rp; rl_le = rl;
+        const int kP = 2 - pab - max(rp, rl);                   // rows 2, 5a at (a,j)
+        const int kL = 2 - max(lab + rl, pab + max(rl, rp));    // rows 4a, 4b, 5b
         const int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
-        const int cap = min(nbP, 2) + 2 * min(nbL, 2);
+        const int cap = nbP + 2 * nbL;                          // both already <= 2
         const int wn = nP + 2 * nL + pab + 2 * lab;
         cov += wn; capsum += cap;
         const int fmax = min(6 * (j - a), capsum);
@@ -333,7 +335,7 @@ k_expand(LevelArgs A_param)
     const int lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int a = A.level;
-    const uint32_t pcount = *A.pcount;
+    const uint32_t pcount = min(*A.pcount, A.cap);
     // records per warp group: spread a small frontier over all resident warps
     const uint32_t nwarps = gridDim.x * WPB;
     const uint32_t grp_n = min((uint32_t)GRP, max(1u, (pcount + 4 * nwarps - 1) / (4 * nwarps)));   // >= 4 groups per warp when possible
@@ -352,12 +354,16 @@ k_expand(LevelArgs A_param)
         int my_n = 0, slack = -1, lmax = 0;
         S.best[lane] = ~0ull; S.cnt[lane] = 0;
         if (have) {
-            const uint32_t pidx = A.plist[base + lane];
+            // no list: the frontier is the previous level's child buffer itself, minus the records the
+            // merge dropped (their header is flagged) and the completed assignments (n == level)
+            const uint32_t pidx = A.plist ? A.plist[base + lane] : base + lane;
             prec = A.parents + (size_t)pidx * A.stride;
-            const int4 hd = reinterpret_cast<const int4 *>(prec)[2];       // score, f, prob, tgs
+            int4 hd = reinterpret_cast<const int4 *>(prec)[2];             // score, f, prob, tgs
+            const bool dropped = (uint32_t)hd.w & 0x80000000u;
+            hd.w &= 0x7fffffff;
             P = &A.probs[hd.z];
             my_n = P->n; lmax = P->lmax;
-            slack = A.limit[hd.z] - hd.x;
+            slack = dropped ? -1 : A.limit[hd.z] - hd.x;
             // heuristic band (the beam only feeds the incumbent): a child may exceed its parent's f by
             // beam_delta, or by half of what is left up to the current limit if that is more
             if (A.beam_delta >= 0) slack = min(slack, hd.y - hd.x + max(A.beam_delta, (A.limit[hd.z] - hd.y) >> A.beam_shift));
@@ -597,6 +603,7 @@ struct FinalizeArgs {
     int stride;
     int level;
     int merge_best;             // chunked mode: keep the better of (stored best, this chunk's best)
+    int build_list;             // append the surviving open records to next_list (else expand reads the buffer itself)
 };
 
 __global__ void k_finalize(FinalizeArgs A)
@@ -628,7 +635,7 @@ __global__ void k_finalize(FinalizeArgs A)
             }
         } else {
             if (A.fmin) atomicMin(&A.fmin[h->prob], h->f);
-            else { uint32_t s = atomicAdd(A.next_count, 1u); A.next_list[s] = i; }
+            else if (A.build_list) { uint32_t s = atomicAdd(A.next_count, 1u); A.next_list[s] = i; }
         }
     }
 }
@@ -838,6 +845,10 @@ int StageA::upload(const DevProblem *host_probs, int count)
     for (int i = 0; i < count; ++i) nmax = std::max(nmax, (int)host_probs[i].n);
     if (nmax != nmax_ && graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
     nmax_ = nmax;
+    uint32_t leaf = 0;
+    for (int i = 0; i < count; ++i) if (host_probs[i].n >= 2) leaf |= 1u << (host_probs[i].n - 1);
+    if (leaf != leaf_levels_ && graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    leaf_levels_ = leaf;
     stride_ = (int)ambi_node_stride(nmax_);
     cap_ = (uint32_t)std::min<uint64_t>(cap_max_, buf_bytes_ / stride_);
     if ((uint64_t)count > cap_) { snprintf(err_, sizeof err_, "batch of %d partitions exceeds node capacity %u", count, cap_); return -5; }
@@ -856,7 +867,10 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     uint32_t *c_cur = counters_ + CTR_FRONT + level, *c_nxt = counters_ + CTR_FRONT + level + 1;
     const bool merge = mode != 0;
     LevelArgs L;
-    L.probs = d_probs_; L.parents = buf_[cur]; L.plist = list_[cur]; L.pcount = c_cur;
+    // level 0 and the beam pass read an index list; otherwise the previous level's children are the frontier
+    const bool listed = level == 0 || mode == 1;
+    L.probs = d_probs_; L.parents = buf_[cur]; L.plist = listed ? list_[cur] : nullptr;
+    L.pcount = listed ? c_cur : counters_ + CTR_CHILD + level - 1;
     L.children = buf_[cur ^ 1]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
     L.cand_count = d_cand_; L.node_count = d_node_; L.work_counter = c_work; L.overflow = c_over;
     L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = mode == 0 ? EMIT_BEST : EMIT_ALL;
@@ -881,8 +895,9 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     F.next_list = list_[cur ^ 1]; F.next_count = c_nxt;
     F.best_score = mode == 2 ? d_best_score_ : d_beam_score_; F.best_rows = mode == 2 ? d_best_rows_ : d_beam_rows_;
     F.fmin = beam ? d_fmin_ + (size_t)level * count_ : nullptr; F.stride = stride_; F.level = level;
-    F.limit = nullptr; F.merge_best = 0;
-    k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_;
+    F.limit = nullptr; F.merge_best = 0; F.build_list = 0;
+    // outside the beam pass this kernel only collects completed assignments: skip the levels where no problem ends
+    if (beam || ((leaf_levels_ >> level) & 1u)) { k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_; }
     if (beam) {
         BeamArgs B;
         B.probs = d_probs_; B.recs = buf_[cur ^ 1]; B.count = c_child; B.cap = cap_;
@@ -1073,7 +1088,7 @@ int StageA::run_chunked(bool sharded)
         FinalizeArgs F;
         F.probs = d_probs_; F.recs = buf_[0]; F.count = c_child; F.cap = cap_;
         F.next_list = list_[1]; F.next_count = c_next; F.best_score = d_best_score_; F.best_rows = d_best_rows_;
-        F.fmin = nullptr; F.limit = d_limit_; F.stride = stride_; F.level = level; F.merge_best = 1;
+        F.fmin = nullptr; F.limit = d_limit_; F.stride = stride_; F.level = level; F.merge_best = 1; F.build_list = 1;
         k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_;
         uint32_t nnext = 0;
         CK(cudaMemcpyAsync(&nnext, c_next, 4, cudaMemcpyDeviceToHost, stream_));

@@ -56,6 +56,7 @@ private:
     int beam_delta_ = 8;          // heuristic band of the incumbent beam (see k_expand)
     int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
     int stride_ = 0, sms_ = 148;
+    uint32_t leaf_levels_ = 0;      // bit a: some problem of the batch has n == a+1
     uint8_t *buf_[2] = {nullptr, nullptr};
     uint32_t *list_[2] = {nullptr, nullptr};
     unsigned long long *table_ = nullptr;
