@@ -789,7 +789,7 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
         cap_base_ = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(recs, 64ull << 20));
     }
     cap_ = cap_base_;
-    beam_ = beam_width > 0 ? beam_width : 8;
+    beam_ = beam_width > 0 ? beam_width : 16;
     if (const char *e = getenv("AMBI_BEAM_WIDTH")) { int v = atoi(e); if (v > 0) beam_ = v; }   // tuning knobs; results do not depend on them
     if (const char *e = getenv("AMBI_BEAM_DELTA")) beam_delta_ = atoi(e);
     if (const char *e = getenv("AMBI_BEAM_SHIFT")) beam_shift_ = std::max(0, std::min(8, atoi(e)));

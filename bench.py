@@ -215,6 +215,26 @@ def main():
     sols = batch.fetch()
     t_best = statistics.mean(s.seconds_to_best for s in sols)
 
+    # ---- Stage B on the same batch (first valid topological order per partition) and single-.lh latency
+    dags = [capi.construct_dag(p.n, p.start_id, s.element_cn) for p, s in zip(problems, sols)]
+    ctx.first_valid_order_batch(dags[:64], [False] * 64)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    orders = ctx.first_valid_order_batch(dags, [False] * len(dags))
+    stage_b_s = time.perf_counter() - t0
+    stage_b = {"dags": len(dags), "seconds": stage_b_s, "partitions_per_s": len(dags) / stage_b_s,
+               "placements_per_s": sum(o.orders_tested for o in orders) / stage_b_s,
+               "found": sum(1 for o in orders if o.found), "note": "host wall clock around ambi_bfb_first_valid_order_batch (H2D + kernel + D2H)"}
+    one = problems[0]
+    for _ in range(3):
+        ctx.solve(one)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ctx.solve(one)
+    single_ms = (time.perf_counter() - t0) / 20 * 1e3
+    batch.free()
+    batch = ctx.upload(problems)
+
     # ---- roofline pass: per-launch duration of the dominant kernel (k_expand) ----
     ctx.set_profile(True)
     batch.run(); ctx.sync(); batch.fetch()
@@ -278,7 +298,7 @@ def main():
                         "h2d_bytes_per_step": args.batch * 416 * world, "d2h_bytes_per_step": args.batch * 156 * world},
                 "gpu_launches": launches_all,
                 "candidates_per_step": cand_all, "records_expanded_per_step": nodes_per_step, "problems_per_s": args.batch * world / (ms_per_step * 1e-3),
-                "time_to_best_ms_per_lh": 1e3 * t_best,
+                "time_to_best_ms_per_lh": 1e3 * t_best, "single_lh_solve_ms": single_ms, "stage_b": stage_b,
                 "roofline": roof, "roofline_int32": roof_int, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(problems)

@@ -60,7 +60,7 @@ typedef struct {
     int32_t device;            /* CUDA device ordinal                           */
     int32_t rank;              /* this process' shard (0 if single GPU)         */
     int32_t world;             /* number of shards (1 if single GPU)            */
-    int32_t beam_width;        /* incumbent pass width per problem (0 = 8)      */
+    int32_t beam_width;        /* incumbent pass width per problem (0 = 16)     */
     int64_t node_capacity;     /* candidate records per frontier buffer (0 = auto) */
     int32_t shard_level;       /* rows expanded redundantly before the frontier
                                   is split by prefix across shards (0 = auto)  */
