@@ -69,7 +69,7 @@ EXPORTS = [
     "ambi_abi_version", "ambi_init", "ambi_destroy", "ambi_last_error", "ambi_status_string",
     "ambi_nccl_unique_id", "ambi_comm_init", "ambi_bfb_solve", "ambi_bfb_solve_batch", "ambi_bfb_solve_shard",
     "ambi_bfb_better", "ambi_bfb_construct_dag", "ambi_bfb_first_valid_order", "ambi_bfb_first_valid_order_batch",
-    "ambi_bfb_expand_path", "ambi_bfb_imperfect_fbi", "ambi_batch_upload", "ambi_batch_run", "ambi_batch_fetch", "ambi_batch_free",
+    "ambi_bfb_expand_path", "ambi_bfb_imperfect_fbi", "ambi_bfb_all_valid_orders", "ambi_batch_upload", "ambi_batch_run", "ambi_batch_fetch", "ambi_batch_free",
     "ambi_ctx_stream", "ambi_ctx_sync", "ambi_ctx_launch_count", "ambi_ctx_set_profile", "ambi_ctx_get_profile",
 ]
 
@@ -105,6 +105,9 @@ def load_library(path: Optional[str] = None):
     lib.ambi_bfb_first_valid_order.argtypes = [vp, C.POINTER(_Dag), C.c_int32, C.POINTER(_OrderResult)]
     lib.ambi_bfb_first_valid_order_batch.argtypes = [vp, C.c_int32, C.POINTER(_Dag), C.POINTER(C.c_int32),
                                                      C.POINTER(_OrderResult)]
+    lib.ambi_bfb_all_valid_orders.argtypes = [vp, C.POINTER(_Dag), C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                              C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
     lib.ambi_bfb_imperfect_fbi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                            C.c_int32]
     lib.ambi_bfb_expand_path.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32]
@@ -344,6 +347,21 @@ class Context:
         self._check(self.lib.ambi_bfb_first_valid_order(self.handle, C.byref(dag.raw), int(reversed_), C.byref(res)))
         return OrderResult(bool(res.found), bool(res.used_flipped), list(res.order[:dag.k]),
                            list(res.bkp[:res.bkp_len]), int(res.orders_tested))
+
+    def all_valid_orders(self, dag: Dag, reversed_: bool = False, max_orders: int = 4096):
+        """--all: -> (orders of the initial orientation, orders of the flipped one, their breakpoint paths)"""
+        k = max(dag.k, 1)
+        orders = np.zeros(max_orders * k, dtype=np.int32)
+        bkp = np.zeros(max_orders * 1024, dtype=np.int32)
+        blen = np.zeros(max_orders, dtype=np.int32)
+        n0, n1, tested = C.c_int32(0), C.c_int32(0), C.c_uint64(0)
+        I = C.POINTER(C.c_int32)
+        self._check(self.lib.ambi_bfb_all_valid_orders(self.handle, C.byref(dag.raw), int(reversed_), max_orders,
+                                                       orders.ctypes.data_as(I), bkp.ctypes.data_as(I), 1024, blen.ctypes.data_as(I),
+                                                       C.byref(n0), C.byref(n1), C.byref(tested)))
+        rows = [[int(v) for v in orders[r * k:(r + 1) * k]] for r in range(n0.value + n1.value)]
+        paths = [[int(v) for v in bkp[r * 1024:r * 1024 + blen[r]]] for r in range(n0.value + n1.value)]
+        return rows[:n0.value], rows[n0.value:], paths
 
     def first_valid_order_batch(self, dags: Sequence[Dag], reversed_: Sequence[bool]) -> List[OrderResult]:
         n = len(dags)

@@ -483,6 +483,64 @@ extern "C" int ambi_bfb_first_valid_order(ambi_ctx *ctx, const ambi_dag *dag, in
     return ambi_bfb_first_valid_order_batch(ctx, 1, dag, &reversed, result);
 }
 
+// --all (printAll): every order the reference would print, in its print order.
+// getBFB visits the orders of the initial orientation lexicographically and prints each valid one; if
+// the lexicographically LAST topological order fails there, it flips the orientation and goes through
+// all orders again (LGM:3691-3695), printing the valid ones of the flipped orientation as well.
+extern "C" int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, int32_t max_orders,
+                                         int32_t *orders_out, int32_t *bkp_out, int32_t bkp_stride, int32_t *bkp_len_out,
+                                         int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested)
+{
+    if (!ctx || !dag || !orders_out || !n_initial || !n_flipped || max_orders <= 0) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_all_valid_orders: bad argument");
+    cudaSetDevice(ctx->cfg.device);
+    *n_initial = *n_flipped = 0;
+    unsigned long long tested = 0;
+    const int k = dag->k;
+    if (k <= 0) { if (n_tested) *n_tested = 0; return AMBI_OK; }
+    std::vector<std::vector<int32_t>> first, second, bfirst, bsecond;
+    bool trunc = false;
+    const int fwd0 = reversed ? 0 : 1;
+    int rc = ctx->sb.run_all(*dag, fwd0, max_orders, first, bfirst, &tested, &trunc);
+    if (rc) return fail(ctx, rc == -2 ? AMBI_ERR_TOO_LARGE : AMBI_ERR_CUDA, ctx->sb.error());
+    if (trunc) return fail(ctx, AMBI_ERR_TOO_LARGE, "more valid orders than max_orders");
+    // lexicographically last topological order: always take the highest free index
+    std::vector<int32_t> last;
+    {
+        std::vector<int> indeg(k, 0); std::vector<char> used(k, 0);
+        for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) if ((dag->adj[i] >> j) & 1) indeg[j]++;
+        for (int step = 0; step < k; ++step) {
+            int pick = -1;
+            for (int i = k - 1; i >= 0; --i) if (!used[i] && indeg[i] == 0) { pick = i; break; }
+            if (pick < 0) break;                       // cyclic: no complete order exists
+            used[pick] = 1; last.push_back(pick);
+            for (int j = 0; j < k; ++j) if ((dag->adj[pick] >> j) & 1) indeg[j]--;
+        }
+    }
+    const bool have_orders = (int)last.size() == k;
+    const bool last_valid = have_orders && std::binary_search(first.begin(), first.end(), last);
+    if (have_orders && !last_valid) {
+        rc = ctx->sb.run_all(*dag, 1 - fwd0, max_orders - (int32_t)first.size() > 0 ? max_orders - (int32_t)first.size() : 1, second, bsecond, &tested, &trunc);
+        if (rc) return fail(ctx, AMBI_ERR_CUDA, ctx->sb.error());
+        if (trunc) return fail(ctx, AMBI_ERR_TOO_LARGE, "more valid orders than max_orders");
+    }
+    if ((int64_t)first.size() + (int64_t)second.size() > max_orders) return fail(ctx, AMBI_ERR_TOO_LARGE, "more valid orders than max_orders");
+    size_t o = 0, row = 0;
+    for (auto *lst : {&first, &second}) {
+        const auto &bl = lst == &first ? bfirst : bsecond;
+        for (size_t i = 0; i < lst->size(); ++i, ++row) {
+            for (int32_t x : (*lst)[i]) orders_out[o++] = x;
+            if (bkp_out && bkp_len_out && bkp_stride > 0) {
+                const int len = (int)std::min<size_t>(bl[i].size(), (size_t)bkp_stride);
+                bkp_len_out[row] = len;
+                for (int t = 0; t < len; ++t) bkp_out[row * (size_t)bkp_stride + t] = bl[i][t];
+            }
+        }
+    }
+    *n_initial = (int32_t)first.size(); *n_flipped = (int32_t)second.size();
+    if (n_tested) *n_tested = tested;
+    return AMBI_OK;
+}
+
 extern "C" int ambi_bfb_expand_path(const int32_t *bkp, int32_t bkp_len, int32_t *path_out, int32_t cap)
 {
     // LGM:3661-3670: each pair (first,last) of a monotone run expands to every id in between

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 
 namespace ambi {
 
@@ -232,6 +233,92 @@ k_first_valid_order(const DevDag *dags, DevOrderOut *outs, int count, uint32_t *
     }
 }
 
+
+// --all (printAll, LGM:3672-3685): every order from which the path assembles, in one orientation.
+// Same walk as above without the early exit; each complete order is appended to `orders`
+// (unordered: the host sorts them lexicographically, which is the order the reference prints).
+__global__ void __launch_bounds__(128)
+k_all_valid_orders(const DevDag *dag, int forward, int32_t *orders, int8_t *bkps, int32_t *bkp_lens, uint32_t max_orders,
+                   uint32_t *n_found, unsigned long long *n_tested)
+{
+    __shared__ DevDag s_dag;
+    const int lane = threadIdx.x & 31;
+    const int worker = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // warp id in the grid
+    const int nworkers = gridDim.x * (blockDim.x >> 5) * 32;                    // lanes in the grid
+    const int me = worker * 32 + lane;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(dag);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_dag);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevDag) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const DevDag &D = s_dag;
+    const int k = D.k;
+    if (k <= 0) return;
+    int8_t B[MAXPATH];
+    uint8_t order[MAXK], indeg[MAXK], nexti[MAXK];
+    Undo undo[MAXK];
+    unsigned long long tested = 0;
+    for (int i = 0; i < k; ++i) indeg[i] = 0;
+    for (int i = 0; i < k; ++i) { uint64_t m = D.adj[i]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]++; } }
+    uint64_t visited = 0;
+    int len = 0, t = 0;
+    auto emit = [&]() {
+        uint32_t s = atomicAdd(n_found, 1u);
+        if (s < max_orders) {
+            for (int i = 0; i < k; ++i) orders[(size_t)s * k + i] = order[i];
+            bkp_lens[s] = len;
+            for (int i = 0; i < len; ++i) bkps[(size_t)s * MAXPATH + i] = B[i];
+        }
+    };
+    for (int v0 = 0; v0 < k; ++v0) {
+        if (indeg[v0] != 0) continue;
+        if (k == 1) { if (me == 0) { seed(D, v0, forward != 0, B, len); order[0] = (uint8_t)v0; ++tested; emit(); } break; }
+        { uint64_t m = D.adj[v0]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]--; } }
+        visited |= 1ull << v0;
+        for (int v1 = 0; v1 < k; ++v1) {
+            if (indeg[v1] != 0 || ((visited >> v1) & 1)) continue;
+            const int tt = t++;
+            if (tt % nworkers != me) continue;
+            seed(D, v0, forward != 0, B, len);
+            order[0] = (uint8_t)v0;
+            ++tested;
+            if (!place(D, v1, B, len, undo[1])) continue;
+            order[1] = (uint8_t)v1;
+            if (k == 2) { emit(); continue; }
+            { uint64_t m = D.adj[v1]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]--; } }
+            visited |= 1ull << v1;
+            int d = 2; nexti[2] = 0;
+            while (d >= 2) {
+                int v = nexti[d];
+                while (v < k && (indeg[v] != 0 || ((visited >> v) & 1))) ++v;
+                if (v >= k) {
+                    --d;
+                    if (d < 2) break;
+                    int pv = order[d];
+                    unplace(B, len, undo[d]);
+                    visited &= ~(1ull << pv);
+                    { uint64_t m = D.adj[pv]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]++; } }
+                    continue;
+                }
+                nexti[d] = (uint8_t)(v + 1);
+                ++tested;
+                if (!place(D, v, B, len, undo[d])) continue;
+                order[d] = (uint8_t)v;
+                if (d == k - 1) { emit(); unplace(B, len, undo[d]); continue; }
+                visited |= 1ull << v;
+                { uint64_t m = D.adj[v]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]--; } }
+                ++d; nexti[d] = 0;
+            }
+            visited &= ~(1ull << v1);
+            { uint64_t m = D.adj[v1]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]++; } }
+        }
+        visited &= ~(1ull << v0);
+        { uint64_t m = D.adj[v0]; while (m) { int j = __ffsll((long long)m) - 1; m &= m - 1; indeg[j]++; } }
+    }
+    if (tested) atomicAdd(n_tested, tested);
+}
+
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
     snprintf(err_, sizeof err_, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return -4; } } while (0)
 
@@ -297,6 +384,69 @@ int StageB::run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_o
         for (int v = 0; v < dags[i].k; ++v) r.order[v] = ho[i].order[v];
         for (int v = 0; v < ho[i].bkp_len && v < 1024; ++v) r.bkp[v] = ho[i].bkp[v];
     }
+    return 0;
+}
+
+
+static void to_devdag(const ambi_dag &g, int reversed, DevDag &d)
+{
+    memset(&d, 0, sizeof d);
+    int base = 0x7fffffff;
+    for (int v = 0; v < g.k; ++v) if (g.a[v] < base) base = g.a[v];
+    if (g.k == 0) base = 1;
+    d.k = g.k; d.base = base; d.reversed = reversed;
+    for (int v = 0; v < g.k; ++v) {
+        d.kind[v] = g.kind[v]; d.a[v] = (int8_t)(g.a[v] - base + 1); d.b[v] = (int8_t)(g.b[v] - base + 1);
+        d.cn[v] = (int8_t)g.cn[v]; d.adj[v] = g.adj[v];
+    }
+}
+
+// every valid order of one orientation, sorted lexicographically (the reference's print order)
+int StageB::run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::vector<std::vector<int32_t>> &out,
+                    std::vector<std::vector<int32_t>> &bkp_out, unsigned long long *tested, bool *truncated)
+{
+    out.clear(); bkp_out.clear(); *truncated = false;
+    if (dag.k <= 0) return 0;
+    if (dag.k > MAXK) return -2;
+    if (int rc = ensure(1)) return rc;
+    DevDag h; to_devdag(dag, 0, h);
+    int32_t *d_orders = nullptr, *d_lens = nullptr; uint32_t *d_cnt = nullptr; int8_t *d_bkps = nullptr;
+    CKB(cudaMalloc(&d_orders, (size_t)max_orders * dag.k * sizeof(int32_t)));
+    CKB(cudaMalloc(&d_bkps, (size_t)max_orders * MAXPATH));
+    CKB(cudaMalloc(&d_lens, (size_t)max_orders * sizeof(int32_t)));
+    CKB(cudaMalloc(&d_cnt, 16));
+    CKB(cudaMemsetAsync(d_cnt, 0, 16, stream_));
+    CKB(cudaMemcpyAsync(d_dags_, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
+    k_all_valid_orders<<<sms_, 128, 0, stream_>>>((const DevDag *)d_dags_, forward, d_orders, d_bkps, d_lens, (uint32_t)max_orders, d_cnt,
+                                                   (unsigned long long *)(d_cnt + 2));
+    ++launches_;
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    CKB(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, stream_));
+    CKB(cudaStreamSynchronize(stream_));
+    uint32_t n = cnt[0] < (uint32_t)max_orders ? cnt[0] : (uint32_t)max_orders;
+    *truncated = cnt[0] > (uint32_t)max_orders;
+    std::vector<int32_t> flat((size_t)n * dag.k), lens(n);
+    std::vector<int8_t> paths((size_t)n * MAXPATH);
+    if (n) {
+        CKB(cudaMemcpy(flat.data(), d_orders, flat.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CKB(cudaMemcpy(lens.data(), d_lens, lens.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CKB(cudaMemcpy(paths.data(), d_bkps, paths.size(), cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_orders); cudaFree(d_cnt); cudaFree(d_bkps); cudaFree(d_lens);
+    // the lanes append in any order: sort lexicographically (the order the reference prints)
+    std::vector<uint32_t> perm(n);
+    for (uint32_t i = 0; i < n; ++i) perm[i] = i;
+    std::sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) {
+        return std::lexicographical_compare(flat.begin() + (size_t)x * dag.k, flat.begin() + (size_t)(x + 1) * dag.k,
+                                            flat.begin() + (size_t)y * dag.k, flat.begin() + (size_t)(y + 1) * dag.k); });
+    out.resize(n); bkp_out.resize(n);
+    for (uint32_t q = 0; q < n; ++q) {
+        const uint32_t i = perm[q];
+        out[q].assign(flat.begin() + (size_t)i * dag.k, flat.begin() + (size_t)(i + 1) * dag.k);
+        bkp_out[q].resize(lens[i]);
+        for (int t = 0; t < lens[i]; ++t) { int v = paths[(size_t)i * MAXPATH + t]; bkp_out[q][t] = v > 0 ? v - 1 + h.base : -(-v - 1 + h.base); }
+    }
+    if (tested) *tested += (unsigned long long)cnt[2] | ((unsigned long long)cnt[3] << 32);
     return 0;
 }
 

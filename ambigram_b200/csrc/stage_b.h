@@ -2,6 +2,7 @@
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
+#include <vector>
 #include "../../include/ambigram_b200.h"
 
 namespace ambi {
@@ -14,6 +15,8 @@ public:
     void release();
     // first valid topological order for each DAG (orientation per reversed[i], flipped if none)
     int run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_order_result *results);
+    int run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::vector<std::vector<int32_t>> &out,
+                std::vector<std::vector<int32_t>> &bkp_out, unsigned long long *tested, bool *truncated);
     const char *error() const { return err_; }
     unsigned long long launches() const { return launches_; }
 

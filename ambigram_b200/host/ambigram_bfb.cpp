@@ -15,7 +15,7 @@
 //   printing                        printBFB                    src/LocalGenomicMap.cpp:3411-3429
 // Translocation modes (PROP I1/I2/C1/C2) are out of scope.
 //
-//   ambigram_bfb --op bfb --in_lh X.lh [--juncdb F --junc_info true] [--reversed] [--lp_prefix P]
+//   ambigram_bfb --op bfb --in_lh X.lh [--juncdb F --junc_info true] [--reversed] [--all] [--lp_prefix P]
 //   ambigram_bfb --op bfb --in_list LIST     one .lh path per line: all partitions go through one
 //                                            ambi_bfb_solve_batch / first_valid_order_batch call
 #include "../../include/ambigram_b200.h"
@@ -323,6 +323,7 @@ int main(int argc, char **argv)
     if (opt["op"] != "bfb") { std::cerr << "only --op bfb is supported" << std::endl; return 1; }
     const bool junc_info = opt["junc_info"] == "true" || opt["junc_info"] == "1";
     const bool reversed = opt.count("reversed") > 0;
+    const bool print_all = opt.count("all") > 0;
     auto t0 = std::chrono::steady_clock::now();
 
     std::vector<std::string> files;
@@ -385,7 +386,23 @@ int main(int argc, char **argv)
             ambi_order_result &r = res[wi];
             ilp_error += sols[wi].objective2 / 2.0;
             ++wi;
-            if (r.found) {
+            if (print_all && r.found) {
+                // --all: every valid order in the reference's print order (LGM:3672-3695); `path` keeps the first
+                const int kmax = 4096;
+                std::vector<int32_t> ords((size_t)kmax * std::max(dags[wi - 1].k, 1)), bk((size_t)kmax * 1024), bl(kmax);
+                int32_t n0 = 0, n1 = 0;
+                if (ambi_bfb_all_valid_orders(ctx, &dags[wi - 1], reversed ? 1 : 0, kmax, ords.data(), bk.data(), 1024, bl.data(), &n0, &n1, nullptr) != AMBI_OK) {
+                    std::cerr << "ambi_bfb_all_valid_orders: " << ambi_last_error(ctx) << std::endl; return 1;
+                }
+                for (int q = 0; q < n0 + n1; ++q) {
+                    ambi_bfb_imperfect_fbi(&bk[(size_t)q * 1024], bl[q], p.inv_src.data(), p.inv_tgt.data(), (int32_t)p.inv_src.size() - 2);
+                    std::vector<int32_t> buf(1 << 16);
+                    int len = ambi_bfb_expand_path(&bk[(size_t)q * 1024], bl[q], buf.data(), (int32_t)buf.size());
+                    Path one(buf.begin(), buf.begin() + std::min<int>(len, (int)buf.size()));
+                    if (q == 0) path = one;
+                    std::cout << format_path(one) << std::endl;
+                }
+            } else if (r.found) {
                 ambi_bfb_imperfect_fbi(r.bkp, r.bkp_len, p.inv_src.data(), p.inv_tgt.data(), (int32_t)p.inv_src.size() - 2);
                 std::vector<int32_t> buf(1 << 16);
                 int len = ambi_bfb_expand_path(r.bkp, r.bkp_len, buf.data(), (int32_t)buf.size());

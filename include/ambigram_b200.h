@@ -179,6 +179,17 @@ int ambi_bfb_first_valid_order(ambi_ctx *ctx, const ambi_dag *dag, int32_t rever
 int ambi_bfb_first_valid_order_batch(ambi_ctx *ctx, int32_t count, const ambi_dag *dags,
                                      const int32_t *reversed, ambi_order_result *results);
 
+/* --all (printAll, LGM:3672-3685): every order getBFB would print, in print order:
+ * the valid orders of the initial orientation in lexicographic order, followed --
+ * only if the lexicographically last topological order fails there (LGM:3691-3695)
+ * -- by the valid orders of the flipped orientation.  orders_out holds
+ * (*n_initial + *n_flipped) rows of dag->k node indices; AMBI_ERR_TOO_LARGE if more
+ * than max_orders exist.  Row r's breakpoint path (before imperfectFBI) is
+ * bkp_out[r*bkp_stride .. + bkp_len_out[r]) (both may be NULL).                 */
+int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, int32_t max_orders,
+                              int32_t *orders_out, int32_t *bkp_out, int32_t bkp_stride, int32_t *bkp_len_out,
+                              int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested);
+
 /* imperfectFBI (LGM:3431-3512), host bookkeeping for the winning order only: fold
  * vertices whose junction joins two different segments are rewritten in place.
  * inv_src/inv_tgt[id] = endpoints of inversions[id] (0 = none), id <= max_id.  */

@@ -728,6 +728,7 @@ typedef struct {
     int32_t res[ORC_MAXK]; int depth;
     int found; int32_t order[ORC_MAXK]; int32_t bkp[BKP_MAX]; int32_t bkp_len;
     int64_t tested, valid, cap; int count_mode; int naive;
+    int32_t *collect; int64_t collect_cap;      /* count_mode: every valid order, in visiting (= lexicographic) order */
 } topo_t;
 
 /* allTopologicalOrders (LGM:3380-3409): lowest free index first.  In pruned mode a
@@ -743,6 +744,7 @@ static void topo_rec(topo_t *T)
         T->tested++;
         int placed = orc_assemble_order(d, T->res, T->forward, B, &len);
         if (placed == d->k) {
+            if (T->collect && T->valid < T->collect_cap) memcpy(T->collect + T->valid * d->k, T->res, sizeof(int32_t) * d->k);
             T->valid++;
             if (!T->found) { T->found = 1; memcpy(T->order, T->res, sizeof(int32_t) * d->k); memcpy(T->bkp, B, sizeof(int32_t) * len); T->bkp_len = len; }
         }
@@ -816,6 +818,18 @@ int64_t orc_count_valid_orders(const orc_dag *dag, int forward, int64_t cap, int
     topo_rec(T);
     int64_t v = T->valid;
     if (n_orders) *n_orders = T->tested;
+    free(T);
+    return v;
+}
+
+/* printAll (LGM:3672-3685): every valid order of one orientation, lexicographic; returns the count
+ * (orders beyond cap are counted but not stored). */
+int64_t orc_all_valid_orders(const orc_dag *dag, int forward, int32_t *orders_out, int64_t cap)
+{
+    topo_t *T = malloc(sizeof *T);
+    topo_init(T, dag, forward); T->count_mode = 1; T->collect = orders_out; T->collect_cap = cap;
+    topo_rec(T);
+    int64_t v = T->valid;
     free(T);
     return v;
 }

@@ -190,3 +190,19 @@ def imperfect_fbi(bkp: Sequence[int], inversions: dict) -> List[int]:
     lib().orc_imperfect_fbi.restype = None
     lib().orc_imperfect_fbi(b.ctypes.data_as(I32P), len(b), src.ctypes.data_as(I32P), tgt.ctypes.data_as(I32P), mx)
     return [int(v) for v in b]
+
+
+def all_valid_orders(dag: Dag, forward: bool = True, cap: int = 4096) -> List[List[int]]:
+    lib().orc_all_valid_orders.restype = C.c_int64
+    buf = np.zeros(cap * max(dag.k, 1), dtype=np.int32)
+    n = lib().orc_all_valid_orders(C.byref(dag), int(forward), buf.ctypes.data_as(I32P), C.c_int64(cap))
+    n = min(int(n), cap)
+    return [[int(v) for v in buf[i * dag.k:(i + 1) * dag.k]] for i in range(n)]
+
+
+def assemble_order(dag: Dag, order: Sequence[int], forward: bool = True):
+    o = _arr(order)
+    bkp = (C.c_int32 * 4096)()
+    blen = C.c_int32(0)
+    placed = lib().orc_assemble_order(C.byref(dag), o.ctypes.data_as(I32P), int(forward), bkp, C.byref(blen))
+    return int(placed), list(bkp[:blen.value])

@@ -239,3 +239,25 @@ def test_config5_sweep_properties():
     for p, s in zip(probs, a):
         if p.n <= 16:
             check_against_oracle(p, s)
+
+
+def test_all_valid_orders_matches_reference_print_all(ctx):
+    """--all (printAll): orders, their order, the flip rule and the paths, against the reference's stdout"""
+    seen_multi = 0
+    for c in CASES:
+        if "ref_inject_paths_all" not in c or c["name"].startswith("indel_"):
+            continue
+        part = partition_of(c)
+        p = part.problem
+        x = np.zeros(p.n * (p.n + 1), dtype=np.int32)
+        for i, v in c["oracle_x_nz"]:
+            x[i] = v
+        dag = capi.construct_dag(p.n, p.start_id, x)
+        for rev, key in ((False, "ref_inject_paths_all"), (True, "ref_inject_paths_all_rev")):
+            first, second, paths = ctx.all_valid_orders(dag, rev)
+            got = [capi.format_path(capi.expand_path(capi.imperfect_fbi(b, part.inversions))) for b in paths]
+            assert got == c[key], c["name"]
+            od = orc.construct_dag(p.n, p.start_id, x)
+            assert first == orc.all_valid_orders(od, forward=not rev)
+            seen_multi += len(first) > 1
+    assert seen_multi >= 10

@@ -114,3 +114,48 @@ def test_stage_b_matches_reference_getbfb(case):
         if d.k <= 8:
             ok2, fl2, order2, bkp2, _ = orc.first_valid_order(d, rev, naive_cap=0)
             assert (ok2, fl2, order2, bkp2) == (ok, flipped, order, bkp)
+
+
+ALL_CASES = [c for c in CASES if "ref_inject_paths_all" in c and not c["name"].startswith("indel_")]
+
+
+def reference_print_all(d, part, rev):
+    """what getBFB prints with printAll=true (LGM:3672-3695): valid orders of the initial orientation in
+    lexicographic order, then -- if the lexicographically last order fails there -- those of the flipped one"""
+    first = orc.all_valid_orders(d, forward=not rev)
+    n_all, _ = orc.count_valid_orders(d, forward=not rev)
+    assert n_all == len(first)
+    last = None
+    indeg = [0] * d.k
+    for (i, j) in d.edges():
+        indeg[j] += 1
+    used, order = [False] * d.k, []
+    for _ in range(d.k):
+        pick = next((i for i in range(d.k - 1, -1, -1) if not used[i] and indeg[i] == 0), None)
+        if pick is None:
+            break
+        used[pick] = True
+        order.append(pick)
+        for (i, j) in d.edges():
+            if i == pick:
+                indeg[j] -= 1
+    second = []
+    if len(order) == d.k and order not in first:
+        second = orc.all_valid_orders(d, forward=rev)
+    out = []
+    for fwd, lst in ((not rev, first), (rev, second)):
+        for o in lst:
+            placed, bkp = orc.assemble_order(d, o, fwd)
+            assert placed == d.k
+            out.append(capi.format_path(orc.expand_path(orc.imperfect_fbi(bkp, part.inversions))))
+    return out
+
+
+@pytest.mark.parametrize("case", ALL_CASES, ids=[c["name"] for c in ALL_CASES])
+def test_print_all_matches_reference(case):
+    """--all: every path the reference prints, in its order (forward and --reversed)"""
+    part = partition_of(case)
+    p = part.problem
+    d = orc.construct_dag(p.n, p.start_id, dense(case["oracle_x_nz"], p.n * (p.n + 1)))
+    for rev, key in ((False, "ref_inject_paths_all"), (True, "ref_inject_paths_all_rev")):
+        assert reference_print_all(d, part, rev) == case[key]

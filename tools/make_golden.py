@@ -33,7 +33,7 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "bin")
 PATH_RE = re.compile(r"^\d+[+-](\|{0,2}\d+[+-])*$")
 
 
-def run_ref(lh_text, juncs_text="", junc_info=False, reversed_=False, inject=None):
+def run_ref(lh_text, juncs_text="", junc_info=False, reversed_=False, inject=None, print_all=False):
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "in.lh"), "w").write(lh_text)
         cmd = [REF, "--op", "bfb", "--in_lh", "in.lh", "--lp_prefix", "p"]
@@ -44,6 +44,8 @@ def run_ref(lh_text, juncs_text="", junc_info=False, reversed_=False, inject=Non
             cmd += ["--junc_info", "true"]
         if reversed_:
             cmd += ["--reversed"]
+        if print_all:
+            cmd += ["--all"]
         env = dict(os.environ, PATH=BIN + ":" + os.environ["PATH"])
         if inject is not None:
             with open(os.path.join(d, "inject.txt"), "w") as f:
@@ -186,7 +188,30 @@ def extra_indel():
     print("wrote", out, len(doc["cases"]), "cases")
 
 
+def extra_all():
+    """--all: every path the reference prints (our Stage-A answer injected), forward and --reversed"""
+    out = os.path.join(ROOT, "tests", "golden", "cases.json")
+    doc = json.load(open(out))
+    done = 0
+    for c in doc["cases"]:
+        if len(c["oracle_x_nz"]) > 12:
+            continue
+        nv = c["n"] * (c["n"] + 1)
+        x = [0] * nv
+        for i, v in c["oracle_x_nz"]:
+            x[i] = v
+        for rev in (False, True):
+            rc, paths, sol, lpt, so = run_ref(c["lh"], c["juncs"], c["junc_info"], reversed_=rev, inject=x, print_all=True)
+            c["ref_inject_paths_all_rev" if rev else "ref_inject_paths_all"] = paths
+        done += 1
+        print(c["name"], len(c["ref_inject_paths_all"]), len(c["ref_inject_paths_all_rev"]), flush=True)
+    json.dump(doc, open(out, "w"), indent=0)
+    print("wrote", out, done, "cases with --all output")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "all":
+        return extra_all()
     if len(sys.argv) > 1 and sys.argv[1] == "imperfect":
         return extra_imperfect()
     if len(sys.argv) > 1 and sys.argv[1] == "indel":
