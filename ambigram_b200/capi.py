@@ -363,11 +363,18 @@ class Context:
         paths = [[int(v) for v in bkp[r * 1024:r * 1024 + blen[r]]] for r in range(n0.value + n1.value)]
         return rows[:n0.value], rows[n0.value:], paths
 
-    def first_valid_order_batch(self, dags: Sequence[Dag], reversed_: Sequence[bool]) -> List[OrderResult]:
+    @staticmethod
+    def pack_dags(dags: Sequence[Dag], reversed_: Sequence[bool]):
+        """host arrays of ambi_dag / ambi_order_result for first_valid_order_packed"""
         n = len(dags)
-        arr = (_Dag * n)(*[d.raw for d in dags])
-        rv = (C.c_int32 * n)(*[int(r) for r in reversed_])
-        res = (_OrderResult * n)()
+        return n, (_Dag * n)(*[d.raw for d in dags]), (C.c_int32 * n)(*[int(r) for r in reversed_]), (_OrderResult * n)()
+
+    def first_valid_order_packed(self, packed) -> None:
+        n, arr, rv, res = packed
+        self._check(self.lib.ambi_bfb_first_valid_order_batch(self.handle, n, arr, rv, res))
+
+    def first_valid_order_batch(self, dags: Sequence[Dag], reversed_: Sequence[bool]) -> List[OrderResult]:
+        n, arr, rv, res = self.pack_dags(dags, reversed_)
         self._check(self.lib.ambi_bfb_first_valid_order_batch(self.handle, n, arr, rv, res))
         return [OrderResult(bool(r.found), bool(r.used_flipped), list(r.order[:dags[i].k]), list(r.bkp[:r.bkp_len]),
                             int(r.orders_tested)) for i, r in enumerate(res)]

@@ -334,17 +334,32 @@ extern "C" void ambi_batch_free(ambi_ctx *ctx, ambi_batch *b)
 }
 
 // ---- Seam A ---------------------------------------------------------------
+// rough number of frontier records a partition of n segments needs at its widest level; only used to
+// cut a large mixed batch into sub-batches that fit the candidate buffers (an underestimate is
+// harmless: the level that does not fit is redone by the chunked depth-first pass)
+static double frontier_estimate(int n) { double e = 64.0; for (int i = 12; i < n; ++i) e *= 1.6; return e; }
+
 extern "C" int ambi_bfb_solve_batch(ambi_ctx *ctx, int32_t count, const ambi_bfb_problem *problems,
                                     ambi_bfb_solution *solutions)
 {
-    if (!ctx || !solutions) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_solve_batch: bad argument");
-    ambi_batch *b = nullptr;
-    int rc = ambi_batch_upload(ctx, count, problems, &b);
-    if (rc) return rc;
-    rc = ambi_batch_run(ctx, b);
-    if (!rc) rc = ambi_batch_fetch(ctx, b, solutions);
-    ambi_batch_free(ctx, b);
-    return rc;
+    if (!ctx || !solutions || !problems || count <= 0) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_solve_batch: bad argument");
+    const double budget = 0.4 * (double)ctx->sa.capacity_base();
+    int worst = AMBI_OK;
+    int32_t lo = 0;
+    while (lo < count) {
+        int32_t hi = lo; double w = 0;
+        while (hi < count && (hi == lo || w + frontier_estimate(problems[hi].n) <= budget)) { w += frontier_estimate(problems[hi].n); ++hi; }
+        ambi_batch *b = nullptr;
+        int rc = ambi_batch_upload(ctx, hi - lo, problems + lo, &b);
+        if (rc) return rc;
+        rc = ambi_batch_run(ctx, b);
+        if (!rc) rc = ambi_batch_fetch(ctx, b, solutions + lo);
+        ambi_batch_free(ctx, b);
+        if (rc && rc != AMBI_ERR_FRONTIER_OVERFLOW) return rc;
+        if (rc) worst = rc;
+        lo = hi;
+    }
+    return worst;
 }
 
 extern "C" int ambi_bfb_solve_shard(ambi_ctx *ctx, const ambi_bfb_problem *problem, ambi_bfb_solution *solution)

@@ -29,6 +29,7 @@ public:
     const char *error() const { return err_; }
     unsigned long long launches() const { return launches_; }
     int count() const { return count_; }
+    uint32_t capacity_base() const { return cap_base_; }
     unsigned long long chunked_runs() const { return chunked_runs_; }
     // per-kernel timing (CUDA events around every k_expand launch; adds launch gaps, so only
     // enabled for the bench's roofline pass)

@@ -32,11 +32,11 @@ struct DevDag {
     uint64_t adj[MAXK];
 };
 
-struct DevOrderOut {
+struct DevOrderOut {                       // compact: 1.1 KB per DAG crosses PCIe / NVLink-C2C
     int32_t found, used_flipped, bkp_len, pad;
     unsigned long long tested;
-    int32_t order[MAXK];
-    int32_t bkp[MAXPATH];
+    uint8_t order[MAXK];
+    int8_t bkp[MAXPATH];                   // relative signed ids, see DevDag
 };
 
 struct Undo { int16_t f; int16_t cnt; int8_t old; int8_t had; };
@@ -218,7 +218,7 @@ k_first_valid_order(const DevDag *dags, DevOrderOut *outs, int count, uint32_t *
                 if (have && my_t == best) {
                     O.found = 1; O.used_flipped = attempt; O.bkp_len = len;
                     for (int i = 0; i < k; ++i) O.order[i] = order[i];
-                    for (int i = 0; i < len; ++i) { int v = B[i]; O.bkp[i] = v > 0 ? v - 1 + D.base : -(-v - 1 + D.base); }
+                    for (int i = 0; i < len; ++i) O.bkp[i] = B[i];
                 }
             }
             __syncwarp();
@@ -324,7 +324,11 @@ k_all_valid_orders(const DevDag *dag, int forward, int32_t *orders, int8_t *bkps
 
 StageB::StageB() { err_[0] = 0; }
 StageB::~StageB() { release(); }
-void StageB::release() { cudaFree(d_dags_); cudaFree(d_out_); cudaFree(d_work_); d_dags_ = d_out_ = d_work_ = nullptr; cap_ = 0; }
+void StageB::release()
+{
+    cudaFree(d_dags_); cudaFree(d_out_); cudaFree(d_work_); cudaFreeHost(h_dags_); cudaFreeHost(h_out_);
+    d_dags_ = d_out_ = d_work_ = h_dags_ = h_out_ = nullptr; cap_ = 0;
+}
 
 int StageB::init(cudaStream_t stream)
 {
@@ -338,10 +342,13 @@ int StageB::init(cudaStream_t stream)
 int StageB::ensure(int count)
 {
     if (count <= cap_) return 0;
-    cudaFree(d_dags_); cudaFree(d_out_); d_dags_ = d_out_ = nullptr;
+    cudaFree(d_dags_); cudaFree(d_out_); cudaFreeHost(h_dags_); cudaFreeHost(h_out_);
+    d_dags_ = d_out_ = h_dags_ = h_out_ = nullptr;
     int c = count < 64 ? 64 : count;
     CKB(cudaMalloc(&d_dags_, (size_t)c * sizeof(DevDag)));
     CKB(cudaMalloc(&d_out_, (size_t)c * sizeof(DevOrderOut)));
+    CKB(cudaMallocHost(&h_dags_, (size_t)c * sizeof(DevDag)));          // pinned staging
+    CKB(cudaMallocHost(&h_out_, (size_t)c * sizeof(DevOrderOut)));
     cap_ = c;
     return 0;
 }
@@ -350,7 +357,7 @@ int StageB::run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_o
 {
     if (count <= 0) return 0;
     if (int rc = ensure(count)) return rc;
-    std::vector<DevDag> h(count);
+    DevDag *h = reinterpret_cast<DevDag *>(h_dags_);
     for (int i = 0; i < count; ++i) {
         const ambi_dag &g = dags[i];
         DevDag &d = h[i];
@@ -366,27 +373,26 @@ int StageB::run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_o
             d.cn[v] = (int8_t)g.cn[v]; d.adj[v] = g.adj[v];
         }
     }
-    CKB(cudaMemcpyAsync(d_dags_, h.data(), (size_t)count * sizeof(DevDag), cudaMemcpyHostToDevice, stream_));
+    CKB(cudaMemcpyAsync(d_dags_, h, (size_t)count * sizeof(DevDag), cudaMemcpyHostToDevice, stream_));
     CKB(cudaMemsetAsync(d_work_, 0, 64, stream_));
-    CKB(cudaMemsetAsync(d_out_, 0, (size_t)count * sizeof(DevOrderOut), stream_));
     int blocks = (count + 3) / 4; if (blocks > sms_ * 8) blocks = sms_ * 8;
     k_first_valid_order<<<blocks, 128, 0, stream_>>>((const DevDag *)d_dags_, (DevOrderOut *)d_out_, count, (uint32_t *)d_work_);
     ++launches_;
     CKB(cudaGetLastError());
-    std::vector<DevOrderOut> ho(count);
-    CKB(cudaMemcpyAsync(ho.data(), d_out_, (size_t)count * sizeof(DevOrderOut), cudaMemcpyDeviceToHost, stream_));
+    DevOrderOut *ho = reinterpret_cast<DevOrderOut *>(h_out_);
+    CKB(cudaMemcpyAsync(ho, d_out_, (size_t)count * sizeof(DevOrderOut), cudaMemcpyDeviceToHost, stream_));
     CKB(cudaStreamSynchronize(stream_));
     for (int i = 0; i < count; ++i) {
         ambi_order_result &r = results[i];
-        memset(&r, 0, sizeof r);
-        r.found = ho[i].found; r.used_flipped = ho[i].used_flipped; r.bkp_len = ho[i].bkp_len;
-        r.orders_tested = ho[i].tested; r.status = 0;
-        for (int v = 0; v < dags[i].k; ++v) r.order[v] = ho[i].order[v];
-        for (int v = 0; v < ho[i].bkp_len && v < 1024; ++v) r.bkp[v] = ho[i].bkp[v];
+        const DevOrderOut &o = ho[i];
+        r.found = o.found; r.used_flipped = o.used_flipped; r.bkp_len = o.found ? o.bkp_len : 0;
+        r.orders_tested = o.tested; r.status = 0; r.reserved = 0;
+        const int base = h[i].base;
+        for (int v = 0; v < dags[i].k; ++v) r.order[v] = o.found ? o.order[v] : 0;
+        for (int v = 0; v < r.bkp_len && v < 1024; ++v) { int q = o.bkp[v]; r.bkp[v] = q > 0 ? q - 1 + base : -(-q - 1 + base); }
     }
     return 0;
 }
-
 
 static void to_devdag(const ambi_dag &g, int reversed, DevDag &d)
 {

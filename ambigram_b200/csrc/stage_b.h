@@ -24,7 +24,7 @@ private:
     int ensure(int count);
     cudaStream_t stream_ = nullptr;
     int cap_ = 0, sms_ = 148;
-    void *d_dags_ = nullptr, *d_out_ = nullptr, *d_work_ = nullptr;
+    void *d_dags_ = nullptr, *d_out_ = nullptr, *d_work_ = nullptr, *h_dags_ = nullptr, *h_out_ = nullptr;
     unsigned long long launches_ = 0;
     char err_[256];
 };

@@ -118,6 +118,82 @@ def cpu_baseline(problems, budget_s: float = 12.0, threads: int = 0):
             "problems_per_s": tot_p / dt}
 
 
+def workload_problems(name: str, count: int, rank: int, world: int):
+    """the other BASELINE configs (parity-test cases; not the default bench line)"""
+    import random
+    from ambigram_b200 import lh, synth
+    if name == "sweep":          # config 5: n ~ U{10..25}, folds = ceil(n/3.5), seeds 0..count-1, sample-sharded
+        rng = random.Random(12345)
+        ns = [rng.randint(10, 25) for _ in range(count)]
+        mine = range(rank, count, world)
+        return [lh.problem_from_lh(synth.generate(ns[s], synth.folds_for(ns[s]), s).lh_text()) for s in mine], "sample-sharded"
+    if name == "n30":            # config 4: n=30 / 8 folds, CN noise +-1 w.p. 0.5, prefix-sharded
+        return [lh.problem_from_lh(synth.generate(30, 8, s, 0.5).lh_text()) for s in range(count)], "prefix-sharded"
+    if name == "n20j":           # config 3: n=20 / 6 folds with .juncs + --junc_info true, prefix-sharded
+        out = []
+        for s in range(count):
+            sm = synth.generate(20, 6, s, 0.0, with_juncs=True)
+            out.append(lh.problem_from_lh(sm.lh_text(), sm.juncs_text(), True))
+        return out, "prefix-sharded"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def run_workload(args):
+    import torch
+    import torch.distributed as dist
+    from ambigram_b200 import capi
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    count = args.batch if args.batch != 4096 else {"sweep": 10000, "n30": 8, "n20j": 64}[args.workload]
+    problems, how = workload_problems(args.workload, count, rank, world)
+    sharded = how == "prefix-sharded"
+    ctx = capi.Context(device=local, rank=rank if sharded else 0, world=world if sharded else 1)
+    if sharded and world > 1:
+        uid = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0])
+
+    def step():
+        if sharded:
+            return [ctx.solve(p) for p in problems]
+        pk = ctx.pack(problems)
+        ctx.solve_packed(pk)
+        return pk.solutions()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sols = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    cand = float(sum(s.candidates_scored for s in sols))
+    t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+    c = torch.tensor([cand if not sharded or rank == 0 else 0.0, float(len(problems)) if not sharded or rank == 0 else 0.0],
+                     dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        secs = float(t[0]) / args.steps
+        print(json.dumps({"metric": METRIC, "value": float(c[0]) / secs, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * secs, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                          "config": {"workload": args.workload, "partitions_per_step": int(c[1]), "parallelism": f"{how} x{world}"},
+                          "partitions_per_s": float(c[1]) / secs, "time_per_lh_ms": 1e3 * secs / max(float(c[1]), 1),
+                          "timing": "host wall clock around the C-ABI calls (host buffers), max over ranks"}))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path for this metric = the oracle port (Cbc, the reference's
     solver, is not in the image and does not count candidates; DESIGN.md 'Reference arm')."""
@@ -162,9 +238,12 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=4096, help="partitions per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="n12", help="n12 (default, BASELINE configs[1]) | n20j | n30 | sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "n12":
+        return run_workload(args)
 
     import torch
     import torch.distributed as dist
@@ -217,14 +296,16 @@ def main():
 
     # ---- Stage B on the same batch (first valid topological order per partition) and single-.lh latency
     dags = [capi.construct_dag(p.n, p.start_id, s.element_cn) for p, s in zip(problems, sols)]
-    ctx.first_valid_order_batch(dags[:64], [False] * 64)
+    dpk = ctx.pack_dags(dags, [False] * len(dags))
+    ctx.first_valid_order_packed(dpk)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    orders = ctx.first_valid_order_batch(dags, [False] * len(dags))
-    stage_b_s = time.perf_counter() - t0
+    for _ in range(5):
+        ctx.first_valid_order_packed(dpk)
+    stage_b_s = (time.perf_counter() - t0) / 5
     stage_b = {"dags": len(dags), "seconds": stage_b_s, "partitions_per_s": len(dags) / stage_b_s,
-               "placements_per_s": sum(o.orders_tested for o in orders) / stage_b_s,
-               "found": sum(1 for o in orders if o.found), "note": "host wall clock around ambi_bfb_first_valid_order_batch (H2D + kernel + D2H)"}
+               "placements_per_s": sum(int(r.orders_tested) for r in dpk[3]) / stage_b_s,
+               "found": sum(1 for r in dpk[3] if r.found), "note": "host wall clock around ambi_bfb_first_valid_order_batch (H2D + kernel + D2H)"}
     one = problems[0]
     for _ in range(3):
         ctx.solve(one)
