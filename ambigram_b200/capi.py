@@ -50,7 +50,8 @@ class _Solution(C.Structure):
 
 class _Profile(C.Structure):
     _fields_ = [("expand_ms", C.c_double), ("expand_launches", C.c_uint64), ("total_ms", C.c_double),
-                ("incumbent_pass_ms", C.c_double), ("record_stride", C.c_uint64)]
+                ("incumbent_pass_ms", C.c_double), ("record_stride", C.c_uint64), ("configs_enumerated", C.c_uint64),
+                ("bounds_evaluated", C.c_uint64), ("children_written", C.c_uint64), ("bound_batches", C.c_uint64)]
 
 
 class _Dag(C.Structure):
@@ -335,7 +336,9 @@ class Context:
         p = _Profile()
         self._check(self.lib.ambi_ctx_get_profile(self.handle, C.byref(p)))
         return {"expand_ms": p.expand_ms, "expand_launches": int(p.expand_launches), "total_ms": p.total_ms,
-                "incumbent_pass_ms": p.incumbent_pass_ms, "record_stride": int(p.record_stride)}
+                "incumbent_pass_ms": p.incumbent_pass_ms, "record_stride": int(p.record_stride),
+                "configs_enumerated": int(p.configs_enumerated), "bounds_evaluated": int(p.bounds_evaluated),
+                "children_written": int(p.children_written), "bound_batches": int(p.bound_batches)}
 
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)

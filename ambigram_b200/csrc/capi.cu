@@ -15,6 +15,9 @@
 #include <string>
 #include <algorithm>
 #include <dlfcn.h>
+#include <thread>
+#include <atomic>
+#include <chrono>
 
 using namespace ambi;
 
@@ -60,10 +63,25 @@ struct ambi_ctx {
 
 struct ambi_batch {
     int count = 0;
-    std::vector<DevProblem> probs;
-    std::vector<int32_t> bias;
+    std::vector<int32_t> n, bias;
     bool ran = false;
 };
+
+// Host-side flattening / result mapping of a large batch is spread over a few threads (it is
+// per-problem independent work that would otherwise sit between the H2D copy and the launch).
+template <class F> static void parallel_for(int count, F fn)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(hw ? hw : 1u, 8u);
+    if (const char *e = getenv("AMBI_HOST_THREADS")) nt = std::max(1, atoi(e));
+    nt = std::min(nt, count / 2048);
+    if (nt <= 1) { fn(0, count); return; }
+    std::vector<std::thread> th;
+    const int per = (count + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) { const int lo = t * per, hi = std::min(count, lo + per); if (lo < hi) th.emplace_back([=] { fn(lo, hi); }); }
+    fn(0, std::min(count, per));
+    for (std::thread &t : th) t.join();
+}
 
 static thread_local std::string g_err;
 
@@ -150,6 +168,8 @@ extern "C" int ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out)
     ctx->sa.profile(&out->expand_ms, &l, &out->total_ms, &out->incumbent_pass_ms);
     out->expand_launches = l;
     out->record_stride = (uint64_t)ctx->sa.record_stride();
+    const unsigned long long *f = ctx->sa.funnel();
+    out->configs_enumerated = f[0]; out->bounds_evaluated = f[1]; out->children_written = f[2]; out->bound_batches = f[3];
     return AMBI_OK;
 }
 extern "C" uint64_t ambi_ctx_launch_count(const ambi_ctx *ctx) { return ctx ? ctx->sa.launches() + ctx->sb.launches() : 0; }
@@ -269,15 +289,22 @@ extern "C" int ambi_batch_upload(ambi_ctx *ctx, int32_t count, const ambi_bfb_pr
 {
     if (!ctx || !out || count <= 0 || !problems) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_batch_upload: bad argument");
     cudaSetDevice(ctx->cfg.device);
+    DevProblem *stage = ctx->sa.staging(count);
+    if (!stage) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
     ambi_batch *b = new ambi_batch();
-    b->count = count; b->probs.resize(count); b->bias.resize(count);
-    for (int i = 0; i < count; ++i) {
-        std::string why;
-        int rc = to_dev(problems[i], b->probs[i], why);
-        if (rc) { delete b; return fail(ctx, rc, "problem " + std::to_string(i) + ": " + why); }
-        b->bias[i] = problems[i].bias;
-    }
-    if (ctx->sa.upload(b->probs.data(), count)) { delete b; return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error()); }
+    b->count = count; b->n.resize(count); b->bias.resize(count);
+    std::atomic<int> bad_rc{0}, bad_i{-1};
+    std::string bad_why;
+    parallel_for(count, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            std::string why;
+            int rc = to_dev(problems[i], stage[i], why);
+            if (rc) { int expect = 0; if (bad_rc.compare_exchange_strong(expect, rc)) { bad_i = i; bad_why = why; } return; }
+            b->n[i] = problems[i].n; b->bias[i] = problems[i].bias;
+        }
+    });
+    if (bad_rc) { delete b; return fail(ctx, bad_rc, "problem " + std::to_string(bad_i.load()) + ": " + bad_why); }
+    if (ctx->sa.upload(stage, count)) { delete b; return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error()); }
     cudaStreamSynchronize(ctx->stream);
     ctx->resident = b;
     *out = b;
@@ -295,26 +322,32 @@ extern "C" int ambi_batch_run(ambi_ctx *ctx, ambi_batch *b)
 
 static int fetch_into(ambi_ctx *ctx, ambi_batch *b, ambi_bfb_solution *sol, bool shard)
 {
-    std::vector<HostResult> hr(b->count);
-    int rc = ctx->sa.fetch(hr.data());
-    if (rc == -4) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
-    int worst = AMBI_OK;
-    for (int i = 0; i < b->count; ++i) {
-        const int n = b->probs[i].n;
-        ambi_bfb_solution &s = sol[i];
-        s.status = hr[i].status;
-        if (shard && hr[i].status == -4) s.status = AMBI_OK;      // this shard saw no completed assignment
-        s.score2 = hr[i].score2;
-        s.objective2 = hr[i].score2 - 2ll * b->bias[i];
-        s.candidates_scored = hr[i].candidates; s.nodes_expanded = hr[i].nodes;
-        s.incumbent_score2 = hr[i].incumbent;
-        s.seconds = hr[i].seconds; s.seconds_to_best = hr[i].seconds_to_best;
-        if (s.element_cn) {
-            if (hr[i].score2 != 0x7fffffff) rows_to_element_cn(n, hr[i].rows, s.element_cn);
-            else memset(s.element_cn, 0, sizeof(int32_t) * n * (n + 1));
+    StageA::Fetched F;
+    int rc = ctx->sa.fetch_raw(&F);
+    if (rc) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
+    std::atomic<int> worst{AMBI_OK};
+    parallel_for(b->count, [&](int lo, int hi) {
+        int w = AMBI_OK;
+        for (int i = lo; i < hi; ++i) {
+            const int n = b->n[i];
+            ambi_bfb_solution &s = sol[i];
+            const int32_t sc = F.score[i];
+            s.status = F.overflow ? AMBI_ERR_FRONTIER_OVERFLOW : (sc == 0x7fffffff ? AMBI_ERR_CUDA : AMBI_OK);
+            if (shard && s.status == AMBI_ERR_CUDA) s.status = AMBI_OK;      // this shard saw no completed assignment
+            s.score2 = sc;
+            s.objective2 = sc - 2ll * b->bias[i];
+            s.candidates_scored = F.cand[i]; s.nodes_expanded = F.node[i];
+            s.incumbent_score2 = F.incumbent[i];
+            s.seconds = F.seconds; s.seconds_to_best = (F.incumbent[i] == sc && !F.used_graph) ? F.seconds_beam : F.seconds;
+            if (s.element_cn) {
+                if (sc != 0x7fffffff) rows_to_element_cn(n, F.rows + (size_t)i * F.rows_stride, s.element_cn);
+                else memset(s.element_cn, 0, sizeof(int32_t) * n * (n + 1));
+            }
+            if (s.status < w) w = s.status;
         }
-        if (s.status < worst) worst = s.status;
-    }
+        int cur = worst.load();
+        while (w < cur && !worst.compare_exchange_weak(cur, w)) {}
+    });
     if (worst == AMBI_ERR_FRONTIER_OVERFLOW) return fail(ctx, worst, ctx->sa.error());
     if (worst) return fail(ctx, worst, "search returned no assignment");
     return AMBI_OK;
@@ -350,11 +383,21 @@ extern "C" int ambi_bfb_solve_batch(ambi_ctx *ctx, int32_t count, const ambi_bfb
         int32_t hi = lo; double w = 0;
         while (hi < count && (hi == lo || w + frontier_estimate(problems[hi].n) <= budget)) { w += frontier_estimate(problems[hi].n); ++hi; }
         ambi_batch *b = nullptr;
+        static const bool timing = getenv("AMBI_TIMING") != nullptr;
+        auto t0 = std::chrono::steady_clock::now();
         int rc = ambi_batch_upload(ctx, hi - lo, problems + lo, &b);
         if (rc) return rc;
+        auto t1 = std::chrono::steady_clock::now();
         rc = ambi_batch_run(ctx, b);
+        if (timing) cudaStreamSynchronize(ctx->stream);
+        auto t2 = std::chrono::steady_clock::now();
         if (!rc) rc = ambi_batch_fetch(ctx, b, solutions + lo);
+        auto t3 = std::chrono::steady_clock::now();
         ambi_batch_free(ctx, b);
+        if (timing) {
+            auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+            fprintf(stderr, "[ambi] solve_batch %d problems: flatten+H2D %.3f ms, search %.3f ms, D2H+map %.3f ms\n", hi - lo, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+        }
         if (rc && rc != AMBI_ERR_FRONTIER_OVERFLOW) return rc;
         if (rc) worst = rc;
         lo = hi;

@@ -44,6 +44,7 @@ struct LevelArgs {
     const int32_t *limit;
     unsigned long long *cand_count;
     unsigned long long *node_count;
+    unsigned long long *funnel;      // [4] configurations enumerated / bounds evaluated / children written / bound batches (whole run)
     uint32_t *work_counter;
     uint32_t *overflow;
     int level;
@@ -53,6 +54,7 @@ struct LevelArgs {
     int beam_shift;
     int beam_delta;                 // >= 0 (incumbent beam only): also drop children whose f exceeds the parent's by more
     int shard_world, shard_rank, shard_level;
+    int gpw;                        // target number of record groups per resident warp
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
@@ -86,6 +88,7 @@ struct GroupShared {
     uint32_t par1[GRP], par2[GRP];      // column already holds >= 1 / >= 2 parents for a loop (row 3)
     uint32_t tmask[GRP];                // third-generation cells of this row
     int32_t  score[GRP], slack[GRP], covC[GRP], fbC[GRP], ptgs[GRP], prob[GRP];
+    int32_t  lslack[GRP];               // slack minus the record's own bound on segments > a (light-test limit)
     uint32_t pidx[GRP];
     uint32_t nl0[GRP];                  // loop multisets whose parents already exist (class 0)
     uint32_t cstart[GRP + 1];           // exclusive prefix of candidate counts
@@ -319,7 +322,7 @@ __device__ __forceinline__ uint32_t light_test(const GroupShared &S, int a, int 
     const int w = (p1 >= 0) + (p2 >= 0) + 2 * nl;
     const uint32_t cja = S.cj[a][slot];
     const int err = abs(2 * (S.covC[slot] + w) - (int)(cja & 0xffff)) + abs(S.fbC[slot] + w - (int)(cja >> 16));
-    *pass = err <= S.slack[slot];
+    *pass = err <= S.lslack[slot];
     return ((uint32_t)slot << 24) | pack_cfg(p1, p2, l1, l2);
 }
 
@@ -338,7 +341,7 @@ k_expand(LevelArgs A_param)
     const uint32_t pcount = min(*A.pcount, A.cap);
     // records per warp group: spread a small frontier over all resident warps
     const uint32_t nwarps = gridDim.x * WPB;
-    const uint32_t grp_n = min((uint32_t)GRP, max(1u, (pcount + 4 * nwarps - 1) / (4 * nwarps)));   // >= 4 groups per warp when possible
+    const uint32_t grp_n = min((uint32_t)GRP, max(1u, (pcount + A.gpw * nwarps - 1) / (A.gpw * nwarps)));   // >= gpw groups per warp when possible
 
     for (;;) {
         uint32_t base = 0;
@@ -395,6 +398,28 @@ k_expand(LevelArgs A_param)
                 par2 |= (uint32_t)(nP + nL >= 2 || root) << j;
             }
         }
+        // The record's own bound on segments > a (what its parent level charged for them): every child's
+        // bound on those segments is at least this (coverage only grows, budgets only shrink), so
+        // err + pf > slack cuts a configuration before the O(n) bound is evaluated for it.
+        int pf = 0;
+        if (have && slack >= 0) {
+            int cov = 0, capsum = 0;
+#pragma unroll 1
+            for (int j = my_n - 1; j > a; --j) {
+                const uint32_t b = S.colb[j][lane];
+                const uint32_t cjw = S.cj[j][lane];
+                const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
+                const int cap = min(bP, 2) + 2 * min(bL, 2);
+                const int wn = nP + 2 * nL;
+                cov += wn; capsum += cap;
+                const int fmax = min(6 * (j - a + 1), capsum);
+                const int d = 2 * cov - (int)(cjw & 0xffff);
+                pf += d > 0 ? d : max(0, -d - 2 * fmax);
+                const int f = wn - (int)(cjw >> 16);
+                pf += f > 0 ? f : max(0, -f - (cap + min(capsum, 6)));
+            }
+        }
+        S.lslack[lane] = slack - pf;
         uint32_t total = 0;
         if (have && my_n > a && slack >= 0) {
             // class-0 loop multisets (parents already exist): {}, singles, doubles, pairs
@@ -424,9 +449,11 @@ k_expand(LevelArgs A_param)
         //      through two shared-memory queues so that each stage runs with full lanes
         int qh = 0, qw = 0;                 // queue fills (warp-uniform)
         uint32_t cb0 = 0;
+        uint32_t n_heavy = 0, n_write = 0, n_hcalls = 0;  // funnel statistics (warp-uniform)
         for (;;) {
             if (qw >= 32 || (cb0 >= T && qh == 0 && qw > 0)) {
                 const int cnt = min(qw, 32);
+                n_write += cnt;
                 write_batch(S, A, cnt);
                 __syncwarp();
                 qw -= cnt;
@@ -439,6 +466,7 @@ k_expand(LevelArgs A_param)
             }
             if (qh >= 32 || (cb0 >= T && qh > 0)) {
                 const int cnt = min(qh, 32);
+                n_heavy += cnt; ++n_hcalls;
                 qw = heavy_batch(S, A, cnt, jtop, qw);
                 __syncwarp();
                 qh -= cnt;
@@ -492,10 +520,11 @@ k_expand(LevelArgs A_param)
                 S.qw_cfg[pos] = ((uint32_t)lane << 24) | pack_cfg(p1, p2, l1, l2); S.qw_err[pos] = err; S.qw_tot[pos] = tot;
             }
             __syncwarp();
-            if (hm) { write_batch(S, A, __popc(hm)); __syncwarp(); }
+            if (hm) { n_write += __popc(hm); write_batch(S, A, __popc(hm)); __syncwarp(); }
         }
         // ---- statistics (per problem of each record)
         __syncwarp();
+        if (lane < 4 && T) atomicAdd(&A.funnel[lane], (unsigned long long)(lane == 0 ? T : (lane == 1 ? n_heavy : (lane == 2 ? n_write : n_hcalls))));
         if (have && S.cstart[lane + 1] - S.cstart[lane] > 0) {
             atomicAdd(&A.cand_count[S.prob[lane]], (unsigned long long)S.cnt[lane]);
             atomicAdd(&A.node_count[S.prob[lane]], 1ull);
@@ -756,7 +785,7 @@ StageA::~StageA() { release(); }
 void StageA::release()
 {
     cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]);
-    cudaFree(table_); cudaFree(counters_); cudaFree(pool_); pool_ = nullptr;
+    cudaFree(table_); cudaFree(counters_); cudaFree(d_funnel_); cudaFree(pool_); pool_ = nullptr; d_funnel_ = nullptr;
     buf_[0] = buf_[1] = nullptr; list_[0] = list_[1] = nullptr; table_ = nullptr;
     counters_ = nullptr;
     free_problem_arrays();
@@ -771,6 +800,7 @@ void StageA::free_problem_arrays()
     cudaFree(d_probs_); cudaFree(d_limit_); cudaFree(d_best_score_); cudaFree(d_best_rows_);
     cudaFree(d_beam_score_); cudaFree(d_beam_rows_); cudaFree(d_cand_); cudaFree(d_node_);
     cudaFree(d_fmin_); cudaFree(d_hist_); cudaFree(d_ticket_); cudaFree(d_incumbent_);
+    cudaFreeHost(h_probs_); cudaFreeHost(h_res_); h_probs_ = nullptr; h_res_ = nullptr; h_cap_ = 0;
     d_probs_ = nullptr; d_limit_ = d_best_score_ = d_beam_score_ = d_fmin_ = d_incumbent_ = nullptr;
     d_best_rows_ = d_beam_rows_ = d_hist_ = d_ticket_ = nullptr; d_cand_ = d_node_ = nullptr;
     prob_cap_ = 0;
@@ -792,6 +822,7 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     beam_ = beam_width > 0 ? beam_width : 16;
     if (const char *e = getenv("AMBI_BEAM_WIDTH")) { int v = atoi(e); if (v > 0) beam_ = v; }   // tuning knobs; results do not depend on them
     if (const char *e = getenv("AMBI_BEAM_DELTA")) beam_delta_ = atoi(e);
+    if (const char *e = getenv("AMBI_GPW")) gpw_ = std::max(1, atoi(e));
     if (const char *e = getenv("AMBI_BEAM_SHIFT")) beam_shift_ = std::max(0, std::min(8, atoi(e)));
     rank_ = rank; world_ = world > 0 ? world : 1; shard_level_ = shard_level;
     // buffers are sized in bytes for the widest record (n = 32); narrower batches fit more records
@@ -805,6 +836,7 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     CK(cudaMalloc(&table_, (size_t)tsize_ * 8));
     CK(cudaMemsetAsync(table_, 0, (size_t)tsize_ * 8, stream_));
     CK(cudaMalloc(&counters_, CTR_TOTAL * sizeof(uint32_t)));
+    CK(cudaMalloc(&d_funnel_, 4 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(counters_, 0, CTR_TOTAL * sizeof(uint32_t), stream_));
     CK(cudaStreamSynchronize(stream_));
     for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&ev_[i]));
@@ -832,8 +864,17 @@ int StageA::ensure_problem_arrays(int count)
     // beam statistics: one slice per level, cleared once per pass
     CK(cudaMalloc(&d_fmin_, (size_t)c * 4 * AMBI_MAXN)); CK(cudaMalloc(&d_hist_, (size_t)c * BEAM_BINS * 4 * AMBI_MAXN));
     CK(cudaMalloc(&d_ticket_, (size_t)c * 4 * AMBI_MAXN));
+    CK(cudaMallocHost(&h_probs_, (size_t)c * sizeof(DevProblem)));
+    CK(cudaMallocHost(&h_res_, (size_t)c * (4 + 4 + 8 + 8 + 4 * AMBI_MAXN)));
+    h_cap_ = c;
     prob_cap_ = c;
     return 0;
+}
+
+DevProblem *StageA::staging(int count)
+{
+    if (ensure_problem_arrays(count)) return nullptr;
+    return h_probs_;
 }
 
 int StageA::upload(const DevProblem *host_probs, int count)
@@ -872,10 +913,10 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     L.probs = d_probs_; L.parents = buf_[cur]; L.plist = listed ? list_[cur] : nullptr;
     L.pcount = listed ? c_cur : counters_ + CTR_CHILD + level - 1;
     L.children = buf_[cur ^ 1]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
-    L.cand_count = d_cand_; L.node_count = d_node_; L.work_counter = c_work; L.overflow = c_over;
+    L.cand_count = d_cand_; L.node_count = d_node_; L.funnel = d_funnel_; L.work_counter = c_work; L.overflow = c_over;
     L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = mode == 0 ? EMIT_BEST : EMIT_ALL;
     L.beam_delta = mode == 1 ? beam_delta_ : -1; L.beam_shift = beam_shift_;
-    L.shard_world = shard_world; L.shard_rank = rank_; L.shard_level = shard_level_eff_;
+    L.shard_world = shard_world; L.shard_rank = rank_; L.shard_level = shard_level_eff_; L.gpw = gpw_;
     const bool prof = profile_ && !capturing_;
     if (prof) {
         if (prof_used_ + 2 > prof_ev_.size()) { cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); prof_ev_.push_back(e0); prof_ev_.push_back(e1); }
@@ -935,6 +976,7 @@ int StageA::enqueue(bool sharded)
     k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
     CK(cudaMemsetAsync(d_cand_, 0, (size_t)count_ * 8, stream_));
     CK(cudaMemsetAsync(d_node_, 0, (size_t)count_ * 8, stream_));
+    CK(cudaMemsetAsync(d_funnel_, 0, 4 * sizeof(unsigned long long), stream_));
     CK(cudaMemsetAsync(d_beam_score_, 0x7f, (size_t)count_ * 4, stream_));
     shard_level_eff_ = -1;
     // ---- pass 0: greedy dive -> first incumbent (limit starts at the all-zero score)
@@ -1063,9 +1105,9 @@ int StageA::run_chunked(bool sharded)
         LevelArgs L;
         L.probs = d_probs_; L.parents = pool_ + sg.off; L.plist = list_[0]; L.pcount = c_par;
         L.children = buf_[0]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
-        L.cand_count = d_cand_; L.node_count = d_node_; L.work_counter = c_work; L.overflow = c_over;
+        L.cand_count = d_cand_; L.node_count = d_node_; L.funnel = d_funnel_; L.work_counter = c_work; L.overflow = c_over;
         L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = EMIT_ALL; L.beam_delta = -1; L.beam_shift = 1;
-        L.shard_world = sw; L.shard_rank = rank_; L.shard_level = shard_level_eff_;
+        L.shard_world = sw; L.shard_rank = rank_; L.shard_level = shard_level_eff_; L.gpw = gpw_;
         k_expand<<<expand_blocks_, WPB * 32, expand_smem_, stream_>>>(L); ++launches_;
         uint32_t ctr[2] = {0, 0};
         CK(cudaMemcpyAsync(&ctr[0], c_over, 4, cudaMemcpyDeviceToHost, stream_));
@@ -1113,7 +1155,7 @@ __global__ void k_reset_best(const DevProblem *probs, int count, int32_t *best_s
     if (p < count && probs[p].n >= 2) best_score[p] = 0x7fffffff;
 }
 
-int StageA::fetch(HostResult *out)
+int StageA::fetch_raw(Fetched *F)
 {
     {   // a level of the breadth-first exact pass did not fit: redo the exact pass depth-first in chunks
         uint32_t over = 0;
@@ -1124,16 +1166,22 @@ int StageA::fetch(HostResult *out)
             if (int rc = run_chunked(last_sharded_)) { if (rc != -5) return rc; }
         }
     }
-    std::vector<int32_t> score(count_), inc(count_);
-    std::vector<uint32_t> rows((size_t)count_ * AMBI_MAXN);
-    std::vector<unsigned long long> cand(count_), node(count_);
+    // one pinned staging area: score | incumbent | cand | node | rows (nmax words per problem)
+    const size_t c = (size_t)count_;
+    int32_t *h_score = reinterpret_cast<int32_t *>(h_res_);
+    int32_t *h_inc = h_score + h_cap_;
+    unsigned long long *h_cand = reinterpret_cast<unsigned long long *>(h_inc + h_cap_);
+    unsigned long long *h_node = h_cand + h_cap_;
+    uint32_t *h_rows = reinterpret_cast<uint32_t *>(h_node + h_cap_);
+    const int rs = nmax_ > 0 ? nmax_ : 1;
     uint32_t ctr[8];   // CTR_OVERFLOW is word 0
-    CK(cudaMemcpyAsync(score.data(), d_best_score_, (size_t)count_ * 4, cudaMemcpyDeviceToHost, stream_));
-    CK(cudaMemcpyAsync(inc.data(), d_incumbent_, (size_t)count_ * 4, cudaMemcpyDeviceToHost, stream_));
-    CK(cudaMemcpyAsync(rows.data(), d_best_rows_, rows.size() * 4, cudaMemcpyDeviceToHost, stream_));
-    CK(cudaMemcpyAsync(cand.data(), d_cand_, (size_t)count_ * 8, cudaMemcpyDeviceToHost, stream_));
-    CK(cudaMemcpyAsync(node.data(), d_node_, (size_t)count_ * 8, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(h_score, d_best_score_, c * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(h_inc, d_incumbent_, c * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpy2DAsync(h_rows, (size_t)rs * 4, d_best_rows_, (size_t)AMBI_MAXN * 4, (size_t)rs * 4, c, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(h_cand, d_cand_, c * 8, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(h_node, d_node_, c * 8, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(ctr, counters_, sizeof ctr, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(funnel_, d_funnel_, sizeof funnel_, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
     float ms_beam = 0, ms_all = 0;
     if (!used_graph_) cudaEventElapsedTime(&ms_beam, ev_[0], ev_[1]);
@@ -1143,16 +1191,25 @@ int StageA::fetch(HostResult *out)
         prof_expand_ms_ = 0; prof_expand_launches_ = prof_used_ / 2;
         for (size_t i = 0; i + 1 < prof_used_; i += 2) { float m = 0; cudaEventElapsedTime(&m, prof_ev_[i], prof_ev_[i + 1]); prof_expand_ms_ += m; }
     }
-    const bool overflow = ctr[CTR_OVERFLOW] != 0;
+    F->score = h_score; F->incumbent = h_inc; F->rows = h_rows; F->rows_stride = rs; F->cand = h_cand; F->node = h_node;
+    F->overflow = ctr[CTR_OVERFLOW] != 0; F->seconds = ms_all * 1e-3; F->seconds_beam = ms_beam * 1e-3; F->used_graph = used_graph_;
+    if (F->overflow) snprintf(err_, sizeof err_, "frontier overflow: more than %u candidate records in one level", cap_);
+    return 0;
+}
+
+int StageA::fetch(HostResult *out)
+{
+    Fetched F;
+    if (int rc = fetch_raw(&F)) return rc;
     for (int p = 0; p < count_; ++p) {
-        out[p].score2 = score[p]; out[p].incumbent = inc[p];
-        out[p].candidates = cand[p]; out[p].nodes = node[p];
-        memcpy(out[p].rows, &rows[(size_t)p * AMBI_MAXN], AMBI_MAXN * 4);
-        out[p].seconds = ms_all * 1e-3; out[p].seconds_to_best = ((inc[p] == score[p] && !used_graph_) ? ms_beam : ms_all) * 1e-3;
-        out[p].status = overflow ? -5 : (score[p] == 0x7fffffff ? -4 : 0);
+        out[p].score2 = F.score[p]; out[p].incumbent = F.incumbent[p];
+        out[p].candidates = F.cand[p]; out[p].nodes = F.node[p];
+        memset(out[p].rows, 0, sizeof out[p].rows);
+        memcpy(out[p].rows, F.rows + (size_t)p * F.rows_stride, (size_t)F.rows_stride * 4);
+        out[p].seconds = F.seconds; out[p].seconds_to_best = (F.incumbent[p] == F.score[p] && !F.used_graph) ? F.seconds_beam : F.seconds;
+        out[p].status = F.overflow ? -5 : (F.score[p] == 0x7fffffff ? -4 : 0);
     }
-    if (overflow) snprintf(err_, sizeof err_, "frontier overflow: more than %u candidate records in one level", cap_);
-    return overflow ? -5 : 0;
+    return F.overflow ? -5 : 0;
 }
 
 }  // namespace ambi

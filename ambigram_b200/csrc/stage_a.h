@@ -20,11 +20,18 @@ public:
     ~StageA();
     int init(cudaStream_t stream, int64_t node_capacity, int beam_width, int rank, int world, int shard_level);
     void release();
+    // pinned staging for `count` problem descriptors; the caller fills it and then calls upload(ptr, count)
+    DevProblem *staging(int count);
     // copy `count` problem descriptors to the device (async on the ctx stream)
     int upload(const DevProblem *host_probs, int count);
     // enqueue the whole search (incumbent pass + exact pass); no host sync
     int run(bool sharded);
-    // wait and read back per-problem results
+    // wait and read back per-problem results (pinned staging; pointers stay valid until the next fetch)
+    struct Fetched {
+        const int32_t *score, *incumbent; const uint32_t *rows; int rows_stride;   // rows_stride words per problem
+        const unsigned long long *cand, *node; bool overflow; double seconds, seconds_beam; bool used_graph;
+    };
+    int fetch_raw(Fetched *out);
     int fetch(HostResult *out);
     const char *error() const { return err_; }
     unsigned long long launches() const { return launches_; }
@@ -38,6 +45,8 @@ public:
         *expand_ms = prof_expand_ms_; *expand_launches = prof_expand_launches_; *total_ms = prof_total_ms_; *beam_ms = prof_beam_ms_;
     }
     size_t record_stride() const { return (size_t)stride_; }
+    // whole-run funnel of the last fetched search: configurations enumerated, bounds evaluated, children written
+    const unsigned long long *funnel() const { return funnel_; }
 
 private:
     int ensure_problem_arrays(int count);
@@ -54,6 +63,7 @@ private:
     bool last_sharded_ = false;
     unsigned long long chunked_runs_ = 0;
     int beam_shift_ = 2;
+    int gpw_ = 4;                 // k_expand: record groups per resident warp (load balance vs lane utilisation)
     int beam_delta_ = 8;          // heuristic band of the incumbent beam (see k_expand)
     int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
     int stride_ = 0, sms_ = 148;
@@ -66,10 +76,13 @@ private:
     int expand_blocks_ = 148;
     // per-problem arrays
     int prob_cap_ = 0, count_ = 0, nmax_ = 0;
-    DevProblem *d_probs_ = nullptr;
+    DevProblem *d_probs_ = nullptr, *h_probs_ = nullptr;   // device array, pinned host staging
+    uint8_t *h_res_ = nullptr;                              // pinned result staging
+    int h_cap_ = 0;
     int32_t *d_limit_ = nullptr, *d_incumbent_ = nullptr, *d_best_score_ = nullptr, *d_beam_score_ = nullptr, *d_fmin_ = nullptr;
     uint32_t *d_best_rows_ = nullptr, *d_beam_rows_ = nullptr, *d_hist_ = nullptr, *d_ticket_ = nullptr;
-    unsigned long long *d_cand_ = nullptr, *d_node_ = nullptr;
+    unsigned long long *d_cand_ = nullptr, *d_node_ = nullptr, *d_funnel_ = nullptr;
+    unsigned long long funnel_[4] = {0, 0, 0, 0};
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches_ = 0;
     bool profile_ = false, capturing_ = false, used_graph_ = false, graph_sharded_ = false;

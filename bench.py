@@ -147,7 +147,7 @@ def run_workload(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    count = args.batch if args.batch != 4096 else {"sweep": 10000, "n30": 8, "n20j": 64}[args.workload]
+    count = args.batch if args.batch > 0 else {"sweep": 10000, "n30": 8, "n20j": 64}[args.workload]
     problems, how = workload_problems(args.workload, count, rank, world)
     sharded = how == "prefix-sharded"
     ctx = capi.Context(device=local, rank=rank if sharded else 0, world=world if sharded else 1)
@@ -236,10 +236,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=4096, help="partitions per step per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="partitions per step per GPU (default 32768 for n12)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="n12", help="n12 (default, BASELINE configs[1]) | n20j | n30 | sweep")
     args = ap.parse_args()
+    if args.workload == "n12" and args.batch <= 0:
+        args.batch = 32768
     if args.impl == "reference":
         return run_reference(args)
     if args.workload != "n12":
@@ -279,7 +281,7 @@ def main():
     cand_per_step = sum(s.candidates_scored for s in sols)
     nodes_per_step = sum(s.nodes_expanded for s in sols)
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("AMBI_BENCH_NO_SAMPLER") else None
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
@@ -336,6 +338,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     e2e_cand = sum(s.candidates_scored for s in e2e_sols)
 
+    if os.environ.get("AMBI_BENCH_DEBUG"):
+        print(f"[rank {rank}] dev_ms/step {dev_ms / args.steps:.3f} e2e_ms/step {1e3 * e2e_s / args.steps:.3f} cand/step {cand_per_step}", file=sys.stderr)
     # max over ranks / sum over ranks
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local}")
     c = torch.tensor([float(cand_per_step), float(e2e_cand), float(launches)], dtype=torch.float64, device=f"cuda:{local}")

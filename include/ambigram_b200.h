@@ -218,6 +218,10 @@ typedef struct {
     double total_ms;           /* whole search (incumbent + exact pass)         */
     double incumbent_pass_ms;
     uint64_t record_stride;    /* bytes per candidate record in HBM             */
+    uint64_t configs_enumerated; /* row configurations decoded (light test)     */
+    uint64_t bounds_evaluated;   /* ... that reached the O(n) admissible bound  */
+    uint64_t children_written;   /* ... that were materialised as records       */
+    uint64_t bound_batches;      /* 32-lane batches the bound ran in (lane use = bounds_evaluated / (32*bound_batches)) */
 } ambi_profile;
 int  ambi_ctx_set_profile(ambi_ctx *ctx, int enable);
 int  ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out);
