@@ -66,8 +66,8 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 
 // position of the k-th (0-based) set bit of m
 __device__ __forceinline__ int nth_bit(uint32_t m, int k) {
-    int pos = 0;                         // branch-free binary search on population counts
-#pragma unroll
+    int pos = 0;                         // branch-free binary search on population counts (a rolled loop
+#pragma unroll                           // over only the open columns measured slower: r01 notes)
     for (int w = 16; w; w >>= 1) {
         const int c = __popc(m & (((1u << w) - 1u) << pos));
         const bool up = k >= c;
@@ -93,7 +93,7 @@ struct GroupShared {
     uint32_t nl0[GRP];                  // loop multisets whose parents already exist (class 0)
     uint32_t cstart[GRP + 1];           // exclusive prefix of candidate counts
     uint8_t  n[GRP];
-    uint32_t cnt[GRP];                  // candidates scored per record
+    uint32_t cnt[GRP];                  // structurally infeasible configurations per record (not scored)
     unsigned long long best[GRP];       // EMIT_BEST: min (tot<<32 | cfg-order key)
     uint32_t qh[64];                    // light-test survivors awaiting the bound: slot<<24 | cfg
     uint32_t qw_cfg[64]; int32_t qw_err[64]; int32_t qw_tot[64];   // children awaiting the write
@@ -123,14 +123,23 @@ __device__ __forceinline__ int child_bound(const GroupShared &S, int slot, int j
                                            int p1, int p2, int l1, int l2, int budget, bool active)
 {
     int lb = 0, cov = 0, capsum = 0;
+    // ends as bit masks aligned so that column jtop-1 sits in bit 31; the walk shifts them left
+    // (pattern ends are distinct columns; a loop column may hold two ends: lm2 = the doubled one)
+    const int sh = 32 - jtop;
+    uint32_t pm = ((p1 >= 0 ? 1u << p1 : 0u) | (p2 >= 0 ? 1u << p2 : 0u)) << sh;
+    uint32_t lm1 = ((l1 >= 0 ? 1u << l1 : 0u) | (l2 >= 0 ? 1u << l2 : 0u)) << sh;
+    uint32_t lm2 = ((l1 >= 0 && l1 == l2) ? 1u << l1 : 0u) << sh;
     // ends at or below the current column (the walk goes right to left, every end is < jtop)
-    int rp_le = (p1 >= 0) + (p2 >= 0), rl_le = (l1 >= 0) + (l2 >= 0);
+    int rp_le = __popc(pm), rl_le = __popc(lm1) + __popc(lm2);
+    int six = 6 * (jtop - 1 - a);                                // 6 * (j - a)
+    const uint16_t *cjh = reinterpret_cast<const uint16_t *>(&S.cj[0][0]);
 #pragma unroll 2
     for (int j = jtop - 1; j > a; --j) {
         const uint32_t cb = S.colb[j][slot];
-        const uint32_t cjw = S.cj[j][slot];
-        const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = (cb >> 6) & 3;
-        const int pab = (j == p1) + (j == p2), lab = (j == l1) + (j == l2);
+        const int c2 = cjh[2 * (j * GRP + slot)], j2 = cjh[2 * (j * GRP + slot) + 1];
+        const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = cb >> 6;
+        const int pab = pm >> 31, lab = (lm1 >> 31) + (lm2 >> 31);
+        pm <<= 1; lm1 <<= 1; lm2 <<= 1;
         const int rp = rp_le - pab, rl = rl_le - lab;          // ends strictly below column j
         rp_le = rp; rl_le = rl;
         const int kP = 2 - pab - max(rp, rl);                   // rows 2, 5a at (a,j)
@@ -139,12 +148,13 @@ __device__ __forceinline__ int child_bound(const GroupShared &S, int slot, int j
         const int cap = nbP + 2 * nbL;                          // both already <= 2
         const int wn = nP + 2 * nL + pab + 2 * lab;
         cov += wn; capsum += cap;
-        const int fmax = min(6 * (j - a), capsum);
-        const int d = 2 * cov - (int)(cjw & 0xffff);
-        lb += d > 0 ? d : max(0, -d - 2 * fmax);
+        const int fmax = min(six, capsum);
+        six -= 6;
+        const int d = 2 * cov - c2;
+        lb += max(max(d, -d - 2 * fmax), 0);
         const int gmax = cap + min(capsum, 6);
-        const int f = wn - (int)(cjw >> 16);
-        lb += f > 0 ? f : max(0, -f - gmax);
+        const int f = wn - j2;
+        lb += max(max(f, -f - gmax), 0);
         if ((j & 3) == 0 && __ballot_sync(0xffffffffu, active && lb <= budget) == 0) break;
     }
     return lb;
@@ -277,7 +287,9 @@ __device__ __forceinline__ uint32_t light_test(const GroupShared &S, int a, int 
             if (r < blk) break;
             r -= blk;
         }
-        const uint32_t pi = r / width;
+        // r < 2^16 and width < 2^11: (r + 0.5) / width is at least 2^-12 away from every integer, far more
+        // than the error of the approximate float division, so truncation gives the exact quotient
+        const uint32_t pi = __float2uint_rz(__fdividef((float)r + 0.5f, (float)width));
         li = r - pi * width;
         if (pi == 0) p1 = hi;
         else { p2 = hi; p1 = nth_bit(lows, pi - 1); }
@@ -481,17 +493,16 @@ k_expand(LevelArgs A_param)
             cb0 += 32;
             bool pass = false;
             uint32_t entry = 0;
+            int bad_slot = 0;
             if (c < T) {
                 int slot = 0;                // owning record: largest slot with cstart[slot] <= c
 #pragma unroll
                 for (int o = 16; o; o >>= 1) if (S.cstart[slot + o] <= c) slot += o;
                 entry = light_test(S, a, slot, c - S.cstart[slot], &pass);
+                bad_slot = slot;
             }
-            {   // candidates scored, per record (lanes of one record are contiguous)
-                const int key = entry ? (int)(entry >> 24) : -1;
-                const uint32_t grp = __match_any_sync(0xffffffffu, key);
-                if (key >= 0 && (grp & lt_mask) == 0) S.cnt[key] += __popc(grp);
-            }
+            // candidates scored = enumerated minus the (few) structurally infeasible ones, per record
+            if (c < T && !entry) atomicAdd(&S.cnt[bad_slot], 1u);
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
             if (pass) S.qh[qh + __popc(bal & lt_mask)] = entry;
             qh += __popc(bal);
@@ -526,7 +537,7 @@ k_expand(LevelArgs A_param)
         __syncwarp();
         if (lane < 4 && T) atomicAdd(&A.funnel[lane], (unsigned long long)(lane == 0 ? T : (lane == 1 ? n_heavy : (lane == 2 ? n_write : n_hcalls))));
         if (have && S.cstart[lane + 1] - S.cstart[lane] > 0) {
-            atomicAdd(&A.cand_count[S.prob[lane]], (unsigned long long)S.cnt[lane]);
+            atomicAdd(&A.cand_count[S.prob[lane]], (unsigned long long)(S.cstart[lane + 1] - S.cstart[lane] - S.cnt[lane]));
             atomicAdd(&A.node_count[S.prob[lane]], 1ull);
         }
         __syncwarp();
