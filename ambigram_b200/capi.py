@@ -54,6 +54,11 @@ class _Profile(C.Structure):
                 ("bounds_evaluated", C.c_uint64), ("children_written", C.c_uint64), ("bound_batches", C.c_uint64)]
 
 
+class _Peaks(C.Structure):
+    _fields_ = [("alu_tops", C.c_double), ("alu_fma_tops", C.c_double), ("smem_tbs", C.c_double),
+                ("sms", C.c_int32), ("reserved", C.c_int32)]
+
+
 class _Dag(C.Structure):
     _fields_ = [("k", C.c_int32), ("kind", C.c_int8 * MAX_COMPONENTS), ("a", C.c_int16 * MAX_COMPONENTS),
                 ("b", C.c_int16 * MAX_COMPONENTS), ("cn", C.c_int16 * MAX_COMPONENTS),
@@ -72,6 +77,7 @@ EXPORTS = [
     "ambi_bfb_better", "ambi_bfb_construct_dag", "ambi_bfb_first_valid_order", "ambi_bfb_first_valid_order_batch",
     "ambi_bfb_expand_path", "ambi_bfb_imperfect_fbi", "ambi_bfb_all_valid_orders", "ambi_batch_upload", "ambi_batch_run", "ambi_batch_fetch", "ambi_batch_free",
     "ambi_ctx_stream", "ambi_ctx_sync", "ambi_ctx_launch_count", "ambi_ctx_set_profile", "ambi_ctx_get_profile",
+    "ambi_measure_peaks", "ambi_bfb_target_cn",
 ]
 
 _lib = None
@@ -122,6 +128,8 @@ def load_library(path: Optional[str] = None):
     lib.ambi_ctx_sync.argtypes = [vp]
     lib.ambi_ctx_set_profile.argtypes = [vp, C.c_int]
     lib.ambi_ctx_get_profile.argtypes = [vp, C.POINTER(_Profile)]
+    lib.ambi_measure_peaks.argtypes = [vp, C.POINTER(_Peaks)]
+    lib.ambi_bfb_target_cn.argtypes = [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.ambi_ctx_launch_count.argtypes = [vp]
     lib.ambi_ctx_launch_count.restype = C.c_uint64
     if path is None:
@@ -340,6 +348,12 @@ class Context:
                 "configs_enumerated": int(p.configs_enumerated), "bounds_evaluated": int(p.bounds_evaluated),
                 "children_written": int(p.children_written), "bound_batches": int(p.bound_batches)}
 
+    def measure_peaks(self) -> dict:
+        """on-box INT32 issue rate (alu pipe; alu + fma pipes) and shared-memory bandwidth"""
+        p = _Peaks()
+        self._check(self.lib.ambi_measure_peaks(self.handle, C.byref(p)))
+        return {"alu_tops": p.alu_tops, "alu_fma_tops": p.alu_fma_tops, "smem_tbs": p.smem_tbs, "sms": int(p.sms)}
+
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         self._check(self.lib.ambi_comm_init(self.handle, buf))
@@ -433,6 +447,17 @@ def better(n: int, score_a: int, x_a, score_b: int, x_b, lib_path: Optional[str]
     xb = np.ascontiguousarray(x_b, dtype=np.int32)
     return bool(lib.ambi_bfb_better(n, score_a, xa.ctypes.data_as(C.POINTER(C.c_int32)), score_b,
                                     xb.ctypes.data_as(C.POINTER(C.c_int32))))
+
+
+def target_cn(n: int, element_cn) -> List[int]:
+    """targetCN of localhap.cpp:222-232 (host helper)"""
+    lib = load_library()
+    x = (C.c_int32 * (n * (n + 1)))(*[int(v) for v in element_cn])
+    out = (C.c_int32 * n)()
+    rc = lib.ambi_bfb_target_cn(n, x, out)
+    if rc:
+        raise AmbiError(rc, "ambi_bfb_target_cn")
+    return list(out)
 
 
 def format_path(path: Sequence[int]) -> str:

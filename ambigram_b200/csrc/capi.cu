@@ -59,6 +59,7 @@ struct ambi_ctx {
     uint32_t *d_gather = nullptr;      // world * 40 words
     std::string err;
     ambi_batch *resident = nullptr;
+    uint64_t extra_launches = 0;
 };
 
 struct ambi_batch {
@@ -172,7 +173,17 @@ extern "C" int ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out)
     out->configs_enumerated = f[0]; out->bounds_evaluated = f[1]; out->children_written = f[2]; out->bound_batches = f[3];
     return AMBI_OK;
 }
-extern "C" uint64_t ambi_ctx_launch_count(const ambi_ctx *ctx) { return ctx ? ctx->sa.launches() + ctx->sb.launches() : 0; }
+namespace ambi { int measure_peaks(cudaStream_t st, ambi_peaks *out); }
+extern "C" int ambi_measure_peaks(ambi_ctx *ctx, ambi_peaks *out)
+{
+    if (!ctx || !out) return AMBI_ERR_BAD_ARG;
+    cudaSetDevice(ctx->cfg.device);
+    memset(out, 0, sizeof *out);
+    if (ambi::measure_peaks(ctx->stream, out)) return fail(ctx, AMBI_ERR_CUDA, "ambi_measure_peaks: kernel failed");
+    ctx->extra_launches += 18;
+    return AMBI_OK;
+}
+extern "C" uint64_t ambi_ctx_launch_count(const ambi_ctx *ctx) { return ctx ? ctx->sa.launches() + ctx->sb.launches() + ctx->extra_launches : 0; }
 
 extern "C" int ambi_nccl_unique_id(void *id128)
 {
@@ -596,6 +607,19 @@ extern "C" int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int
     }
     *n_initial = (int32_t)first.size(); *n_flipped = (int32_t)second.size();
     if (n_tested) *n_tested = tested;
+    return AMBI_OK;
+}
+
+extern "C" int ambi_bfb_target_cn(int32_t n, const int32_t *x, int32_t *target)
+{
+    if (!x || !target || n < 1 || n > AMBI_MAX_SEGMENTS) return AMBI_ERR_BAD_ARG;
+    const int H = n * (n + 1) / 2;
+    for (int i = 0; i < n; ++i) target[i] = 0;
+    for (int a = 0; a < n; ++a)
+        for (int b = a; b < n; ++b) {
+            const int w = x[pair_index(n, a, b)] + 2 * x[H + pair_index(n, a, b)];
+            for (int i = a; i <= b && w; ++i) target[i] += w;
+        }
     return AMBI_OK;
 }
 

@@ -199,6 +199,10 @@ int ambi_bfb_imperfect_fbi(int32_t *bkp, int32_t bkp_len, const int32_t *inv_src
 /* Expand breakpoint pairs to the vertex path (LGM:3661-3670); returns length. */
 int ambi_bfb_expand_path(const int32_t *bkp, int32_t bkp_len, int32_t *path_out, int32_t cap);
 
+/* targetCN (localhap.cpp:222-232): copy number of every segment implied by element_cn,
+ * target_cn[i] = sum over components covering segment i of cn (patterns) / 2*cn (loops). */
+int ambi_bfb_target_cn(int32_t n, const int32_t *element_cn, int32_t *target_cn);
+
 /* ---- device-resident batch (bench: inputs already in HBM) ---------------- */
 /* Upload a batch once, then run the search repeatedly without host<->device
  * copies of the inputs; results stay on the device until fetched.            */
@@ -225,6 +229,17 @@ typedef struct {
 } ambi_profile;
 int  ambi_ctx_set_profile(ambi_ctx *ctx, int enable);
 int  ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out);
+/* On-box roofline denominators that MEASURED_PEAKS.json does not carry: integer issue
+ * rate of the alu pipe alone (IADD3/LOP3 chains), of the alu and fma pipes together (IADD3 + IMAD),
+ * and conflict-free shared-memory load bandwidth.  A few milliseconds of micro-benchmark kernels. */
+typedef struct {
+    double alu_tops;           /* 1e12 thread-level INT32 operations / s, alu pipe only      */
+    double alu_fma_tops;       /* ... with every other operation an IMAD (both pipes)       */
+    double smem_tbs;           /* 1e12 bytes / s of LDS.128                                  */
+    int32_t sms;
+    int32_t reserved;
+} ambi_peaks;
+int  ambi_measure_peaks(ambi_ctx *ctx, ambi_peaks *out);
 /* kernels launched by the ctx since creation (bench "gpu_launches") */
 uint64_t ambi_ctx_launch_count(const ambi_ctx *ctx);
 

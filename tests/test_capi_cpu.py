@@ -112,3 +112,19 @@ def test_imperfect_fbi_matches_oracle_on_golden_cases():
         if d.k <= 16 and c["ref_inject_paths"]:
             assert capi.format_path(capi.expand_path(a)) == c["ref_inject_paths"][0]
     assert seen >= 5        # the imperfect_* fixtures really exercise the rewrite
+
+
+def test_target_cn_is_the_coverage_of_the_assignment():
+    """targetCN (localhap.cpp:222-232): cov_i = sum of P + 2L over the components covering segment i,
+    the same vector the model's coverage rows use (LGM:4427-4440)."""
+    for n, folds, seed in [(6, 3, 0), (12, 4, 3), (16, 5, 2)]:
+        p = lh.problem_from_lh(synth.generate(n, folds, seed, 0.5).lh_text())
+        x, _ = orc.solve(p, want_unique=False)
+        H = n * (n + 1) // 2
+        want, i = [0] * n, 0
+        for a in range(n):
+            for b in range(a, n):
+                for s in range(a, b + 1):
+                    want[s] += int(x[i]) + 2 * int(x[H + i])
+                i += 1
+        assert capi.target_cn(n, x) == want

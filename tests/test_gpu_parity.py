@@ -261,3 +261,26 @@ def test_all_valid_orders_matches_reference_print_all(ctx):
             assert first == orc.all_valid_orders(od, forward=not rev)
             seen_multi += len(first) > 1
     assert seen_multi >= 10
+
+
+def test_measured_peaks_are_plausible(ctx):
+    """on-box roofline denominators: integer issue rate and shared-memory bandwidth"""
+    pk = ctx.measure_peaks()
+    assert pk["sms"] >= 100
+    assert 5.0 < pk["alu_tops"] < 60.0 and 5.0 < pk["alu_fma_tops"] < 60.0
+    assert 10.0 < pk["smem_tbs"] < 60.0
+
+
+def test_profile_funnel_counters(ctx):
+    ps = [lh.problem_from_lh(synth.generate(12, 4, s).lh_text()) for s in range(64)]
+    b = ctx.upload(ps)
+    ctx.set_profile(True)
+    b.run(); ctx.sync()
+    sols = b.fetch()
+    pr = ctx.profile()
+    ctx.set_profile(False)
+    b.free()
+    cand = sum(s.candidates_scored for s in sols)
+    assert pr["configs_enumerated"] >= cand > 0
+    assert pr["configs_enumerated"] >= pr["bounds_evaluated"] >= pr["children_written"] > 0
+    assert pr["bound_batches"] * 32 >= pr["bounds_evaluated"]

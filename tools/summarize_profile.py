@@ -49,7 +49,7 @@ def launches(round_, path):
     ex = [l for l in step if l["name"] == "k_expand"]
     tsum = sum(l["gpu__time_duration.sum"] for l in ex)
     out = {"round": round_, "complete_step": len(idx) > 1,
-           "note": "one full step (4096 partitions n=12 / 4 folds: greedy + beam + exact pass) of `AMBI_NO_GRAPH=1 ncu --metrics "
+           "note": "one full step (" + os.environ.get("AMBI_PROFILE_BATCH", "32768") + " partitions n=12 / 4 folds: greedy + beam + exact pass) of `AMBI_NO_GRAPH=1 ncu --metrics "
                    "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,... --clock-control none python bench.py "
                    "--steps 2 --warmup 1 --no-cpu-baseline` (graph replay disabled so that ncu sees the kernels). Per-launch times "
                    "are cold-cache and serialised: compare shares, not absolutes.",
@@ -64,7 +64,8 @@ def launches(round_, path):
     print("wrote", p, "k_expand share", agg["k_expand"]["share"])
 
 
-KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+KEYS = ["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+        "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
         "sm__warps_active.avg.per_cycle_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
@@ -82,7 +83,7 @@ def full(round_, rep):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     md = [f"# {round_}: `ncu --set full --clock-control none --import-source on -k regex:k_expand` (exact-pass levels of one step)\n",
-          "Command: `AMBI_NO_GRAPH=1 ncu --set full ... -k regex:k_expand -s 134 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline`;",
+          "Command: `" + os.environ.get("AMBI_PROFILE_CMD", "AMBI_NO_GRAPH=1 ncu --set full --clock-control none --import-source on -k regex:k_expand -s 26 -c 2 python scratch/prof_target.py 32768") + "`;",
           "the same command exited 0 without ncu directly before.  Numbers under a profiler are not bench values.\n"]
     stall = [k for k in hdr if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")]
     for r in rows[2:]:
@@ -94,44 +95,37 @@ def full(round_, rep):
         md.append("\nWarp stall reasons (warps per issue-active cycle): " +
                   ", ".join("%s=%.2f" % (k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""),
                                          float(r[hdr.index(k)])) for k in stall if float(r[hdr.index(k)]) >= 0.1) + "\n")
-    # hottest source lines of the first launch
-    src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    srows = list(csv.reader(src_csv.splitlines()))
-    shdr = srows[1]
-    ie, te, ss = shdr.index("Instructions Executed"), shdr.index("Thread Instructions Executed"), shdr.index("# Samples")
-    tbl = []
-    for r in srows[2:]:
-        if len(r) < 10 or not r[0].startswith("0x"):
-            break
-        tbl.append(r)
-    so = os.path.join(ROOT, "ambigram_b200", "libambigram_b200.so")
-    subprocess.run(["cuobjdump", "-xelf", "all", so], cwd="/tmp", capture_output=True)
-    sass = subprocess.run(["nvdisasm", "-g", "/tmp/stage_a.sm_100a.cubin"], capture_output=True, text=True).stdout.splitlines()
-    start = next(i for i, l in enumerate(sass) if l.startswith(".text._ZN4ambi8k_expandENS_9LevelArgsE:"))
-    end = next((i for i in range(start + 1, len(sass)) if sass[i].startswith("//---------------------")), len(sass))
-    ins_line, cur = [], None
-    for ln in sass[start:end]:
-        m = re.search(r'stage_a.cu", line (\d+)', ln)
-        if m:
-            cur = int(m.group(1)); continue
-        if re.search(r'ambi_common.cuh", line (\d+)', ln):
-            cur = None; continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
-            ins_line.append(cur)
-    src = open(os.path.join(ROOT, "ambigram_b200", "csrc", "stage_a.cu")).read().splitlines()
-    if len(ins_line) == len(tbl):
-        agg = collections.defaultdict(lambda: [0, 0, 0])
-        for i, r in enumerate(tbl):
-            a = agg[ins_line[i]]
-            a[0] += int(r[ie]); a[1] += int(r[te]); a[2] += int(r[ss])
-        tot = sum(v[0] for v in agg.values()); tots = sum(v[2] for v in agg.values())
-        md.append(f"## hottest source lines of launch 0 ({tot} warp instructions, {len(tbl)} SASS instructions = {len(tbl) * 16 // 1024} KB of code)\n")
-        md.append("| % warp inst | % stall samples | threads / inst | stage_a.cu line | source |\n|---|---|---|---|---|")
-        for l, v in sorted(agg.items(), key=lambda t: -t[1][0])[:25]:
-            text = src[l - 1].strip()[:100].replace("|", "\\|") if l else "(helpers in ambi_common.cuh)"
-            md.append("| %.1f | %.1f | %.1f | %s | `%s` |" % (100 * v[0] / tot, 100 * v[2] / max(tots, 1), v[1] / max(v[0], 1), l, text))
-    else:
-        md.append(f"(source mapping skipped: the .so in the tree ({len(ins_line)} SASS instructions) is not the profiled build ({len(tbl)}))")
+    # hottest source lines of the first launch: ncu's own SASS -> CUDA-C mapping (-lineinfo, --import-source on)
+    src_csv = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"],
+                             capture_output=True, text=True).stdout
+    first, cur_file, hdr2, launch = None, None, None, -1
+    agg = collections.OrderedDict()
+    for r in csv.reader(src_csv.splitlines()):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur_file = r[1].split("/")[-1]
+            first = first or cur_file
+            if cur_file == first:
+                launch += 1
+            continue
+        if r[0] == "Line No":
+            hdr2 = r; continue
+        if hdr2 and len(r) == len(hdr2) and launch == 0:
+            try:
+                ln = int(r[0])
+            except ValueError:
+                continue
+            a = agg.setdefault((cur_file, ln, r[1].strip()), [0, 0, 0])
+            a[0] += int(r[hdr2.index("Instructions Executed")]); a[1] += int(r[hdr2.index("Thread Instructions Executed")])
+            a[2] += int(r[hdr2.index("# Samples")])
+    tot = sum(v[0] for v in agg.values()) or 1
+    tots = sum(v[2] for v in agg.values()) or 1
+    md.append(f"## hottest source lines of launch 0 ({tot} warp instructions)\n")
+    md.append("| % warp inst | % stall samples | threads / inst | file:line | source |\n|---|---|---|---|---|")
+    for (f, l, text), v in sorted(agg.items(), key=lambda t: -t[1][0])[:30]:
+        md.append("| %.1f | %.1f | %.1f | %s:%d | `%s` |" % (100 * v[0] / tot, 100 * v[2] / tots, v[1] / max(v[0], 1), f, l,
+                                                              text[:100].replace("|", "\\|")))
     p = os.path.join(ROOT, "profiles", f"{round_}_k_expand_full.md")
     open(p, "w").write("\n".join(md) + "\n")
     print("wrote", p)
