@@ -220,7 +220,12 @@ __device__ __noinline__ void write_batch(GroupShared &S, const LevelArgs &A, int
     cbase = __shfl_sync(0xffffffffu, cbase, 0);
     if (!wr) return;
     const uint32_t cslot = cbase + __popc(wm & lt_mask);
-    if (cslot >= A.cap) { atomicExch(A.overflow, 1u); return; }
+    if (cslot >= A.cap) {
+        // the incumbent beam just loses the record (it is a heuristic); the exact pass records the level it
+        // overflowed at, every later launch of the pass returns at once and the host continues depth-first
+        if (A.beam_delta < 0) atomicExch(A.overflow, (uint32_t)a + 1u);
+        return;
+    }
     uint8_t *crec = A.children + (size_t)cslot * A.stride;
     reinterpret_cast<uint4 *>(crec)[0] = make_uint4(0, 0, 0, 0);
     reinterpret_cast<uint4 *>(crec)[1] = make_uint4(0, 0, 0, 0);
@@ -346,6 +351,7 @@ k_expand(LevelArgs A_param)
     if (threadIdx.x == 0) s_args = A_param;
     __syncthreads();
     const LevelArgs &A = s_args;
+    if (*A.overflow) return;                // an earlier level of this pass did not fit (block-uniform)
     GroupShared &S = reinterpret_cast<GroupShared *>(s_raw)[threadIdx.x >> 5];
     const int lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -357,9 +363,9 @@ k_expand(LevelArgs A_param)
 
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(A.work_counter, grp_n);
+        if (lane == 0) base = *reinterpret_cast<volatile uint32_t *>(A.overflow) ? 0xffffffffu : atomicAdd(A.work_counter, grp_n);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= pcount) break;
+        if (base >= pcount) break;          // no work left, or this level has overflowed: stop early
         __syncwarp();
 
         // ---- phase 1: lane = record slot; stage column state and problem data, count candidates
@@ -561,6 +567,7 @@ struct DedupArgs {
     uint32_t gen_off;
     int stride;
     int level;          // rows 0..level are fixed in these records
+    const uint32_t *overflow;
 };
 
 __device__ __forceinline__ uint32_t hdr_tgs(const NodeHdr *h) {
@@ -589,6 +596,7 @@ __device__ __forceinline__ bool rec_better(const uint8_t *x, const uint8_t *y, i
 
 __global__ void k_dedup(DedupArgs A)
 {
+    if (*A.overflow) return;
     uint32_t cnt = min(*A.count, A.cap);
     const uint32_t gen = *A.gen_base + A.gen_off;
     // use only as much of the table as this level needs (>= 4 slots per record), so that small
@@ -644,10 +652,12 @@ struct FinalizeArgs {
     int level;
     int merge_best;             // chunked mode: keep the better of (stored best, this chunk's best)
     int build_list;             // append the surviving open records to next_list (else expand reads the buffer itself)
+    const uint32_t *overflow;
 };
 
 __global__ void k_finalize(FinalizeArgs A)
 {
+    if (*A.overflow) return;
     uint32_t cnt = min(*A.count, A.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const uint8_t *rec = A.recs + (size_t)i * A.stride;
@@ -693,7 +703,9 @@ struct BeamArgs {
     uint32_t *ticket;           // [prob]
     uint32_t *next_list;
     uint32_t *next_count;
-    int width;
+    int width_floor;            // batch-scaled width (a fixed budget of beam records per batch)
+    int width;                  // per-problem beam width of a 12-segment partition ...
+    float growth;               // ... doubled every 1/growth further segments (a longer partition needs a wider beam)
     int stride;
     int level;
 };
@@ -720,9 +732,10 @@ __global__ void k_beam_select(BeamArgs A)
         uint32_t below = 0;
         for (int k = 0; k < bin; ++k) below += hs[k];
         bool keep;
-        if (below + hs[bin] <= (uint32_t)A.width) keep = true;
-        else if (below >= (uint32_t)A.width) keep = false;
-        else keep = below + atomicAdd(&A.ticket[h->prob], 1u) < (uint32_t)A.width;
+        const uint32_t width = (uint32_t)max((float)A.width_floor, min(8192.0f, (float)A.width * exp2f(A.growth * (float)max(0, A.probs[h->prob].n - 12))));
+        if (below + hs[bin] <= width) keep = true;
+        else if (below >= width) keep = false;
+        else keep = below + atomicAdd(&A.ticket[h->prob], 1u) < width;
         if (keep) { uint32_t s = atomicAdd(A.next_count, 1u); A.next_list[s] = i; }
     }
 }
@@ -834,6 +847,7 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     if (const char *e = getenv("AMBI_BEAM_WIDTH")) { int v = atoi(e); if (v > 0) beam_ = v; }   // tuning knobs; results do not depend on them
     if (const char *e = getenv("AMBI_BEAM_DELTA")) beam_delta_ = atoi(e);
     if (const char *e = getenv("AMBI_GPW")) gpw_ = std::max(1, atoi(e));
+    if (const char *e = getenv("AMBI_BEAM_GROWTH")) beam_growth_ = (float)atof(e);
     if (const char *e = getenv("AMBI_BEAM_SHIFT")) beam_shift_ = std::max(0, std::min(8, atoi(e)));
     rank_ = rank; world_ = world > 0 ? world : 1; shard_level_ = shard_level;
     // buffers are sized in bytes for the widest record (n = 32); narrower batches fit more records
@@ -938,7 +952,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     if (merge) {
         DedupArgs D;
         D.recs = buf_[cur ^ 1]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
-        D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = stride_; D.level = level;
+        D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = stride_; D.level = level; D.overflow = c_over;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
     }
     const bool beam = mode == 1;
@@ -947,7 +961,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     F.next_list = list_[cur ^ 1]; F.next_count = c_nxt;
     F.best_score = mode == 2 ? d_best_score_ : d_beam_score_; F.best_rows = mode == 2 ? d_best_rows_ : d_beam_rows_;
     F.fmin = beam ? d_fmin_ + (size_t)level * count_ : nullptr; F.stride = stride_; F.level = level;
-    F.limit = nullptr; F.merge_best = 0; F.build_list = 0;
+    F.limit = nullptr; F.merge_best = 0; F.build_list = 0; F.overflow = c_over;
     // outside the beam pass this kernel only collects completed assignments: skip the levels where no problem ends
     if (beam || ((leaf_levels_ >> level) & 1u)) { k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_; }
     if (beam) {
@@ -956,7 +970,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
         B.fmin = d_fmin_ + (size_t)level * count_; B.hist = d_hist_ + (size_t)level * count_ * BEAM_BINS;
         B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = list_[cur ^ 1];
         // a fixed budget of beam records per batch: few large partitions get a wide beam
-        B.next_count = c_nxt; B.width = std::min(8192, std::max(beam_, beam_ * 4096 / std::max(count_, 1))); B.stride = stride_; B.level = level;
+        B.next_count = c_nxt; B.width = beam_; B.width_floor = std::min(8192, std::max(beam_, beam_ * 4096 / std::max(count_, 1))); B.stride = stride_; B.level = level; B.growth = beam_growth_;
         k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
         k_beam_select<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
     }
@@ -1074,7 +1088,7 @@ __global__ void k_gather(const uint8_t *recs, const uint32_t *list, uint32_t m, 
     }
 }
 
-int StageA::run_chunked(bool sharded)
+int StageA::run_chunked(bool sharded, int start_level)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
     if (!pool_) {
@@ -1090,15 +1104,29 @@ int StageA::run_chunked(bool sharded)
     CK(cudaMemsetAsync(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t), stream_));
     struct Seg { int level; size_t off; uint32_t cnt, pos; };
     std::vector<Seg> stack;
-    // roots -> pool
-    CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
-    k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, pool_, stride_, nmax_, list_[0],
-                                              counters_ + CTR_FRONT, d_limit_, d_best_score_, 0); ++launches_;
     uint32_t nroots = 0;
-    CK(cudaMemcpyAsync(&nroots, counters_ + CTR_FRONT, 4, cudaMemcpyDeviceToHost, stream_));
-    CK(cudaStreamSynchronize(stream_));
-    if (nroots == 0) return 0;
-    stack.push_back({0, 0, nroots, 0});
+    if (start_level >= 1) {
+        // continue from the last level the breadth-first pass completed: its frontier (the children of level
+        // start_level-1, dropped and completed records included -- k_expand skips those) is still intact in
+        // the parent buffer of the level that overflowed; every per-problem result found so far stays valid
+        CK(cudaMemcpyAsync(&nroots, counters_ + CTR_CHILD + start_level - 1, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        nroots = std::min(nroots, cap_);
+        if ((size_t)nroots * stride_ > pool_bytes_) { snprintf(err_, sizeof err_, "chunked pass: frontier pool too small"); return -5; }
+        CK(cudaMemcpyAsync(pool_, buf_[start_level & 1], (size_t)nroots * stride_, cudaMemcpyDeviceToDevice, stream_));
+        CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
+        if (nroots == 0) return 0;
+        stack.push_back({start_level, 0, nroots, 0});
+    } else {
+        // roots -> pool
+        CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
+        k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, pool_, stride_, nmax_, list_[0],
+                                                  counters_ + CTR_FRONT, d_limit_, d_best_score_, 0); ++launches_;
+        CK(cudaMemcpyAsync(&nroots, counters_ + CTR_FRONT, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        if (nroots == 0) return 0;
+        stack.push_back({0, 0, nroots, 0});
+    }
     size_t pool_top = (size_t)nroots * stride_;
     std::vector<uint32_t> chunk(AMBI_MAXN + 1, cap_ / 16 ? cap_ / 16 : 1);   // parents per chunk, per level (adaptive)
     uint32_t *c_over = counters_ + CTR_OVERFLOW;
@@ -1135,13 +1163,13 @@ int StageA::run_chunked(bool sharded)
         ++chunks;
         DedupArgs D;
         D.recs = buf_[0]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
-        D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = stride_; D.level = level;
+        D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = stride_; D.level = level; D.overflow = c_over;
         k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
         FinalizeArgs F;
         F.probs = d_probs_; F.recs = buf_[0]; F.count = c_child; F.cap = cap_;
         F.next_list = list_[1]; F.next_count = c_next; F.best_score = d_best_score_; F.best_rows = d_best_rows_;
-        F.fmin = nullptr; F.limit = d_limit_; F.stride = stride_; F.level = level; F.merge_best = 1; F.build_list = 1;
+        F.fmin = nullptr; F.limit = d_limit_; F.stride = stride_; F.level = level; F.merge_best = 1; F.build_list = 1; F.overflow = c_over;
         k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_;
         uint32_t nnext = 0;
         CK(cudaMemcpyAsync(&nnext, c_next, 4, cudaMemcpyDeviceToHost, stream_));
@@ -1173,8 +1201,11 @@ int StageA::fetch_raw(Fetched *F)
         CK(cudaMemcpyAsync(&over, counters_ + CTR_OVERFLOW, 4, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
         if (over && getenv("AMBI_NO_CHUNKED") == nullptr) {
-            k_reset_best<<<(count_ + 127) / 128, 128, 0, stream_>>>(d_probs_, count_, d_best_score_); ++launches_;
-            if (int rc = run_chunked(last_sharded_)) { if (rc != -5) return rc; }
+            // `over` = 1 + the level of the exact pass that did not fit
+            const int lvl = (int)over - 1;
+            const bool resume = lvl >= 1 && getenv("AMBI_CHUNKED_FROM_ROOT") == nullptr;
+            if (!resume) { k_reset_best<<<(count_ + 127) / 128, 128, 0, stream_>>>(d_probs_, count_, d_best_score_); ++launches_; }
+            if (int rc = run_chunked(last_sharded_, resume ? lvl : 0)) { if (rc != -5) return rc; }
         }
     }
     // one pinned staging area: score | incumbent | cand | node | rows (nmax words per problem)

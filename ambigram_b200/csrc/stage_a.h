@@ -54,7 +54,7 @@ private:
     int run_level(int level, int cur, int mode, int shard_world);
     int run_pass(int mode, int shard_world, bool first);
     int enqueue(bool sharded);
-    int run_chunked(bool sharded);
+    int run_chunked(bool sharded, int start_level);
 
     cudaStream_t stream_ = nullptr;
     uint32_t cap_ = 0, cap_base_ = 0, cap_max_ = 0, tsize_ = 0, gen_ = 1;
@@ -63,6 +63,7 @@ private:
     bool last_sharded_ = false;
     unsigned long long chunked_runs_ = 0;
     int beam_shift_ = 2;
+    float beam_growth_ = 0.5f;    // beam width doubles every 1/growth segments beyond 12 (see k_beam_select)
     int gpw_ = 4;                 // k_expand: record groups per resident warp (load balance vs lane utilisation)
     int beam_delta_ = 8;          // heuristic band of the incumbent beam (see k_expand)
     int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
