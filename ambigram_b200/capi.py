@@ -51,7 +51,8 @@ class _Solution(C.Structure):
 class _Profile(C.Structure):
     _fields_ = [("expand_ms", C.c_double), ("expand_launches", C.c_uint64), ("total_ms", C.c_double),
                 ("incumbent_pass_ms", C.c_double), ("record_stride", C.c_uint64), ("configs_enumerated", C.c_uint64),
-                ("bounds_evaluated", C.c_uint64), ("children_written", C.c_uint64), ("bound_batches", C.c_uint64)]
+                ("bounds_evaluated", C.c_uint64), ("children_written", C.c_uint64), ("bound_batches", C.c_uint64), ("exchange_rounds", C.c_uint64),
+                ("chunked_runs", C.c_uint64)]
 
 
 class _Peaks(C.Structure):
@@ -346,7 +347,8 @@ class Context:
         return {"expand_ms": p.expand_ms, "expand_launches": int(p.expand_launches), "total_ms": p.total_ms,
                 "incumbent_pass_ms": p.incumbent_pass_ms, "record_stride": int(p.record_stride),
                 "configs_enumerated": int(p.configs_enumerated), "bounds_evaluated": int(p.bounds_evaluated),
-                "children_written": int(p.children_written), "bound_batches": int(p.bound_batches)}
+                "children_written": int(p.children_written), "bound_batches": int(p.bound_batches), "exchange_rounds": int(p.exchange_rounds),
+                "chunked_runs": int(p.chunked_runs)}
 
     def measure_peaks(self) -> dict:
         """on-box INT32 issue rate (alu pipe; alu + fma pipes) and shared-memory bandwidth"""

@@ -171,6 +171,7 @@ extern "C" int ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out)
     out->record_stride = (uint64_t)ctx->sa.record_stride();
     const unsigned long long *f = ctx->sa.funnel();
     out->configs_enumerated = f[0]; out->bounds_evaluated = f[1]; out->children_written = f[2]; out->bound_batches = f[3];
+    out->exchange_rounds = ctx->sa.exchange_rounds(); out->chunked_runs = ctx->sa.chunked_runs();
     return AMBI_OK;
 }
 namespace ambi { int measure_peaks(cudaStream_t st, ambi_peaks *out); }
@@ -204,6 +205,12 @@ extern "C" int ambi_comm_init(ambi_ctx *ctx, const void *id128)
     ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, ctx->cfg.world, id, ctx->cfg.rank);
     if (r != 0) return fail(ctx, AMBI_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     if (cudaMalloc(&ctx->d_gather, (size_t)(ctx->cfg.world + 1) * 40 * 4) != cudaSuccess) return fail(ctx, AMBI_ERR_CUDA, "cudaMalloc gather");
+    // periodic exchange of pruning limits between the ranks of a prefix-sharded depth-first search
+    ctx->sa.set_allreduce([](void *user, int32_t *d_buf, int count, int op) -> int {
+        ambi_ctx *c = static_cast<ambi_ctx *>(user);
+        static const int nccl_op[3] = {3 /* ncclMin */, 2 /* ncclMax */, 0 /* ncclSum */};
+        return g_nccl.AllReduce(d_buf, d_buf, (size_t)count, kNcclInt32, nccl_op[op], c->comm, c->stream) != 0;
+    }, ctx);
     return AMBI_OK;
 }
 

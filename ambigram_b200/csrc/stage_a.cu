@@ -809,7 +809,7 @@ StageA::~StageA() { release(); }
 void StageA::release()
 {
     cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]);
-    cudaFree(table_); cudaFree(counters_); cudaFree(d_funnel_); cudaFree(pool_); pool_ = nullptr; d_funnel_ = nullptr;
+    cudaFree(table_); cudaFree(counters_); cudaFree(d_funnel_); cudaFree(d_flag_); cudaFree(pool_); pool_ = nullptr; d_funnel_ = nullptr; d_flag_ = nullptr;
     buf_[0] = buf_[1] = nullptr; list_[0] = list_[1] = nullptr; table_ = nullptr;
     counters_ = nullptr;
     free_problem_arrays();
@@ -862,6 +862,7 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     CK(cudaMemsetAsync(table_, 0, (size_t)tsize_ * 8, stream_));
     CK(cudaMalloc(&counters_, CTR_TOTAL * sizeof(uint32_t)));
     CK(cudaMalloc(&d_funnel_, 4 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&d_flag_, 4 * sizeof(int32_t)));
     CK(cudaMemsetAsync(counters_, 0, CTR_TOTAL * sizeof(uint32_t), stream_));
     CK(cudaStreamSynchronize(stream_));
     for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&ev_[i]));
@@ -1088,7 +1089,40 @@ __global__ void k_gather(const uint8_t *recs, const uint32_t *list, uint32_t m, 
     }
 }
 
-int StageA::run_chunked(bool sharded, int start_level)
+__global__ void k_fold_best_into_limit(int count, int32_t *limit, const int32_t *best_score)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < count && best_score[p] < limit[p]) limit[p] = best_score[p];
+}
+
+// One round of the bound exchange between the ranks of a prefix-sharded search: every rank's pruning limit
+// becomes the minimum over ranks (a completed assignment found anywhere prunes everywhere; the limit test is
+// `<=`, so equal-score assignments survive and the tie-break winner does not depend on who found what), and
+// the ranks learn how many of them are still searching.
+int StageA::exchange_round(int active, int *total_active)
+{
+    int32_t a = active;
+    if (allreduce_(allreduce_user_, d_limit_, count_, 0)) { snprintf(err_, sizeof err_, "bound exchange: all-reduce(min) failed"); return -4; }
+    CK(cudaMemcpyAsync(d_flag_, &a, 4, cudaMemcpyHostToDevice, stream_));
+    if (allreduce_(allreduce_user_, d_flag_, 1, 2)) { snprintf(err_, sizeof err_, "bound exchange: all-reduce(sum) failed"); return -4; }
+    CK(cudaMemcpyAsync(&a, d_flag_, 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    *total_active = a;
+    ++exchange_rounds_;
+    return 0;
+}
+
+int StageA::run_chunked(bool sharded, int start_level, bool exchange)
+{
+    const int rc = run_chunked_core(sharded, start_level, exchange);
+    if (exchange) {         // done (or failed) here: keep answering the other ranks' rounds until nobody is searching
+        int total = 1;
+        while (total > 0) if (exchange_round(0, &total)) return -4;
+    }
+    return rc;
+}
+
+int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
     if (!pool_) {
@@ -1115,8 +1149,7 @@ int StageA::run_chunked(bool sharded, int start_level)
         if ((size_t)nroots * stride_ > pool_bytes_) { snprintf(err_, sizeof err_, "chunked pass: frontier pool too small"); return -5; }
         CK(cudaMemcpyAsync(pool_, buf_[start_level & 1], (size_t)nroots * stride_, cudaMemcpyDeviceToDevice, stream_));
         CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
-        if (nroots == 0) return 0;
-        stack.push_back({start_level, 0, nroots, 0});
+        if (nroots > 0) stack.push_back({start_level, 0, nroots, 0});
     } else {
         // roots -> pool
         CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
@@ -1124,16 +1157,21 @@ int StageA::run_chunked(bool sharded, int start_level)
                                                   counters_ + CTR_FRONT, d_limit_, d_best_score_, 0); ++launches_;
         CK(cudaMemcpyAsync(&nroots, counters_ + CTR_FRONT, 4, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
-        if (nroots == 0) return 0;
-        stack.push_back({0, 0, nroots, 0});
+        if (nroots > 0) stack.push_back({0, 0, nroots, 0});
     }
     size_t pool_top = (size_t)nroots * stride_;
     std::vector<uint32_t> chunk(AMBI_MAXN + 1, cap_ / 16 ? cap_ / 16 : 1);   // parents per chunk, per level (adaptive)
     uint32_t *c_over = counters_ + CTR_OVERFLOW;
     uint32_t *c_work = counters_ + CTR_WORK, *c_child = counters_ + CTR_CHILD;
     uint32_t *c_par = counters_ + CTR_FRONT, *c_next = counters_ + CTR_FRONT + 1;
-    unsigned long long chunks = 0;
+    unsigned long long chunks = 0, since_exchange = 0;
+    const unsigned long long exchange_every = 8;
     while (!stack.empty()) {
+        if (exchange && since_exchange >= exchange_every) {
+            int total = 0;
+            if (int rc = exchange_round(1, &total)) return rc;
+            since_exchange = 0;
+        }
         Seg &sg = stack.back();
         if (sg.pos >= sg.cnt) { pool_top = sg.off; stack.pop_back(); continue; }
         const int level = sg.level;
@@ -1160,7 +1198,7 @@ int StageA::run_chunked(bool sharded, int start_level)
         }
         if (ctr[1] * 4ull < cap_ && chunk[level] < cap_) chunk[level] = std::min<uint64_t>(cap_, 2ull * chunk[level]);
         sg.pos += m;
-        ++chunks;
+        ++chunks; ++since_exchange;
         DedupArgs D;
         D.recs = buf_[0]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = stride_; D.level = level; D.overflow = c_over;
@@ -1196,16 +1234,32 @@ __global__ void k_reset_best(const DevProblem *probs, int count, int32_t *best_s
 
 int StageA::fetch_raw(Fetched *F)
 {
-    {   // a level of the breadth-first exact pass did not fit: redo the exact pass depth-first in chunks
+    {   // a level of the breadth-first exact pass did not fit: continue depth-first in chunks
         uint32_t over = 0;
         CK(cudaMemcpyAsync(&over, counters_ + CTR_OVERFLOW, 4, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
-        if (over && getenv("AMBI_NO_CHUNKED") == nullptr) {
+        const bool chunked_ok = getenv("AMBI_NO_CHUNKED") == nullptr;
+        // prefix-sharded with a communicator: the ranks agree whether anybody goes depth-first; if so, all of
+        // them join the periodic bound exchange (those whose shard fitted contribute their final best score)
+        bool exchange = false;
+        if (allreduce_ && last_sharded_ && world_ > 1 && chunked_ok) {
+            int32_t f = over ? 1 : 0;
+            CK(cudaMemcpyAsync(d_flag_, &f, 4, cudaMemcpyHostToDevice, stream_));
+            if (allreduce_(allreduce_user_, d_flag_, 1, 1)) { snprintf(err_, sizeof err_, "all-reduce(max) failed"); return -4; }
+            CK(cudaMemcpyAsync(&f, d_flag_, 4, cudaMemcpyDeviceToHost, stream_));
+            CK(cudaStreamSynchronize(stream_));
+            exchange = f != 0;
+        }
+        if (over && chunked_ok) {
             // `over` = 1 + the level of the exact pass that did not fit
             const int lvl = (int)over - 1;
             const bool resume = lvl >= 1 && getenv("AMBI_CHUNKED_FROM_ROOT") == nullptr;
             if (!resume) { k_reset_best<<<(count_ + 127) / 128, 128, 0, stream_>>>(d_probs_, count_, d_best_score_); ++launches_; }
-            if (int rc = run_chunked(last_sharded_, resume ? lvl : 0)) { if (rc != -5) return rc; }
+            if (int rc = run_chunked(last_sharded_, resume ? lvl : 0, exchange)) { if (rc != -5) return rc; }
+        } else if (exchange) {
+            k_fold_best_into_limit<<<(count_ + 127) / 128, 128, 0, stream_>>>(count_, d_limit_, d_best_score_); ++launches_;
+            int total = 1;
+            while (total > 0) if (int rc = exchange_round(0, &total)) return rc;
         }
     }
     // one pinned staging area: score | incumbent | cand | node | rows (nmax words per problem)

@@ -45,6 +45,12 @@ public:
         *expand_ms = prof_expand_ms_; *expand_launches = prof_expand_launches_; *total_ms = prof_total_ms_; *beam_ms = prof_beam_ms_;
     }
     size_t record_stride() const { return (size_t)stride_; }
+    // Prefix-sharded search over several GPUs: in-place all-reduce of `count` int32 on the ctx stream
+    // (op 0 = min, 1 = max, 2 = sum), supplied by the C-ABI layer when an NCCL communicator exists.  Used for
+    // the periodic exchange of pruning limits while ranks search depth-first (run_chunked).
+    typedef int (*AllReduceFn)(void *user, int32_t *d_buf, int count, int op);
+    void set_allreduce(AllReduceFn fn, void *user) { allreduce_ = fn; allreduce_user_ = user; }
+    unsigned long long exchange_rounds() const { return exchange_rounds_; }
     // whole-run funnel of the last fetched search: configurations enumerated, bounds evaluated, children written
     const unsigned long long *funnel() const { return funnel_; }
 
@@ -54,7 +60,9 @@ private:
     int run_level(int level, int cur, int mode, int shard_world);
     int run_pass(int mode, int shard_world, bool first);
     int enqueue(bool sharded);
-    int run_chunked(bool sharded, int start_level);
+    int run_chunked(bool sharded, int start_level, bool exchange);
+    int run_chunked_core(bool sharded, int start_level, bool exchange);
+    int exchange_round(int active, int *total_active);
 
     cudaStream_t stream_ = nullptr;
     uint32_t cap_ = 0, cap_base_ = 0, cap_max_ = 0, tsize_ = 0, gen_ = 1;
@@ -94,6 +102,10 @@ private:
     size_t prof_used_ = 0;
     double prof_expand_ms_ = 0, prof_total_ms_ = 0, prof_beam_ms_ = 0;
     unsigned long long prof_expand_launches_ = 0;
+    AllReduceFn allreduce_ = nullptr;
+    void *allreduce_user_ = nullptr;
+    int32_t *d_flag_ = nullptr;
+    unsigned long long exchange_rounds_ = 0;
     char err_[256];
 };
 

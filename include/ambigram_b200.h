@@ -226,6 +226,8 @@ typedef struct {
     uint64_t bounds_evaluated;   /* ... that reached the O(n) admissible bound  */
     uint64_t children_written;   /* ... that were materialised as records       */
     uint64_t bound_batches;      /* 32-lane batches the bound ran in (lane use = bounds_evaluated / (32*bound_batches)) */
+    uint64_t exchange_rounds;    /* bound-exchange rounds (NCCL all-reduce of the pruning limits) since ambi_init */
+    uint64_t chunked_runs;       /* searches that continued depth-first because a level did not fit, since ambi_init */
 } ambi_profile;
 int  ambi_ctx_set_profile(ambi_ctx *ctx, int enable);
 int  ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out);
