@@ -848,6 +848,7 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     if (const char *e = getenv("AMBI_BEAM_DELTA")) beam_delta_ = atoi(e);
     if (const char *e = getenv("AMBI_GPW")) gpw_ = std::max(1, atoi(e));
     if (const char *e = getenv("AMBI_BEAM_GROWTH")) beam_growth_ = (float)atof(e);
+    if (const char *e = getenv("AMBI_BEAM_FLOOR_MAX")) beam_floor_max_ = std::max(1, atoi(e));
     if (const char *e = getenv("AMBI_BEAM_SHIFT")) beam_shift_ = std::max(0, std::min(8, atoi(e)));
     rank_ = rank; world_ = world > 0 ? world : 1; shard_level_ = shard_level;
     // buffers are sized in bytes for the widest record (n = 32); narrower batches fit more records
@@ -971,7 +972,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
         B.fmin = d_fmin_ + (size_t)level * count_; B.hist = d_hist_ + (size_t)level * count_ * BEAM_BINS;
         B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = list_[cur ^ 1];
         // a fixed budget of beam records per batch: few large partitions get a wide beam
-        B.next_count = c_nxt; B.width = beam_; B.width_floor = std::min(8192, std::max(beam_, beam_ * 4096 / std::max(count_, 1))); B.stride = stride_; B.level = level; B.growth = beam_growth_;
+        B.next_count = c_nxt; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1))); B.stride = stride_; B.level = level; B.growth = beam_growth_;
         k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
         k_beam_select<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
     }

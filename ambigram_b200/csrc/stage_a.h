@@ -71,6 +71,8 @@ private:
     bool last_sharded_ = false;
     unsigned long long chunked_runs_ = 0;
     int beam_shift_ = 2;
+    int beam_floor_max_ = 16;     // cap of the batch-scaled beam width `16*4096/count` (measured: with the width growing
+                                  // in n a wide beam for small batches only costs time; AMBI_BEAM_FLOOR_MAX restores it)
     float beam_growth_ = 0.5f;    // beam width doubles every 1/growth segments beyond 12 (see k_beam_select)
     int gpw_ = 4;                 // k_expand: record groups per resident warp (load balance vs lane utilisation)
     int beam_delta_ = 8;          // heuristic band of the incumbent beam (see k_expand)
