@@ -706,6 +706,7 @@ struct BeamArgs {
     int width_floor;            // batch-scaled width (a fixed budget of beam records per batch)
     int width;                  // per-problem beam width of a 12-segment partition ...
     float growth;               // ... doubled every 1/growth further segments (a longer partition needs a wider beam)
+    int width_div;              // cooperative beam: this rank runs 1/width_div of the width on its share of the prefixes
     int stride;
     int level;
 };
@@ -732,7 +733,7 @@ __global__ void k_beam_select(BeamArgs A)
         uint32_t below = 0;
         for (int k = 0; k < bin; ++k) below += hs[k];
         bool keep;
-        const uint32_t width = (uint32_t)max((float)A.width_floor, min(8192.0f, (float)A.width * exp2f(A.growth * (float)max(0, A.probs[h->prob].n - 12))));
+        const uint32_t width = max(16u, (uint32_t)max((float)A.width_floor, min(8192.0f, (float)A.width * exp2f(A.growth * (float)max(0, A.probs[h->prob].n - 12)))) / (uint32_t)A.width_div);
         if (below + hs[bin] <= width) keep = true;
         else if (below >= width) keep = false;
         else keep = below + atomicAdd(&A.ticket[h->prob], 1u) < width;
@@ -817,6 +818,7 @@ void StageA::release()
     for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
     prof_ev_.clear();
     if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    if (graph_exec2_) { cudaGraphExecDestroy(graph_exec2_); graph_exec2_ = nullptr; }
 }
 
 void StageA::free_problem_arrays()
@@ -898,6 +900,12 @@ int StageA::ensure_problem_arrays(int count)
     return 0;
 }
 
+void StageA::drop_graphs()
+{
+    if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    if (graph_exec2_) { cudaGraphExecDestroy(graph_exec2_); graph_exec2_ = nullptr; }
+}
+
 DevProblem *StageA::staging(int count)
 {
     if (ensure_problem_arrays(count)) return nullptr;
@@ -907,15 +915,15 @@ DevProblem *StageA::staging(int count)
 int StageA::upload(const DevProblem *host_probs, int count)
 {
     if (int rc = ensure_problem_arrays(count)) return rc;
-    if (count != count_ && graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    if (count != count_) drop_graphs();
     count_ = count;
     int nmax = 0;
     for (int i = 0; i < count; ++i) nmax = std::max(nmax, (int)host_probs[i].n);
-    if (nmax != nmax_ && graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    if (nmax != nmax_) drop_graphs();
     nmax_ = nmax;
     uint32_t leaf = 0;
     for (int i = 0; i < count; ++i) if (host_probs[i].n >= 2) leaf |= 1u << (host_probs[i].n - 1);
-    if (leaf != leaf_levels_ && graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+    if (leaf != leaf_levels_) drop_graphs();
     leaf_levels_ = leaf;
     stride_ = (int)ambi_node_stride(nmax_);
     cap_ = (uint32_t)std::min<uint64_t>(cap_max_, buf_bytes_ / stride_);
@@ -972,7 +980,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
         B.fmin = d_fmin_ + (size_t)level * count_; B.hist = d_hist_ + (size_t)level * count_ * BEAM_BINS;
         B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = list_[cur ^ 1];
         // a fixed budget of beam records per batch: few large partitions get a wide beam
-        B.next_count = c_nxt; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1))); B.stride = stride_; B.level = level; B.growth = beam_growth_;
+        B.next_count = c_nxt; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1))); B.stride = stride_; B.level = level; B.growth = beam_growth_; B.width_div = beam_div_;
         k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
         k_beam_select<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
     }
@@ -996,7 +1004,11 @@ int StageA::run_pass(int mode, int shard_world, bool first)
     return 0;
 }
 
-int StageA::enqueue(bool sharded)
+// Incumbent part of a search: greedy dive, then the beam.  `coop` (prefix-sharded with a communicator): the
+// beam is sharded by prefix like the exact pass -- every rank keeps the children of row `shard_level` that hash
+// to it and runs a beam of 1/world of the width below them; the ranks' incumbents are min-reduced over NCCL
+// before the exact part starts (run()).
+int StageA::enqueue_incumbent(bool coop)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
     CK(cudaMemsetAsync(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t), stream_));
@@ -1013,12 +1025,26 @@ int StageA::enqueue(bool sharded)
     // ---- pass 1: beam of width W inside that limit -> tighter incumbent
     if (beam_ > 1) {
         CK(cudaMemsetAsync(d_beam_score_, 0x7f, (size_t)count_ * 4, stream_));
-        if (int rc = run_pass(1, 1, false)) return rc;
-        k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_); ++launches_;
+        beam_div_ = 1;
+        if (coop) {
+            int sl = shard_level_ > 0 ? shard_level_ : 2;
+            shard_level_eff_ = std::min(sl, std::max(0, nmax_ - 2));
+            beam_div_ = world_;
+        }
+        if (int rc = run_pass(1, coop ? world_ : 1, false)) return rc;
+        beam_div_ = 1;
     }
+    return 0;
+}
+
+// Exact part: the limit becomes the best incumbent, then the exact pass (prefix-sharded when `sharded`).
+int StageA::enqueue_exact(bool sharded)
+{
+    const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
+    if (beam_ > 1) { k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_); ++launches_; }
     if (!capturing_) CK(cudaEventRecord(ev_[1], stream_));
-    // ---- pass 2: exact
     int sw = sharded ? world_ : 1;
+    shard_level_eff_ = -1;
     if (sw > 1) {
         int sl = shard_level_ > 0 ? shard_level_ : 2;
         shard_level_eff_ = std::min(sl, std::max(0, nmax_ - 2));
@@ -1029,38 +1055,67 @@ int StageA::enqueue(bool sharded)
 
 // The launch sequence depends only on (count, nmax, sharding): every size that matters lives in
 // device counters.  It is captured once into a CUDA graph and replayed, so a step costs one
-// graph launch instead of ~150 kernel launches; the profiling pass uses plain launches.
+// graph launch instead of ~150 kernel launches; the profiling pass uses plain launches.  A cooperative
+// (prefix-sharded, NCCL) search is two graphs with the all-reduce(min) of the incumbents in between.
+int StageA::capture(cudaGraphExec_t *exec, unsigned long long *nlaunch, int part, bool flag)
+{
+    cudaGraph_t g = nullptr;
+    const unsigned long long l0 = launches_;
+    CK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    capturing_ = true;
+    int rc = 0;
+    if (part == 0) { rc = enqueue_incumbent(false); if (!rc) rc = enqueue_exact(flag); }      // everything, one graph
+    else if (part == 1) rc = enqueue_incumbent(true);
+    else rc = enqueue_exact(true);
+    capturing_ = false;
+    cudaError_t e = cudaStreamEndCapture(stream_, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    CK(e);
+    CK(cudaGraphInstantiate(exec, g, 0));
+    cudaGraphDestroy(g);
+    *nlaunch = launches_ - l0;
+    launches_ = l0;
+    return 0;
+}
+
 int StageA::run(bool sharded)
 {
     prof_used_ = 0;
     last_sharded_ = sharded;
     CK(cudaEventRecord(ev_[0], stream_));
+    const bool coop = sharded && world_ > 1 && allreduce_ != nullptr && beam_ > 1 && getenv("AMBI_REPLICATED_BEAM") == nullptr;
     const bool use_graph = !profile_ && getenv("AMBI_NO_GRAPH") == nullptr;
-    if (!use_graph) {
-        if (int rc = enqueue(sharded)) return rc;
-        used_graph_ = false;
-    } else {
-        if (graph_exec_ && graph_sharded_ != sharded) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
-        if (!graph_exec_) {
-            cudaGraph_t g = nullptr;
-            const unsigned long long l0 = launches_;
-            CK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
-            capturing_ = true;
-            int rc = enqueue(sharded);
-            capturing_ = false;
-            cudaError_t e = cudaStreamEndCapture(stream_, &g);
-            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-            CK(e);
-            CK(cudaGraphInstantiate(&graph_exec_, g, 0));
-            cudaGraphDestroy(g);
-            graph_sharded_ = sharded;
-            graph_launches_ = launches_ - l0;
-            launches_ = l0;
-        }
-        CK(cudaGraphLaunch(graph_exec_, stream_));
-        launches_ += graph_launches_;
-        used_graph_ = true;
+    const int mode = coop ? 2 : (sharded ? 1 : 0);
+    if (use_graph && graph_exec_ && graph_mode_ != mode) {
+        cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
+        if (graph_exec2_) { cudaGraphExecDestroy(graph_exec2_); graph_exec2_ = nullptr; }
     }
+    if (!coop) {
+        if (!use_graph) {
+            if (int rc = enqueue_incumbent(false)) return rc;
+            if (int rc = enqueue_exact(sharded)) return rc;
+        } else {
+            if (!graph_exec_) { if (int rc = capture(&graph_exec_, &graph_launches_, 0, sharded)) return rc; graph_mode_ = mode; }
+            CK(cudaGraphLaunch(graph_exec_, stream_));
+            launches_ += graph_launches_;
+        }
+    } else {
+        if (!use_graph) { if (int rc = enqueue_incumbent(true)) return rc; }
+        else {
+            if (!graph_exec_) { if (int rc = capture(&graph_exec_, &graph_launches_, 1, true)) return rc; graph_mode_ = mode; }
+            CK(cudaGraphLaunch(graph_exec_, stream_));
+            launches_ += graph_launches_;
+        }
+        // the ranks' beams covered disjoint prefixes: everybody continues with the best incumbent found anywhere
+        if (allreduce_(allreduce_user_, d_beam_score_, count_, 0)) { snprintf(err_, sizeof err_, "incumbent all-reduce(min) failed"); return -4; }
+        if (!use_graph) { if (int rc = enqueue_exact(true)) return rc; }
+        else {
+            if (!graph_exec2_) { if (int rc = capture(&graph_exec2_, &graph_launches2_, 2, true)) return rc; }
+            CK(cudaGraphLaunch(graph_exec2_, stream_));
+            launches_ += graph_launches2_;
+        }
+    }
+    used_graph_ = use_graph;
     CK(cudaEventRecord(ev_[2], stream_));
     return 0;
 }

@@ -59,7 +59,10 @@ private:
     void free_problem_arrays();
     int run_level(int level, int cur, int mode, int shard_world);
     int run_pass(int mode, int shard_world, bool first);
-    int enqueue(bool sharded);
+    int enqueue_incumbent(bool coop);
+    int enqueue_exact(bool sharded);
+    int capture(cudaGraphExec_t *exec, unsigned long long *nlaunch, int part, bool flag);
+    void drop_graphs();
     int run_chunked(bool sharded, int start_level, bool exchange);
     int run_chunked_core(bool sharded, int start_level, bool exchange);
     int exchange_round(int active, int *total_active);
@@ -97,7 +100,9 @@ private:
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches_ = 0;
     bool profile_ = false, capturing_ = false, used_graph_ = false, graph_sharded_ = false;
-    cudaGraphExec_t graph_exec_ = nullptr;
+    cudaGraphExec_t graph_exec_ = nullptr, graph_exec2_ = nullptr;
+    int graph_mode_ = 0, beam_div_ = 1;
+    unsigned long long graph_launches2_ = 0;
     uint32_t graph_gens_ = 0;
     unsigned long long graph_launches_ = 0;
     std::vector<cudaEvent_t> prof_ev_;
