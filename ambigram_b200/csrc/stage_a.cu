@@ -568,7 +568,16 @@ struct DedupArgs {
     int stride;
     int level;          // rows 0..level are fixed in these records
     const uint32_t *overflow;
+    // incumbent beam only (hist != nullptr): the merge also builds the per-problem f-histogram of the records
+    // that are alive (a record replaced later takes its count back) and the level's minimum f
+    const DevProblem *probs;
+    uint32_t *hist;             // [prob][BEAM_BINS], bins of width 1 from the previous level's minimum f
+    int32_t *fmin_cur;          // [prob] minimum f of this level (base of the next level's bins)
+    const int32_t *fmin_prev;   // [prob] or nullptr at level 0 (base = root bound)
 };
+
+// f only grows along a path, so the previous level's minimum f is a lower bound of every f of this level
+__device__ __forceinline__ int beam_bin(int f, int base) { return max(0, min(f - base, BEAM_BINS - 1)); }
 
 __device__ __forceinline__ uint32_t hdr_tgs(const NodeHdr *h) {
     return *reinterpret_cast<const volatile uint32_t *>(&h->tgs) & ~DEAD_BIT;
@@ -613,11 +622,13 @@ __global__ void k_dedup(DedupArgs A)
         for (int k = 0; k < 8; ++k) hv = mix32(hv ^ cw[k]) + 0x85ebca6bu * (k + 1);
         uint32_t slot = hv & tmask;
         const unsigned long long mine = ((unsigned long long)gen << 32) | i;
+        bool alive = false;
+        int replaced_f = 0x7fffffff;                    // f of the record this one displaced, if any
         for (;;) {
             unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&A.table[slot]);
             if ((uint32_t)(cur >> 32) != gen) {
                 unsigned long long old = atomicCAS(&A.table[slot], cur, mine);
-                if (old == cur) break;
+                if (old == cur) { alive = true; break; }
                 continue;                              // re-read the same slot
             }
             uint32_t o = (uint32_t)cur;
@@ -625,11 +636,22 @@ __global__ void k_dedup(DedupArgs A)
             if (same_state(h, reinterpret_cast<const NodeHdr *>(orec))) {
                 if (rec_better(rec, orec, A.level + 1)) {
                     unsigned long long old = atomicCAS(&A.table[slot], cur, mine);
-                    if (old == cur) { hdr_kill(reinterpret_cast<NodeHdr *>(orec)); break; }
+                    if (old == cur) { hdr_kill(reinterpret_cast<NodeHdr *>(orec)); alive = true; replaced_f = reinterpret_cast<const NodeHdr *>(orec)->f; break; }
                     continue;
                 } else { hdr_kill(h); break; }
             }
             slot = (slot + 1) & tmask;
+        }
+        if (A.hist && alive) {
+            const int prob = h->prob;
+            const DevProblem &P = A.probs[prob];
+            if (P.n != A.level + 1) {                   // completed assignments are not part of the beam
+                const int base = A.fmin_prev ? A.fmin_prev[prob] : P.root_lb;
+                uint32_t *hs = A.hist + (size_t)prob * BEAM_BINS;
+                atomicAdd(&hs[beam_bin(h->f, base)], 1u);
+                if (replaced_f != 0x7fffffff) atomicSub(&hs[beam_bin(replaced_f, base)], 1u);
+                atomicMin(&A.fmin_cur[prob], h->f);
+            }
         }
     }
 }
@@ -698,11 +720,13 @@ struct BeamArgs {
     const uint8_t *recs;
     const uint32_t *count;
     uint32_t cap;
-    const int32_t *fmin;
-    uint32_t *hist;             // [prob][BEAM_BINS]
+    const int32_t *fmin_prev;   // [prob] base of the bins (nullptr at level 0: root bound)
+    const uint32_t *hist;       // [prob][BEAM_BINS], built by k_dedup
+    uint32_t *cutq;             // [prob] cut bin << 16 | records still to take from it
     uint32_t *ticket;           // [prob]
     uint32_t *next_list;
     uint32_t *next_count;
+    int nprob;
     int width_floor;            // batch-scaled width (a fixed budget of beam records per batch)
     int width;                  // per-problem beam width of a 12-segment partition ...
     float growth;               // ... doubled every 1/growth further segments (a longer partition needs a wider beam)
@@ -711,15 +735,23 @@ struct BeamArgs {
     int level;
 };
 
-__global__ void k_beam_hist(BeamArgs A)
+// per problem: the bin in which the cumulative count reaches the beam width, and how many records of that bin
+// still fit (every record in a lower bin is kept, records of the cut bin draw tickets)
+__global__ void k_beam_cut(BeamArgs A)
 {
-    uint32_t cnt = min(*A.count, A.cap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const NodeHdr *h = reinterpret_cast<const NodeHdr *>(A.recs + (size_t)i * A.stride);
-        if (hdr_dead(h) || A.probs[h->prob].n == A.level + 1) continue;
-        int bin = min(h->f - A.fmin[h->prob], BEAM_BINS - 1);
-        atomicAdd(&A.hist[(size_t)h->prob * BEAM_BINS + bin], 1u);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.nprob) return;
+    const uint32_t width = max(16u, (uint32_t)max((float)A.width_floor, min(8192.0f, (float)A.width * exp2f(A.growth * (float)max(0, A.probs[p].n - 12)))) / (uint32_t)A.width_div);
+    const uint32_t *hs = A.hist + (size_t)p * BEAM_BINS;
+    uint32_t below = 0;
+    int cut = BEAM_BINS;                                // keep everything
+    uint32_t quota = 0;
+    for (int k = 0; k < BEAM_BINS; ++k) {
+        const uint32_t c = hs[k];
+        if (below + c > width) { cut = k; quota = width - below; break; }
+        below += c;
     }
+    A.cutq[p] = ((uint32_t)cut << 16) | quota;
 }
 
 __global__ void k_beam_select(BeamArgs A)
@@ -727,16 +759,14 @@ __global__ void k_beam_select(BeamArgs A)
     uint32_t cnt = min(*A.count, A.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const NodeHdr *h = reinterpret_cast<const NodeHdr *>(A.recs + (size_t)i * A.stride);
-        if (hdr_dead(h) || A.probs[h->prob].n == A.level + 1) continue;
-        int bin = min(h->f - A.fmin[h->prob], BEAM_BINS - 1);
-        const uint32_t *hs = A.hist + (size_t)h->prob * BEAM_BINS;
-        uint32_t below = 0;
-        for (int k = 0; k < bin; ++k) below += hs[k];
-        bool keep;
-        const uint32_t width = max(16u, (uint32_t)max((float)A.width_floor, min(8192.0f, (float)A.width * exp2f(A.growth * (float)max(0, A.probs[h->prob].n - 12)))) / (uint32_t)A.width_div);
-        if (below + hs[bin] <= width) keep = true;
-        else if (below >= width) keep = false;
-        else keep = below + atomicAdd(&A.ticket[h->prob], 1u) < width;
+        const int prob = h->prob;
+        const DevProblem &P = A.probs[prob];
+        if (hdr_dead(h) || P.n == A.level + 1) continue;
+        const int bin = beam_bin(h->f, A.fmin_prev ? A.fmin_prev[prob] : P.root_lb);
+        const uint32_t cq = A.cutq[prob];
+        const int cut = (int)(cq >> 16);
+        bool keep = bin < cut;
+        if (bin == cut) keep = atomicAdd(&A.ticket[prob], 1u) < (cq & 0xffffu);
         if (keep) { uint32_t s = atomicAdd(A.next_count, 1u); A.next_list[s] = i; }
     }
 }
@@ -825,7 +855,7 @@ void StageA::free_problem_arrays()
 {
     cudaFree(d_probs_); cudaFree(d_limit_); cudaFree(d_best_score_); cudaFree(d_best_rows_);
     cudaFree(d_beam_score_); cudaFree(d_beam_rows_); cudaFree(d_cand_); cudaFree(d_node_);
-    cudaFree(d_fmin_); cudaFree(d_hist_); cudaFree(d_ticket_); cudaFree(d_incumbent_);
+    cudaFree(d_fmin_); cudaFree(d_hist_); cudaFree(d_ticket_); cudaFree(d_cutq_); cudaFree(d_incumbent_); d_cutq_ = nullptr;
     cudaFreeHost(h_probs_); cudaFreeHost(h_res_); h_probs_ = nullptr; h_res_ = nullptr; h_cap_ = 0;
     d_probs_ = nullptr; d_limit_ = d_best_score_ = d_beam_score_ = d_fmin_ = d_incumbent_ = nullptr;
     d_best_rows_ = d_beam_rows_ = d_hist_ = d_ticket_ = nullptr; d_cand_ = d_node_ = nullptr;
@@ -893,6 +923,7 @@ int StageA::ensure_problem_arrays(int count)
     // beam statistics: one slice per level, cleared once per pass
     CK(cudaMalloc(&d_fmin_, (size_t)c * 4 * AMBI_MAXN)); CK(cudaMalloc(&d_hist_, (size_t)c * BEAM_BINS * 4 * AMBI_MAXN));
     CK(cudaMalloc(&d_ticket_, (size_t)c * 4 * AMBI_MAXN));
+    CK(cudaMalloc(&d_cutq_, (size_t)c * 4 * AMBI_MAXN));
     CK(cudaMallocHost(&h_probs_, (size_t)c * sizeof(DevProblem)));
     CK(cudaMallocHost(&h_res_, (size_t)c * (4 + 4 + 8 + 8 + 4 * AMBI_MAXN)));
     h_cap_ = c;
@@ -959,29 +990,33 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     }
     k_expand<<<expand_blocks_, WPB * 32, expand_smem_, stream_>>>(L); ++launches_;
     if (prof) { CK(cudaEventRecord(prof_ev_[prof_used_ + 1], stream_)); prof_used_ += 2; }
+    const bool beam = mode == 1;
+    int32_t *fmin_cur = d_fmin_ + (size_t)level * count_;
+    const int32_t *fmin_prev = level > 0 ? d_fmin_ + (size_t)(level - 1) * count_ : nullptr;
+    uint32_t *hist = d_hist_ + (size_t)level * count_ * BEAM_BINS;
     if (merge) {
         DedupArgs D;
         D.recs = buf_[cur ^ 1]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = stride_; D.level = level; D.overflow = c_over;
+        D.probs = d_probs_; D.hist = beam ? hist : nullptr; D.fmin_cur = fmin_cur; D.fmin_prev = fmin_prev;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
     }
-    const bool beam = mode == 1;
     FinalizeArgs F;
     F.probs = d_probs_; F.recs = buf_[cur ^ 1]; F.count = c_child; F.cap = cap_;
     F.next_list = list_[cur ^ 1]; F.next_count = c_nxt;
     F.best_score = mode == 2 ? d_best_score_ : d_beam_score_; F.best_rows = mode == 2 ? d_best_rows_ : d_beam_rows_;
-    F.fmin = beam ? d_fmin_ + (size_t)level * count_ : nullptr; F.stride = stride_; F.level = level;
+    F.fmin = nullptr; F.stride = stride_; F.level = level;
     F.limit = nullptr; F.merge_best = 0; F.build_list = 0; F.overflow = c_over;
-    // outside the beam pass this kernel only collects completed assignments: skip the levels where no problem ends
-    if (beam || ((leaf_levels_ >> level) & 1u)) { k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_; }
+    // this kernel only collects completed assignments: skip the levels where no problem ends
+    if ((leaf_levels_ >> level) & 1u) { k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_; }
     if (beam) {
         BeamArgs B;
         B.probs = d_probs_; B.recs = buf_[cur ^ 1]; B.count = c_child; B.cap = cap_;
-        B.fmin = d_fmin_ + (size_t)level * count_; B.hist = d_hist_ + (size_t)level * count_ * BEAM_BINS;
+        B.fmin_prev = fmin_prev; B.hist = hist; B.cutq = d_cutq_ + (size_t)level * count_;
         B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = list_[cur ^ 1];
-        // a fixed budget of beam records per batch: few large partitions get a wide beam
-        B.next_count = c_nxt; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1))); B.stride = stride_; B.level = level; B.growth = beam_growth_; B.width_div = beam_div_;
-        k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
+        B.next_count = c_nxt; B.nprob = count_; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1)));
+        B.stride = stride_; B.level = level; B.growth = beam_growth_; B.width_div = beam_div_;
+        k_beam_cut<<<(count_ + 127) / 128, 128, 0, stream_>>>(B); ++launches_;
         k_beam_select<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
     }
     return 0;
@@ -1258,6 +1293,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         DedupArgs D;
         D.recs = buf_[0]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = stride_; D.level = level; D.overflow = c_over;
+        D.probs = d_probs_; D.hist = nullptr; D.fmin_cur = nullptr; D.fmin_prev = nullptr;
         k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
         FinalizeArgs F;

@@ -94,7 +94,7 @@ private:
     uint8_t *h_res_ = nullptr;                              // pinned result staging
     int h_cap_ = 0;
     int32_t *d_limit_ = nullptr, *d_incumbent_ = nullptr, *d_best_score_ = nullptr, *d_beam_score_ = nullptr, *d_fmin_ = nullptr;
-    uint32_t *d_best_rows_ = nullptr, *d_beam_rows_ = nullptr, *d_hist_ = nullptr, *d_ticket_ = nullptr;
+    uint32_t *d_best_rows_ = nullptr, *d_beam_rows_ = nullptr, *d_hist_ = nullptr, *d_ticket_ = nullptr, *d_cutq_ = nullptr;
     unsigned long long *d_cand_ = nullptr, *d_node_ = nullptr, *d_funnel_ = nullptr;
     unsigned long long funnel_[4] = {0, 0, 0, 0};
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
