@@ -53,14 +53,14 @@ struct DevProblem {
 };
 
 // Candidate record (one partial assignment: rows 0..level-1 fixed).
-//   col[b]  = nP | nL<<2 | bP<<4 | bL<<6 for columns b >= level, 0 elsewhere
+//   col[b]  = nP | nL<<2 | bP<<4 | bL<<6 for columns b >= level, 0 elsewhere (at byte 16 + b)
 //   rows[a] = ip<<10 | il of row a (a < level)
-struct NodeHdr {
+struct NodeHdr {             // the four header words and columns 0..15 share the record's first 32-byte sector:
+    int32_t score;           // exact deviation (x2) of segments < level          partitions of <= 16 segments
+    int32_t f;               // score + admissible bound on the rest             are merged, selected and staged
+    int32_t prob;            //                                                  from that one sector
+    int32_t tgs;             // running count of the third-generation row (bit 31: dropped by the merge)
     uint8_t col[AMBI_MAXN];
-    int32_t score;           // exact deviation (x2) of segments < level
-    int32_t f;               // score + admissible bound on the rest
-    int32_t prob;
-    int32_t tgs;             // running count of the third-generation row
 };                           // 48 bytes, followed by uint32 rows[nmax]
 
 __host__ __device__ inline size_t ambi_node_stride(int nmax) {

@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <cstddef>
 #include <vector>
 #include <algorithm>
 
@@ -227,8 +228,9 @@ __device__ __noinline__ void write_batch(GroupShared &S, const LevelArgs &A, int
         return;
     }
     uint8_t *crec = A.children + (size_t)cslot * A.stride;
-    reinterpret_cast<uint4 *>(crec)[0] = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4 *>(crec)[1] = make_uint4(0, 0, 0, 0);
+    uint8_t *ccol = crec + offsetof(NodeHdr, col);
+    reinterpret_cast<uint4 *>(ccol)[0] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4 *>(ccol)[1] = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
     for (int j = a + 1; j < n; ++j) {
         const uint32_t cb = S.colb[j][slot];
@@ -239,7 +241,7 @@ __device__ __noinline__ void write_batch(GroupShared &S, const LevelArgs &A, int
         const int kP = 2 - pab - max(rp, rl);
         const int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
         const int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
-        crec[j] = (uint8_t)((nP + pab) | ((nL + lab) << 2) | (nbP << 4) | (nbL << 6));
+        ccol[j] = (uint8_t)((nP + pab) | ((nL + lab) << 2) | (nbP << 4) | (nbL << 6));
     }
     const uint32_t tm = S.tmask[slot];
     int hits = 0;
@@ -247,7 +249,7 @@ __device__ __noinline__ void write_batch(GroupShared &S, const LevelArgs &A, int
                    (l1 >= 0 && ((tm >> l1) & 1)) + (l2 >= 0 && ((tm >> l2) & 1));
     const int sc = S.score[slot];
     // completed assignments all share one (empty) state: drop the running third-generation count
-    reinterpret_cast<int4 *>(crec)[2] = make_int4(sc + err, sc + tot, S.prob[slot], (n == a + 1) ? 0 : S.ptgs[slot] + hits);
+    reinterpret_cast<int4 *>(crec)[0] = make_int4(sc + err, sc + tot, S.prob[slot], (n == a + 1) ? 0 : S.ptgs[slot] + hits);
     const uint4 *src = reinterpret_cast<const uint4 *>(prec + sizeof(NodeHdr));
     uint4 *dst = reinterpret_cast<uint4 *>(crec + sizeof(NodeHdr));
     const int nq = (A.nmax + 3) >> 2;
@@ -379,7 +381,7 @@ k_expand(LevelArgs A_param)
             // merge dropped (their header is flagged) and the completed assignments (n == level)
             const uint32_t pidx = A.plist ? A.plist[base + lane] : base + lane;
             prec = A.parents + (size_t)pidx * A.stride;
-            int4 hd = reinterpret_cast<const int4 *>(prec)[2];             // score, f, prob, tgs
+            int4 hd = reinterpret_cast<const int4 *>(prec)[0];             // score, f, prob, tgs
             const bool dropped = (uint32_t)hd.w & 0x80000000u;
             hd.w &= 0x7fffffff;
             P = &A.probs[hd.z];
@@ -400,7 +402,7 @@ k_expand(LevelArgs A_param)
 #pragma unroll 1
         for (int j = a; j < jtop; ++j) {
             uint32_t b = 0, cjv = 0;
-            if (have && j < my_n) { b = prec[j]; cjv = P->cj[j]; }
+            if (have && j < my_n) { b = prec[offsetof(NodeHdr, col) + j]; cjv = P->cj[j]; }
             S.colb[j][lane] = (uint8_t)b;
             S.cj[j][lane] = cjv;
             const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
@@ -574,6 +576,7 @@ struct DedupArgs {
     uint32_t *hist;             // [prob][BEAM_BINS], bins of width 1 from the previous level's minimum f
     int32_t *fmin_cur;          // [prob] minimum f of this level (base of the next level's bins)
     const int32_t *fmin_prev;   // [prob] or nullptr at level 0 (base = root bound)
+    int nmax;                   // longest partition of the batch
 };
 
 // f only grows along a path, so the previous level's minimum f is a lower bound of every f of this level
@@ -585,12 +588,16 @@ __device__ __forceinline__ uint32_t hdr_tgs(const NodeHdr *h) {
 __device__ __forceinline__ bool hdr_dead(const NodeHdr *h) { return (uint32_t)h->tgs & DEAD_BIT; }
 __device__ __forceinline__ void hdr_kill(NodeHdr *h) { atomicOr(reinterpret_cast<unsigned int *>(&h->tgs), DEAD_BIT); }
 
-__device__ __forceinline__ bool same_state(const NodeHdr *x, const NodeHdr *y) {
+// `wide`: some partition of the batch has more than 16 segments (otherwise columns 16..31 are zero everywhere
+// and only the first sector of either record is touched)
+__device__ __forceinline__ bool same_state(const NodeHdr *x, const NodeHdr *y, bool wide) {
     if (x->prob != y->prob || hdr_tgs(x) != hdr_tgs(y)) return false;
     const uint4 *a = reinterpret_cast<const uint4 *>(x->col), *b = reinterpret_cast<const uint4 *>(y->col);
-    uint4 a0 = a[0], b0 = b[0], a1 = a[1], b1 = b[1];
-    return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w &&
-           a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
+    const uint4 a0 = a[0], b0 = b[0];
+    if (!(a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w)) return false;
+    if (!wide) return true;
+    const uint4 a1 = a[1], b1 = b[1];
+    return a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
 }
 
 // strict order: lower score, then smaller prefix in search order
@@ -613,13 +620,18 @@ __global__ void k_dedup(DedupArgs A)
     uint32_t tmask = 1023u;
     while (tmask < A.tmask && (tmask >> 2) < cnt) tmask = (tmask << 1) | 1u;
     tmask = min(tmask, A.tmask);
+    const bool wide = A.nmax > 16;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         uint8_t *rec = A.recs + (size_t)i * A.stride;
         NodeHdr *h = reinterpret_cast<NodeHdr *>(rec);
         const uint32_t *cw = reinterpret_cast<const uint32_t *>(h->col);
         uint32_t hv = mix32((uint32_t)h->prob * 0x9e3779b9u + hdr_tgs(h));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) hv = mix32(hv ^ cw[k]) + 0x85ebca6bu * (k + 1);
+        for (int k = 0; k < 4; ++k) hv = mix32(hv ^ cw[k]) + 0x85ebca6bu * (k + 1);
+        if (wide) {
+#pragma unroll
+            for (int k = 4; k < 8; ++k) hv = mix32(hv ^ cw[k]) + 0x85ebca6bu * (k + 1);
+        }
         uint32_t slot = hv & tmask;
         const unsigned long long mine = ((unsigned long long)gen << 32) | i;
         bool alive = false;
@@ -633,7 +645,7 @@ __global__ void k_dedup(DedupArgs A)
             }
             uint32_t o = (uint32_t)cur;
             uint8_t *orec = A.recs + (size_t)o * A.stride;
-            if (same_state(h, reinterpret_cast<const NodeHdr *>(orec))) {
+            if (same_state(h, reinterpret_cast<const NodeHdr *>(orec), wide)) {
                 if (rec_better(rec, orec, A.level + 1)) {
                     unsigned long long old = atomicCAS(&A.table[slot], cur, mine);
                     if (old == cur) { hdr_kill(reinterpret_cast<NodeHdr *>(orec)); alive = true; replaced_f = reinterpret_cast<const NodeHdr *>(orec)->f; break; }
@@ -998,7 +1010,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
         DedupArgs D;
         D.recs = buf_[cur ^ 1]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = stride_; D.level = level; D.overflow = c_over;
-        D.probs = d_probs_; D.hist = beam ? hist : nullptr; D.fmin_cur = fmin_cur; D.fmin_prev = fmin_prev;
+        D.probs = d_probs_; D.hist = beam ? hist : nullptr; D.fmin_cur = fmin_cur; D.fmin_prev = fmin_prev; D.nmax = nmax_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
     }
     FinalizeArgs F;
@@ -1293,7 +1305,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         DedupArgs D;
         D.recs = buf_[0]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = stride_; D.level = level; D.overflow = c_over;
-        D.probs = d_probs_; D.hist = nullptr; D.fmin_cur = nullptr; D.fmin_prev = nullptr;
+        D.probs = d_probs_; D.hist = nullptr; D.fmin_cur = nullptr; D.fmin_prev = nullptr; D.nmax = nmax_;
         k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
         FinalizeArgs F;
