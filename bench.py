@@ -3,7 +3,7 @@
 
 A "step" is one pass of the hot path (Stage-A fold-pattern search: incumbent pass + exact pass)
 over one batch of synthetic BFB partitions.  Workload at N=1 = BASELINE.json configs[1]:
-synthetic BFB .lh, 12 segments / 4 folds (seeded, ambigram_b200/synth.py), --batch of them per step.
+synthetic BFB .lh, 12 segments / 4 folds (seeded, ambigram_b200/synth.py), --batch (default 32768) of them per step.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, C ABI)
     python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port on host cores
