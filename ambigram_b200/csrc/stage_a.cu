@@ -29,7 +29,7 @@ namespace ambi {
 
 constexpr int WPB = 8;              // warps per block in k_expand
 constexpr int GRP = 32;             // frontier records handled together by one warp
-constexpr int BEAM_BINS = 64;
+constexpr int BEAM_BINS = 256;
 constexpr int CFG_NONE = 63;        // "no column" in a packed row configuration
 
 enum { EMIT_ALL = 0, EMIT_BEST = 1 };
@@ -576,11 +576,17 @@ struct DedupArgs {
     uint32_t *hist;             // [prob][BEAM_BINS], bins of width 1 from the previous level's minimum f
     int32_t *fmin_cur;          // [prob] minimum f of this level (base of the next level's bins)
     const int32_t *fmin_prev;   // [prob] or nullptr at level 0 (base = root bound)
+    const int32_t *limit;       // [prob] pruning limit of the pass
     int nmax;                   // longest partition of the batch
 };
 
-// f only grows along a path, so the previous level's minimum f is a lower bound of every f of this level
-__device__ __forceinline__ int beam_bin(int f, int base) { return max(0, min(f - base, BEAM_BINS - 1)); }
+// f only grows along a path, so the previous level's minimum f is a lower bound of every f of this level, and
+// the pruning limit is an upper bound: BEAM_BINS equal bins over [base, limit], of width 1 whenever that range
+// is at most BEAM_BINS wide (small copy numbers), coarser for partitions whose scores run into the thousands
+__device__ __forceinline__ int beam_bin(int f, int base, int limit) {
+    const int w = max(0, limit - base) / BEAM_BINS + 1;
+    return max(0, min((f - base) / w, BEAM_BINS - 1));
+}
 
 __device__ __forceinline__ uint32_t hdr_tgs(const NodeHdr *h) {
     return *reinterpret_cast<const volatile uint32_t *>(&h->tgs) & ~DEAD_BIT;
@@ -658,10 +664,10 @@ __global__ void k_dedup(DedupArgs A)
             const int prob = h->prob;
             const DevProblem &P = A.probs[prob];
             if (P.n != A.level + 1) {                   // completed assignments are not part of the beam
-                const int base = A.fmin_prev ? A.fmin_prev[prob] : P.root_lb;
+                const int base = A.fmin_prev ? A.fmin_prev[prob] : P.root_lb, lim = A.limit[prob];
                 uint32_t *hs = A.hist + (size_t)prob * BEAM_BINS;
-                atomicAdd(&hs[beam_bin(h->f, base)], 1u);
-                if (replaced_f != 0x7fffffff) atomicSub(&hs[beam_bin(replaced_f, base)], 1u);
+                atomicAdd(&hs[beam_bin(h->f, base, lim)], 1u);
+                if (replaced_f != 0x7fffffff) atomicSub(&hs[beam_bin(replaced_f, base, lim)], 1u);
                 atomicMin(&A.fmin_cur[prob], h->f);
             }
         }
@@ -733,6 +739,7 @@ struct BeamArgs {
     const uint32_t *count;
     uint32_t cap;
     const int32_t *fmin_prev;   // [prob] base of the bins (nullptr at level 0: root bound)
+    const int32_t *limit;       // [prob] pruning limit of the pass (top of the bins)
     const uint32_t *hist;       // [prob][BEAM_BINS], built by k_dedup
     uint32_t *cutq;             // [prob] cut bin << 16 | records still to take from it
     uint32_t *ticket;           // [prob]
@@ -774,7 +781,7 @@ __global__ void k_beam_select(BeamArgs A)
         const int prob = h->prob;
         const DevProblem &P = A.probs[prob];
         if (hdr_dead(h) || P.n == A.level + 1) continue;
-        const int bin = beam_bin(h->f, A.fmin_prev ? A.fmin_prev[prob] : P.root_lb);
+        const int bin = beam_bin(h->f, A.fmin_prev ? A.fmin_prev[prob] : P.root_lb, A.limit[prob]);
         const uint32_t cq = A.cutq[prob];
         const int cut = (int)(cq >> 16);
         bool keep = bin < cut;
@@ -933,7 +940,7 @@ int StageA::ensure_problem_arrays(int count)
     CK(cudaMalloc(&d_best_rows_, (size_t)c * AMBI_MAXN * 4)); CK(cudaMalloc(&d_beam_rows_, (size_t)c * AMBI_MAXN * 4));
     CK(cudaMalloc(&d_cand_, (size_t)c * 8)); CK(cudaMalloc(&d_node_, (size_t)c * 8));
     // beam statistics: one slice per level, cleared once per pass
-    CK(cudaMalloc(&d_fmin_, (size_t)c * 4 * AMBI_MAXN)); CK(cudaMalloc(&d_hist_, (size_t)c * BEAM_BINS * 4 * AMBI_MAXN));
+    CK(cudaMalloc(&d_fmin_, (size_t)c * 4 * AMBI_MAXN)); CK(cudaMalloc(&d_hist_, (size_t)c * BEAM_BINS * 4));       // one level's histograms, cleared per beam level
     CK(cudaMalloc(&d_ticket_, (size_t)c * 4 * AMBI_MAXN));
     CK(cudaMalloc(&d_cutq_, (size_t)c * 4 * AMBI_MAXN));
     CK(cudaMallocHost(&h_probs_, (size_t)c * sizeof(DevProblem)));
@@ -1005,12 +1012,13 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     const bool beam = mode == 1;
     int32_t *fmin_cur = d_fmin_ + (size_t)level * count_;
     const int32_t *fmin_prev = level > 0 ? d_fmin_ + (size_t)(level - 1) * count_ : nullptr;
-    uint32_t *hist = d_hist_ + (size_t)level * count_ * BEAM_BINS;
+    uint32_t *hist = d_hist_;
+    if (beam) CK(cudaMemsetAsync(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4, stream_));
     if (merge) {
         DedupArgs D;
         D.recs = buf_[cur ^ 1]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = stride_; D.level = level; D.overflow = c_over;
-        D.probs = d_probs_; D.hist = beam ? hist : nullptr; D.fmin_cur = fmin_cur; D.fmin_prev = fmin_prev; D.nmax = nmax_;
+        D.probs = d_probs_; D.hist = beam ? hist : nullptr; D.fmin_cur = fmin_cur; D.fmin_prev = fmin_prev; D.limit = d_limit_; D.nmax = nmax_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
     }
     FinalizeArgs F;
@@ -1024,7 +1032,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     if (beam) {
         BeamArgs B;
         B.probs = d_probs_; B.recs = buf_[cur ^ 1]; B.count = c_child; B.cap = cap_;
-        B.fmin_prev = fmin_prev; B.hist = hist; B.cutq = d_cutq_ + (size_t)level * count_;
+        B.fmin_prev = fmin_prev; B.limit = d_limit_; B.hist = hist; B.cutq = d_cutq_ + (size_t)level * count_;
         B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = list_[cur ^ 1];
         B.next_count = c_nxt; B.nprob = count_; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1)));
         B.stride = stride_; B.level = level; B.growth = beam_growth_; B.width_div = beam_div_;
@@ -1041,7 +1049,6 @@ int StageA::run_pass(int mode, int shard_world, bool first)
     CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
     if (mode == 1) {
         CK(cudaMemsetAsync(d_fmin_, 0x7f, (size_t)count_ * 4 * nmax_, stream_));
-        CK(cudaMemsetAsync(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4 * nmax_, stream_));
         CK(cudaMemsetAsync(d_ticket_, 0, (size_t)count_ * 4 * nmax_, stream_));
     }
     k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, buf_[0], stride_, nmax_, list_[0],
@@ -1305,7 +1312,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         DedupArgs D;
         D.recs = buf_[0]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = stride_; D.level = level; D.overflow = c_over;
-        D.probs = d_probs_; D.hist = nullptr; D.fmin_cur = nullptr; D.fmin_prev = nullptr; D.nmax = nmax_;
+        D.probs = d_probs_; D.hist = nullptr; D.fmin_cur = nullptr; D.fmin_prev = nullptr; D.limit = d_limit_; D.nmax = nmax_;
         k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
         FinalizeArgs F;
