@@ -29,7 +29,7 @@ namespace ambi {
 
 constexpr int WPB = 8;              // warps per block in k_expand
 constexpr int GRP = 32;             // frontier records handled together by one warp
-constexpr int BEAM_BINS = 256;
+constexpr int BEAM_BINS = 64;
 constexpr int CFG_NONE = 63;        // "no column" in a packed row configuration
 
 enum { EMIT_ALL = 0, EMIT_BEST = 1 };
@@ -570,23 +570,17 @@ struct DedupArgs {
     int stride;
     int level;          // rows 0..level are fixed in these records
     const uint32_t *overflow;
-    // incumbent beam only (hist != nullptr): the merge also builds the per-problem f-histogram of the records
-    // that are alive (a record replaced later takes its count back) and the level's minimum f
+    // incumbent beam only (fmin_cur != nullptr): the merge also finds the level's minimum f per problem (a record
+    // displaced later has an f at least as large as its displacer's, so records alive at insertion suffice)
     const DevProblem *probs;
-    uint32_t *hist;             // [prob][BEAM_BINS], bins of width 1 from the previous level's minimum f
-    int32_t *fmin_cur;          // [prob] minimum f of this level (base of the next level's bins)
-    const int32_t *fmin_prev;   // [prob] or nullptr at level 0 (base = root bound)
-    const int32_t *limit;       // [prob] pruning limit of the pass
+    int32_t *fmin_cur;          // [prob]
     int nmax;                   // longest partition of the batch
 };
 
-// f only grows along a path, so the previous level's minimum f is a lower bound of every f of this level, and
-// the pruning limit is an upper bound: BEAM_BINS equal bins over [base, limit], of width 1 whenever that range
-// is at most BEAM_BINS wide (small copy numbers), coarser for partitions whose scores run into the thousands
-__device__ __forceinline__ int beam_bin(int f, int base, int limit) {
-    const int w = max(0, limit - base) / BEAM_BINS + 1;
-    return max(0, min((f - base) / w, BEAM_BINS - 1));
-}
+// beam bins: width 1 from the level's minimum f, everything beyond in the last bin (the cut for the W best
+// records lies at the low end; measured: bins scaled to the whole [minimum, limit] range, or based on the
+// previous level's minimum, lose the resolution that matters and cost hard partitions their incumbent)
+__device__ __forceinline__ int beam_bin(int f, int base) { return max(0, min(f - base, BEAM_BINS - 1)); }
 
 __device__ __forceinline__ uint32_t hdr_tgs(const NodeHdr *h) {
     return *reinterpret_cast<const volatile uint32_t *>(&h->tgs) & ~DEAD_BIT;
@@ -641,7 +635,6 @@ __global__ void k_dedup(DedupArgs A)
         uint32_t slot = hv & tmask;
         const unsigned long long mine = ((unsigned long long)gen << 32) | i;
         bool alive = false;
-        int replaced_f = 0x7fffffff;                    // f of the record this one displaced, if any
         for (;;) {
             unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&A.table[slot]);
             if ((uint32_t)(cur >> 32) != gen) {
@@ -654,22 +647,15 @@ __global__ void k_dedup(DedupArgs A)
             if (same_state(h, reinterpret_cast<const NodeHdr *>(orec), wide)) {
                 if (rec_better(rec, orec, A.level + 1)) {
                     unsigned long long old = atomicCAS(&A.table[slot], cur, mine);
-                    if (old == cur) { hdr_kill(reinterpret_cast<NodeHdr *>(orec)); alive = true; replaced_f = reinterpret_cast<const NodeHdr *>(orec)->f; break; }
+                    if (old == cur) { hdr_kill(reinterpret_cast<NodeHdr *>(orec)); alive = true; break; }
                     continue;
                 } else { hdr_kill(h); break; }
             }
             slot = (slot + 1) & tmask;
         }
-        if (A.hist && alive) {
+        if (A.fmin_cur && alive) {
             const int prob = h->prob;
-            const DevProblem &P = A.probs[prob];
-            if (P.n != A.level + 1) {                   // completed assignments are not part of the beam
-                const int base = A.fmin_prev ? A.fmin_prev[prob] : P.root_lb, lim = A.limit[prob];
-                uint32_t *hs = A.hist + (size_t)prob * BEAM_BINS;
-                atomicAdd(&hs[beam_bin(h->f, base, lim)], 1u);
-                if (replaced_f != 0x7fffffff) atomicSub(&hs[beam_bin(replaced_f, base, lim)], 1u);
-                atomicMin(&A.fmin_cur[prob], h->f);
-            }
+            if (A.probs[prob].n != A.level + 1) atomicMin(&A.fmin_cur[prob], h->f);   // completed assignments are not part of the beam
         }
     }
 }
@@ -738,9 +724,8 @@ struct BeamArgs {
     const uint8_t *recs;
     const uint32_t *count;
     uint32_t cap;
-    const int32_t *fmin_prev;   // [prob] base of the bins (nullptr at level 0: root bound)
-    const int32_t *limit;       // [prob] pruning limit of the pass (top of the bins)
-    const uint32_t *hist;       // [prob][BEAM_BINS], built by k_dedup
+    const int32_t *fmin;        // [prob] minimum f of the level (k_dedup): base of the bins
+    uint32_t *hist;             // [prob][BEAM_BINS]
     uint32_t *cutq;             // [prob] cut bin << 16 | records still to take from it
     uint32_t *ticket;           // [prob]
     uint32_t *next_list;
@@ -753,6 +738,17 @@ struct BeamArgs {
     int stride;
     int level;
 };
+
+__global__ void k_beam_hist(BeamArgs A)
+{
+    uint32_t cnt = min(*A.count, A.cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const NodeHdr *h = reinterpret_cast<const NodeHdr *>(A.recs + (size_t)i * A.stride);
+        const int prob = h->prob;
+        if (hdr_dead(h) || A.probs[prob].n == A.level + 1) continue;
+        atomicAdd(&A.hist[(size_t)prob * BEAM_BINS + beam_bin(h->f, A.fmin[prob])], 1u);
+    }
+}
 
 // per problem: the bin in which the cumulative count reaches the beam width, and how many records of that bin
 // still fit (every record in a lower bin is kept, records of the cut bin draw tickets)
@@ -781,7 +777,7 @@ __global__ void k_beam_select(BeamArgs A)
         const int prob = h->prob;
         const DevProblem &P = A.probs[prob];
         if (hdr_dead(h) || P.n == A.level + 1) continue;
-        const int bin = beam_bin(h->f, A.fmin_prev ? A.fmin_prev[prob] : P.root_lb, A.limit[prob]);
+        const int bin = beam_bin(h->f, A.fmin[prob]);
         const uint32_t cq = A.cutq[prob];
         const int cut = (int)(cq >> 16);
         bool keep = bin < cut;
@@ -1011,14 +1007,13 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     if (prof) { CK(cudaEventRecord(prof_ev_[prof_used_ + 1], stream_)); prof_used_ += 2; }
     const bool beam = mode == 1;
     int32_t *fmin_cur = d_fmin_ + (size_t)level * count_;
-    const int32_t *fmin_prev = level > 0 ? d_fmin_ + (size_t)(level - 1) * count_ : nullptr;
     uint32_t *hist = d_hist_;
     if (beam) CK(cudaMemsetAsync(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4, stream_));
     if (merge) {
         DedupArgs D;
         D.recs = buf_[cur ^ 1]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = stride_; D.level = level; D.overflow = c_over;
-        D.probs = d_probs_; D.hist = beam ? hist : nullptr; D.fmin_cur = fmin_cur; D.fmin_prev = fmin_prev; D.limit = d_limit_; D.nmax = nmax_;
+        D.probs = d_probs_; D.fmin_cur = beam ? fmin_cur : nullptr; D.nmax = nmax_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
     }
     FinalizeArgs F;
@@ -1032,10 +1027,11 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     if (beam) {
         BeamArgs B;
         B.probs = d_probs_; B.recs = buf_[cur ^ 1]; B.count = c_child; B.cap = cap_;
-        B.fmin_prev = fmin_prev; B.limit = d_limit_; B.hist = hist; B.cutq = d_cutq_ + (size_t)level * count_;
+        B.fmin = fmin_cur; B.hist = hist; B.cutq = d_cutq_ + (size_t)level * count_;
         B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = list_[cur ^ 1];
         B.next_count = c_nxt; B.nprob = count_; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1)));
         B.stride = stride_; B.level = level; B.growth = beam_growth_; B.width_div = beam_div_;
+        k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
         k_beam_cut<<<(count_ + 127) / 128, 128, 0, stream_>>>(B); ++launches_;
         k_beam_select<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
     }
@@ -1312,7 +1308,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         DedupArgs D;
         D.recs = buf_[0]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = stride_; D.level = level; D.overflow = c_over;
-        D.probs = d_probs_; D.hist = nullptr; D.fmin_cur = nullptr; D.fmin_prev = nullptr; D.limit = d_limit_; D.nmax = nmax_;
+        D.probs = d_probs_; D.fmin_cur = nullptr; D.nmax = nmax_;
         k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
         FinalizeArgs F;
