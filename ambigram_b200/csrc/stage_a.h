@@ -99,11 +99,10 @@ private:
     unsigned long long funnel_[4] = {0, 0, 0, 0};
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches_ = 0;
-    bool profile_ = false, capturing_ = false, used_graph_ = false, graph_sharded_ = false;
+    bool profile_ = false, capturing_ = false, used_graph_ = false;
     cudaGraphExec_t graph_exec_ = nullptr, graph_exec2_ = nullptr;
     int graph_mode_ = 0, beam_div_ = 1;
     unsigned long long graph_launches2_ = 0;
-    uint32_t graph_gens_ = 0;
     unsigned long long graph_launches_ = 0;
     std::vector<cudaEvent_t> prof_ev_;
     size_t prof_used_ = 0;
