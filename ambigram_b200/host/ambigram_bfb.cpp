@@ -93,11 +93,19 @@ static bool parse_lh(const std::string &fn, LhGraph &g)
     for (const Seg &s : g.segs) need |= s.cn <= 0;
     for (const Junc &j : g.juncs) need |= j.cn <= 0;
     if (need) {
-        double ap = g.avg_ploidy > 0 ? g.avg_ploidy : g.purity * g.avg_tumor_ploidy + (1 - g.purity) * 2;
-        double hdp = g.avg_cov_raw * g.purity / ap;
+        // calculateHapDepth (Graph.cpp:312-367; Graph(const char*) starts with mAvgPloidy = 0, so its "AVG_PLOIDY
+        // given" branch always runs): the normal-cell share of the depth, ratio = 1 - pT / (pT + 2(1-p)), is
+        // subtracted before dividing by the haploid depth; a given AVG_PLOIDY is kept only within 0.1 of pT + 2(1-p)
+        double ap = g.avg_ploidy, ratio = 0;
+        if (g.avg_tumor_ploidy >= 0 && g.purity >= 0) {
+            const double tumour = g.purity * g.avg_tumor_ploidy, computed = tumour + (1 - g.purity) * 2;
+            ratio = 1 - tumour / computed;
+            if (std::fabs(ap - computed) > 0.1) ap = computed;
+        }
+        const double hdp = g.avg_cov_raw * g.purity / ap;
         for (Seg &s : g.segs) if (s.cn <= 0)
-            s.cn = std::max(s.id >= g.virus_start ? s.cov / g.avg_cov_raw * 2 : s.cov / hdp, 0.0);
-        for (Junc &j : g.juncs) if (j.cn <= 0) j.cn = std::max(j.cov / hdp, 0.0);
+            s.cn = std::max(s.id >= g.virus_start ? s.cov / g.avg_cov_raw * 2 : (s.cov - g.avg_cov_raw * ratio) / hdp, 0.0);
+        for (Junc &j : g.juncs) if (j.cn <= 0) j.cn = std::max((j.cov - g.avg_cov_raw * ratio) / hdp, 0.0);
     }
     return true;
 }

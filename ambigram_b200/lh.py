@@ -85,11 +85,18 @@ def parse_lh(text: str) -> LhGraph:
         raise ValueError("SOURCE/SINK count mismatch")
     # calculateHapDepth / calculateCopyNum: only entries without a positive CN are derived from depth
     if any(v <= 0 for v in g.seg_cn.values()) or any(j.cn <= 0 for j in g.juncs):
-        avg_ploidy = g.avg_ploidy
-        if avg_ploidy <= 0:
-            avg_ploidy = g.purity * g.avg_tumor_ploidy + (1 - g.purity) * 2
+        # Graph(const char*) starts with mAvgPloidy = 0 (Graph.cpp:38), so calculateHapDepth always takes its
+        # "AVG_PLOIDY given" branch (Graph.cpp:332-355): with purity and tumour ploidy present the normal-cell
+        # share of the depth, ratio = 1 - pT / (pT + 2(1-p)), is subtracted before dividing by the haploid
+        # depth, and a given AVG_PLOIDY is kept only if it is within 0.1 of pT + 2(1-p)
+        avg_ploidy, ratio = g.avg_ploidy, 0.0
+        if g.avg_tumor_ploidy >= 0 and g.purity >= 0:
+            tumour = g.purity * g.avg_tumor_ploidy
+            computed = tumour + (1 - g.purity) * 2
+            ratio = 1 - tumour / computed
+            if abs(avg_ploidy - computed) > 0.1:
+                avg_ploidy = computed
         hdp = g.avg_cov_raw * g.purity / avg_ploidy
-        ratio = 0.0
         for sid in g.seg_ids:
             if g.seg_cn[sid] > 0:
                 continue

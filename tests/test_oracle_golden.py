@@ -12,6 +12,9 @@ from tests import oracle_lib as orc
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = json.load(open(os.path.join(ROOT, "tests", "golden", "cases.json")))["cases"]
 BY_NAME = {c["name"]: c for c in CASES}
+# further input shapes (copy numbers from depth only, impure samples, large copy numbers, junction copy numbers
+# in (0.5, 1)); generated the same way (`tools/make_golden.py inputs`), CPU parity only in this round
+CASES = CASES + json.load(open(os.path.join(ROOT, "tests", "golden", "cases_extra.json")))["cases"]
 README_PATH = "1+2+3+4+5+6+|6-5-4-3-2-|2+3+4+|4-3-|3+4+|4-3-2-|2+3+4+5+6+|6-5-4-3-2-1-"          # README.md:122
 README_REV = "6-5-4-3-2-1-|1+2+3+4+5+6+|6-5-4-3-2-|2+3+4+|4-3-|3+4+|4-3-2-|2+3+4+5+6+"
 

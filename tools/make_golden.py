@@ -209,7 +209,67 @@ def extra_all():
     print("wrote", out, done, "cases with --all output")
 
 
+def zero_cn(text, hdp=15.0, normal=0.0):
+    """same profile with every explicit copy number removed (cn = 0): the reader has to derive it from the depth
+    (Graph::calculateHapDepth / calculateCopyNum, Graph.cpp:312-405); depths are cn x `hdp` + `normal` (the share
+    of the depth that normal cells contribute when PURITY < 1)"""
+    out = []
+    for ln in text.splitlines():
+        t = ln.split()
+        if t and t[0] == "SEG":
+            t[2], t[3] = str(hdp * float(t[3]) + normal), "0"
+        elif t and t[0] == "JUNC":
+            t[3], t[4] = str(hdp * float(t[4]) + normal), "0"
+        out.append(" ".join(t))
+    return "\n".join(out) + "\n"
+
+
+def extra_inputs():
+    """input shapes beyond the synthetic generator's defaults -> tests/golden/cases_extra.json (CPU parity of the
+    oracle and of the host-side flattening against the reference's own rows and printed paths)"""
+    out = os.path.join(ROOT, "tests", "golden", "cases_extra.json")
+    rng = random.Random(17)
+    cases = []
+
+    def add(name, text, **kw):
+        c = make_case(name, text, rng=rng, **kw)
+        cases.append(c)
+        print(c["name"], c["n"], c["seg_cn2"], c["fbi_cn2"], c["oracle_score2"], c.get("ref_highs_objective"), c["ref_inject_paths"][:1], flush=True)
+
+    # copy numbers derived from depth only
+    for n, folds, seed in [(6, 3, 0), (8, 3, 1), (12, 4, 2)]:
+        add(f"depth_only_n{n}_s{seed}", zero_cn(synth.generate(n, folds, seed, 0.0).lh_text()))
+    # ... with an impure sample: haploid depth = 30 * 0.5 / (0.5 * 2 + 0.5 * 2) = 7.5, normal-cell share 30 * 0.5 = 15
+    for n, folds, seed in [(6, 3, 3), (10, 4, 4)]:
+        t = synth.generate(n, folds, seed, 0.5).lh_text().replace("PURITY 1", "PURITY 0.5")
+        add(f"depth_purity_n{n}_s{seed}", zero_cn(t, 7.5, 15.0))
+    # copy numbers eight times larger (scores in the hundreds)
+    for n, folds, seed in [(6, 3, 5), (10, 4, 6)]:
+        lines = []
+        for ln in synth.generate(n, folds, seed, 0.5).lh_text().splitlines():
+            t = ln.split()
+            if t and t[0] == "SEG":
+                t[2], t[3] = str(8 * float(t[2])), str(8 * float(t[3]))
+            elif t and t[0] == "JUNC":
+                t[3], t[4] = str(8 * float(t[3])), str(8 * float(t[4]))
+            lines.append(" ".join(t))
+        add(f"big_cn_n{n}_s{seed}", "\n".join(lines) + "\n")
+    # a fold-back junction with copy number in (0.5, 1): getJuncCN rounds it up to 1 (LGM:4001-4002)
+    for n, folds, seed in [(6, 3, 7), (8, 3, 8)]:
+        lines, done = [], False
+        for ln in synth.generate(n, folds, seed, 0.0).lh_text().splitlines():
+            t = ln.split()
+            if t and t[0] == "JUNC" and not done and float(t[4]) == 1.0:
+                t[3], t[4], done = "10.5", "0.7", True
+            lines.append(" ".join(t))
+        add(f"junc_cn_0p7_n{n}_s{seed}", "\n".join(lines) + "\n")
+    json.dump({"generator": "tools/make_golden.py inputs", "cases": cases}, open(out, "w"), indent=0)
+    print("wrote", out, len(cases), "cases")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "inputs":
+        return extra_inputs()
     if len(sys.argv) > 1 and sys.argv[1] == "all":
         return extra_all()
     if len(sys.argv) > 1 and sys.argv[1] == "imperfect":
