@@ -162,3 +162,28 @@ def test_print_all_matches_reference(case):
     d = orc.construct_dag(p.n, p.start_id, dense(case["oracle_x_nz"], p.n * (p.n + 1)))
     for rev, key in ((False, "ref_inject_paths_all"), (True, "ref_inject_paths_all_rev")):
         assert reference_print_all(d, part, rev) == case[key]
+
+
+MULTI = json.load(open(os.path.join(ROOT, "tests", "golden", "cases_multi.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", MULTI, ids=[c["name"] for c in MULTI])
+def test_multi_partition_and_small_shapes(case):
+    """several partitions per .lh (searched one after the other, localhap.cpp:111), a one-segment partition and a
+    fold-back junction two segments apart: one printed path per partition, equal to the reference's wherever the
+    optimum is unique (HiGHS played cbc there, so ties are its choice)"""
+    parts = lh.flatten(lh.parse_lh(case["lh"]), [], False)
+    assert case["ref_rc"] == 0 and len(parts) == len(case["ref_highs_paths"]) == len(case["oracle_unique"])
+    compared = 0
+    for part, ref, uniq in zip(parts, case["ref_highs_paths"], case["oracle_unique"]):
+        p = part.problem
+        x, st = orc.solve(p)
+        assert int(st.unique) == uniq
+        ok, s2 = orc.model_eval(p, x)
+        assert ok and s2 == st.score2
+        d = orc.construct_dag(p.n, p.start_id, x)
+        found, flipped, order, bkp, _ = orc.first_valid_order(d, False)
+        if uniq and found:
+            assert capi.format_path(orc.expand_path(orc.imperfect_fbi(bkp, part.inversions))) == ref
+            compared += 1
+    assert compared >= (1 if case["name"].startswith("two_chrom") else 0)

@@ -267,7 +267,46 @@ def extra_inputs():
     print("wrote", out, len(cases), "cases")
 
 
+def two_chrom(n1, f1, s1, n2, f2, s2):
+    """two partitions (SOURCE a,b / SINK c,d) in one .lh: the reference searches them one after the other"""
+    a, b = synth.generate(n1, f1, s1), synth.generate(n2, f2, s2)
+    lines = ["SAMPLE two", "AVG_CHR_SEG_DP 30", "AVG_WHOLE_HOST_DP 30", "AVG_JUNC_DP 30", "PURITY 1", "AVG_TUMOR_PLOIDY 2",
+             "PLOIDY 2m1", f"VIRUS_START {n1 + n2 + 1}", f"SOURCE 1,{n1 + 1}", f"SINK {n1},{n1 + n2}"]
+    for off, smp, chrom in ((0, a, "chr7"), (n1, b, "chr8")):
+        for i, cn in enumerate(smp.seg_cn, 1):
+            lines.append(f"SEG H:{off + i}:{chrom}:{1000 * i}:{1000 * i + 999} {15.0 * cn} {float(cn)}")
+    for off, smp in ((0, a), (n1, b)):
+        for (si, sd, ti, td, cn) in smp.juncs:
+            lines.append(f"JUNC H:{off + si}:{'+' if sd > 0 else '-'} H:{off + ti}:{'+' if td > 0 else '-'} {15.0 * cn} {float(cn)} U B")
+    return "\n".join(lines) + "\n"
+
+
+def extra_multi():
+    """shapes make_case() does not take (several partitions per file, a one-segment partition, a fold-back
+    junction two segments apart): the reference's printed paths with HiGHS as the solver ->
+    tests/golden/cases_multi.json.  Paths are only comparable where the optimum is unique; the oracle says where."""
+    out = os.path.join(ROOT, "tests", "golden", "cases_multi.json")
+    texts = [(f"two_chrom_{a}", two_chrom(*a)) for a in [(6, 3, 0, 6, 3, 1), (8, 3, 1, 5, 3, 2), (5, 3, 3, 10, 4, 4), (4, 2, 5, 7, 3, 6)]]
+    texts.append(("one_segment", "SAMPLE one\nAVG_CHR_SEG_DP 30\nAVG_WHOLE_HOST_DP 30\nAVG_JUNC_DP 30\nPURITY 1\nAVG_TUMOR_PLOIDY 2\n"
+                  "PLOIDY 2m1\nVIRUS_START 2\nSOURCE 1\nSINK 1\nSEG H:1:chr7:1000:1999 60.0 4.0\nJUNC H:1:+ H:1:- 15.0 1.0 U B\n"))
+    texts.append(("foldback_two_apart", synth.generate(8, 3, 1).lh_text().replace("JUNC H:2:- H:2:+", "JUNC H:3:- H:1:+")))
+    cases = []
+    for name, text in texts:
+        rc, paths, sol, lpt, so = run_ref(text)
+        parts = lh.flatten(lh.parse_lh(text), [], False)
+        uniq = []
+        for part in parts:
+            x, st = orc.solve(part.problem, want_unique=True)
+            uniq.append(int(st.unique))
+        cases.append({"name": name, "lh": text, "ref_rc": rc, "ref_highs_paths": paths, "oracle_unique": uniq})
+        print(name, rc, paths, uniq, flush=True)
+    json.dump({"generator": "tools/make_golden.py multi", "cases": cases}, open(out, "w"), indent=0)
+    print("wrote", out, len(cases), "cases")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "multi":
+        return extra_multi()
     if len(sys.argv) > 1 and sys.argv[1] == "inputs":
         return extra_inputs()
     if len(sys.argv) > 1 and sys.argv[1] == "all":
