@@ -158,9 +158,11 @@ class Problem:
     bias: int = 1
     tgs_pairs: Sequence[int] = ()
     junc_info: bool = False
+    unit: int = 1          # seg_cn2 / fbi_cn2 are 2*unit*copies; only unit 1 is accepted by the library today
+                           # (lh.flatten(unit=...) and the oracle's *_units entry points are the next round's groundwork)
 
     def effective_loop_ub(self) -> int:
-        return int(self.loop_ub) if self.loop_ub is not None else int(sum(self.seg_cn2) // 2)
+        return int(self.loop_ub) if self.loop_ub is not None else int(sum(self.seg_cn2) // (2 * self.unit))
 
 
 @dataclass
@@ -199,6 +201,8 @@ class _Packed:
         self.sol = (_Solution * self.count)()
         self.x = []
         for i, p in enumerate(problems):
+            if getattr(p, "unit", 1) != 1:
+                raise AmbiError(-6, f"problem {i}: the CUDA path takes half-integral copy numbers only (unit = 1)")
             c2 = np.ascontiguousarray(p.seg_cn2, dtype=np.int32)
             j2 = np.ascontiguousarray(p.fbi_cn2, dtype=np.int32)
             tg = np.ascontiguousarray(p.tgs_pairs if len(p.tgs_pairs) else [0, 0], dtype=np.int32)

@@ -201,9 +201,11 @@ def get_indel_bias(g: LhGraph, start_id: int, end_id: int) -> None:
                 g.seg_cn[abs(k)] -= 1
 
 
-def flatten(g: LhGraph, components: Optional[List[List[int]]] = None, junc_info: bool = False) -> List[Partition]:
+def flatten(g: LhGraph, components: Optional[List[List[int]]] = None, junc_info: bool = False, unit: int = 1) -> List[Partition]:
     """Per SOURCE/SINK pair: getJuncCN (LGM:3989-4050), bias (localhap.cpp:141-146), getIndelBias,
-    component selection (localhap.cpp:158-162) -> the integer arrays of ambi_bfb_problem."""
+    component selection (localhap.cpp:158-162) -> the integer arrays of ambi_bfb_problem.
+    `unit`: the arrays are 2*unit*copies (copy numbers that are multiples of 1/(2*unit)); the library takes
+    unit 1 only, larger units exist for the oracle's *_units entry points."""
     components = components or []
     parts: List[Partition] = []
     for s_id, e_id in zip(g.sources, g.sinks):
@@ -238,16 +240,17 @@ def flatten(g: LhGraph, components: Optional[List[List[int]]] = None, junc_info:
         trivial = abs(sum(fbi_list)) < 1e-6 and not valid
         problem = None
         if not trivial:
-            c2 = [2 * g.seg_cn[i] for i in range(s_id, e_id + 1)]
-            j2 = [2 * v for v in fbi_list]
+            c2 = [2 * unit * g.seg_cn[i] for i in range(s_id, e_id + 1)]
+            j2 = [2 * unit * v for v in fbi_list]
             if any(abs(v - round(v)) > 1e-9 for v in c2 + j2):
-                raise ValueError("copy numbers are not half-integral (AMBI_ERR_NOT_HALF_INTEGRAL)")
+                raise ValueError("copy numbers are not half-integral (AMBI_ERR_NOT_HALF_INTEGRAL)" if unit == 1 else
+                                 f"copy numbers are not multiples of 1/{2 * unit}")
             tgs: List[int] = []
             for c in valid:
                 tgs += [min(c[0], c[-1]), max(c[0], c[-1])]
             loop_ub = int(sum(g.seg_cn[i] for i in g.seg_ids))
             problem = Problem(n=n, seg_cn2=[int(round(v)) for v in c2], fbi_cn2=[int(round(v)) for v in j2],
-                              start_id=s_id, loop_ub=loop_ub, bias=bias, tgs_pairs=tgs, junc_info=junc_info)
+                              start_id=s_id, loop_ub=loop_ub, bias=bias, tgs_pairs=tgs, junc_info=junc_info, unit=unit)
         parts.append(Partition(s_id, e_id, problem, inversions, fbi_list, trivial))
     return parts
 

@@ -36,6 +36,15 @@ int orc_model_eval(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub,
                    int n_tgs, const int32_t *tgs_pairs, int junc_info,
                    const int32_t *x, int64_t *score2)
 {
+    return orc_model_eval_units(n, c2, j2, 1, loop_ub, n_tgs, tgs_pairs, junc_info, x, score2);
+}
+
+/* The same rows with the right-hand sides in units of 1/(2*unit) copies: c2[i] = 2*unit*c_i,
+ * j2[i] = 2*unit*J_i (any copy number that is a multiple of 1/(2*unit)); *score2 = 2*unit*sum(eps). */
+int orc_model_eval_units(int n, const int32_t *c2, const int32_t *j2, int unit, int32_t loop_ub,
+                         int n_tgs, const int32_t *tgs_pairs, int junc_info,
+                         const int32_t *x, int64_t *score2)
+{
     const int H = n * (n + 1) / 2;
     int64_t tot = 0;
     int ok = 1;
@@ -50,7 +59,7 @@ int orc_model_eval(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub,
         int64_t cov = 0;
         for (int a = 0; a <= i; a++)
             for (int b = i; b < n; b++) cov += PX(a, b) + 2 * LX(a, b);
-        int64_t d = 2 * cov - c2[i];
+        int64_t d = 2 * (int64_t)unit * cov - c2[i];
         tot += d < 0 ? -d : d;
         /* coef[] of LGM:4455-4477, doubled: loops 2 (coef 1), patterns 1 (0.5) */
         int64_t fb2 = 0;
@@ -72,7 +81,7 @@ int orc_model_eval(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub,
                     }
                 if (half) fb2 += PX(a, b);
             }
-        int64_t f = fb2 - j2[i];
+        int64_t f = (int64_t)unit * fb2 - j2[i];
         tot += f < 0 ? -f : f;
     }
     /* pattern parent / children rows, LGM:4544-4583 */
@@ -220,6 +229,7 @@ typedef struct { uint8_t key[ORC_MAXN + 2]; int32_t score; uint8_t used; } memo_
 
 typedef struct {
     int n, loop_ub, has_tgs;
+    int unit;                   /* scores and right-hand sides are in units of 1/(2*unit) copies */
     int c2[ORC_MAXN], j2[ORC_MAXN];
     uint8_t tgs[ORC_MAXN][ORC_MAXN];
     /* search */
@@ -322,6 +332,7 @@ static int memo_visit(srch_t *S, int a, const st_t *st, int score)
 static int future_bound(const srch_t *S, int a, const st_t *t)
 {
     int n = S->n, lb = 0, cov = 0, capsum = 0;
+    const int U = S->unit;
     for (int j = n - 1; j > a; j--) {
         int w = t->nP[j] + 2 * t->nL[j];
         cov += w;
@@ -329,11 +340,11 @@ static int future_bound(const srch_t *S, int a, const st_t *t)
         int cap = cp + 2 * cl;
         capsum += cap;
         int fmax = 6 * (j - a) < capsum ? 6 * (j - a) : capsum;
-        int d = 2 * cov - S->c2[j];
-        if (d > 0) lb += d; else if (-d - 2 * fmax > 0) lb += -d - 2 * fmax;
+        int d = 2 * U * cov - S->c2[j];
+        if (d > 0) lb += d; else if (-d - 2 * U * fmax > 0) lb += -d - 2 * U * fmax;
         int gmax = cap + (capsum < 6 ? capsum : 6);
-        int f = w - S->j2[j];
-        if (f > 0) lb += f; else if (-f - gmax > 0) lb += -f - gmax;
+        int f = U * w - S->j2[j];
+        if (f > 0) lb += f; else if (-f - U * gmax > 0) lb += -f - U * gmax;
     }
     return lb;
 }
@@ -347,8 +358,8 @@ static void try_config(srch_t *S, int a, const st_t *st, int covC, int fbC, int 
     int np = (p1 >= 0) + (p2 >= 0), nl = (l1 >= 0) + (l2 >= 0);
     int w = np + 2 * nl;
     int fbw = (n == 1) ? 2 * nl : w;      /* pattern coefficient is 0 when n==1 */
-    int e1 = 2 * (covC + w) - S->c2[a]; if (e1 < 0) e1 = -e1;
-    int e2 = fbC + fbw - S->j2[a]; if (e2 < 0) e2 = -e2;
+    int e1 = 2 * S->unit * (covC + w) - S->c2[a]; if (e1 < 0) e1 = -e1;
+    int e2 = S->unit * (fbC + fbw) - S->j2[a]; if (e2 < 0) e2 = -e2;
     int err = e1 + e2;
     if (err > slack) return;
     st_t t = *st;
@@ -504,11 +515,20 @@ int orc_solve_shard(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub
                     int n_tgs, const int32_t *tgs_pairs, int junc_info, int want_unique,
                     int world, int rank, int shard_level, int32_t *x_out, orc_solve_stats *stats)
 {
+    return orc_solve_units(n, c2, j2, 1, loop_ub, n_tgs, tgs_pairs, junc_info, want_unique, world, rank, shard_level, x_out, stats);
+}
+
+/* Exact search with right-hand sides in units of 1/(2*unit) copies (see orc_model_eval_units);
+ * stats->score2 = 2*unit*sum(eps).  unit = 1 is the half-integral case every other entry point uses. */
+int orc_solve_units(int n, const int32_t *c2, const int32_t *j2, int unit, int32_t loop_ub,
+                    int n_tgs, const int32_t *tgs_pairs, int junc_info, int want_unique,
+                    int world, int rank, int shard_level, int32_t *x_out, orc_solve_stats *stats)
+{
     orc_solve_stats dummy;
     if (!stats) stats = &dummy;
     memset(stats, 0, sizeof *stats);
     stats->unique = -1;
-    if (n < 1 || n > ORC_MAXN) { stats->status = -1; return -1; }
+    if (n < 1 || n > ORC_MAXN || unit < 1) { stats->status = -1; return -1; }
     const int H = n * (n + 1) / 2;
     if (n == 1) {
         /* single segment: no a<b rows exist; P[s,s] in {0,1}, L[s,s] in
@@ -517,8 +537,8 @@ int orc_solve_shard(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub
         int64_t best = -1; int bp = 0, bl = 0; int64_t nopt = 0;
         for (int p = 0; p <= 1; p++)
             for (int l = 0; l <= loop_ub; l++) {
-                int64_t e1 = 2 * (p + 2 * l) - c2[0]; if (e1 < 0) e1 = -e1;
-                int64_t e2 = 2 * l - j2[0]; if (e2 < 0) e2 = -e2;
+                int64_t e1 = 2 * (int64_t)unit * (p + 2 * l) - c2[0]; if (e1 < 0) e1 = -e1;
+                int64_t e2 = 2 * (int64_t)unit * l - j2[0]; if (e2 < 0) e2 = -e2;
                 stats->candidates++;
                 if (best < 0 || e1 + e2 < best) { best = e1 + e2; bp = p; bl = l; nopt = 1; }
                 else if (e1 + e2 == best) nopt++;
@@ -528,7 +548,7 @@ int orc_solve_shard(int n, const int32_t *c2, const int32_t *j2, int32_t loop_ub
         return 0;
     }
     srch_t *S = calloc(1, sizeof *S);
-    S->n = n; S->loop_ub = loop_ub;
+    S->n = n; S->loop_ub = loop_ub; S->unit = unit;
     S->shard_world = world > 1 ? world : 1; S->shard_rank = rank;
     S->shard_level = shard_level < 0 ? 0 : (shard_level > n - 2 ? n - 2 : shard_level);
     for (int i = 0; i < n; i++) { S->c2[i] = c2[i]; S->j2[i] = j2[i]; }

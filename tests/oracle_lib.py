@@ -68,8 +68,14 @@ def solve(problem, want_unique: bool = True):
     t, nt = _tgs_rel(problem)
     x = np.zeros(problem.n * (problem.n + 1), dtype=np.int32)
     st = Stats()
-    rc = L.orc_solve(problem.n, c2.ctypes.data_as(I32P), j2.ctypes.data_as(I32P), problem.effective_loop_ub(), nt,
-                     t.ctypes.data_as(I32P), int(problem.junc_info), int(want_unique), x.ctypes.data_as(I32P), C.byref(st))
+    unit = int(getattr(problem, "unit", 1))
+    if unit != 1:       # copy numbers in units of 1/(2*unit): Stats.score2 = 2*unit*sum(eps)
+        rc = L.orc_solve_units(problem.n, c2.ctypes.data_as(I32P), j2.ctypes.data_as(I32P), unit, problem.effective_loop_ub(), nt,
+                               t.ctypes.data_as(I32P), int(problem.junc_info), int(want_unique), 1, 0, -1,
+                               x.ctypes.data_as(I32P), C.byref(st))
+    else:
+        rc = L.orc_solve(problem.n, c2.ctypes.data_as(I32P), j2.ctypes.data_as(I32P), problem.effective_loop_ub(), nt,
+                         t.ctypes.data_as(I32P), int(problem.junc_info), int(want_unique), x.ctypes.data_as(I32P), C.byref(st))
     if rc != 0:
         raise RuntimeError(f"orc_solve failed: {rc}")
     return x, st
@@ -96,8 +102,9 @@ def model_eval(problem, x) -> Tuple[bool, int]:
     t, nt = _tgs_rel(problem)
     xx = _arr(x)
     s = C.c_int64(0)
-    ok = L.orc_model_eval(problem.n, c2.ctypes.data_as(I32P), j2.ctypes.data_as(I32P), problem.effective_loop_ub(), nt,
-                          t.ctypes.data_as(I32P), int(problem.junc_info), xx.ctypes.data_as(I32P), C.byref(s))
+    ok = L.orc_model_eval_units(problem.n, c2.ctypes.data_as(I32P), j2.ctypes.data_as(I32P), int(getattr(problem, "unit", 1)),
+                                problem.effective_loop_ub(), nt, t.ctypes.data_as(I32P), int(problem.junc_info),
+                                xx.ctypes.data_as(I32P), C.byref(s))
     return bool(ok), int(s.value)
 
 

@@ -15,6 +15,9 @@ BY_NAME = {c["name"]: c for c in CASES}
 # further input shapes (copy numbers from depth only, impure samples, large copy numbers, junction copy numbers
 # in (0.5, 1)); generated the same way (`tools/make_golden.py inputs`), CPU parity only in this round
 CASES = CASES + json.load(open(os.path.join(ROOT, "tests", "golden", "cases_extra.json")))["cases"]
+# copy numbers that are multiples of 1/8 (case["unit"] = 4): what the oracle's *_units entry points are pinned by
+# (`tools/make_golden.py fractional`); the CUDA path takes unit 1 only so far
+CASES = CASES + json.load(open(os.path.join(ROOT, "tests", "golden", "cases_fractional.json")))["cases"]
 README_PATH = "1+2+3+4+5+6+|6-5-4-3-2-|2+3+4+|4-3-|3+4+|4-3-2-|2+3+4+5+6+|6-5-4-3-2-1-"          # README.md:122
 README_REV = "6-5-4-3-2-1-|1+2+3+4+5+6+|6-5-4-3-2-|2+3+4+|4-3-|3+4+|4-3-2-|2+3+4+5+6+"
 
@@ -22,7 +25,7 @@ README_REV = "6-5-4-3-2-1-|1+2+3+4+5+6+|6-5-4-3-2-|2+3+4+|4-3-|3+4+|4-3-2-|2+3+4
 def partition_of(case):
     g = lh.parse_lh(case["lh"])
     comps = lh.read_components(g, case["juncs"]) if case["juncs"] else []
-    parts = lh.flatten(g, comps, case["junc_info"])
+    parts = lh.flatten(g, comps, case["junc_info"], case.get("unit", 1))
     assert len(parts) == 1
     return parts[0]
 
@@ -76,7 +79,7 @@ def test_oracle_optimum_equals_reference_milp(case):
     ok, s2 = orc.model_eval(p, x)
     assert ok and s2 == st.score2
     if case.get("ref_highs_objective") is not None:
-        assert abs(2 * (case["ref_highs_objective"] + case["bias"]) - st.score2) < 1e-6
+        assert abs(2 * case.get("unit", 1) * (case["ref_highs_objective"] + case["bias"]) - st.score2) < 1e-6
         if st.unique == 1:      # unique optimum => solver independent => identical assignment
             assert case["ref_highs_x_nz"] == case["oracle_x_nz"]
 

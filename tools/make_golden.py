@@ -95,7 +95,7 @@ def lp_eval(lp, x, nvars):
         val = sum(c * x[i] for i, c in r if i < nvars)
         if val < lo - 1e-9 or val > hi + 1e-9:
             ok = False
-    return ok, int(round(score2))
+    return ok, score2
 
 
 def probes(problem, xopt, rng, k=24):
@@ -116,17 +116,17 @@ def probes(problem, xopt, rng, k=24):
     return out
 
 
-def make_case(name, lh_text, juncs_text="", junc_info=False, want_highs=True, rng=None):
+def make_case(name, lh_text, juncs_text="", junc_info=False, want_highs=True, rng=None, unit=1):
     rng = rng or random.Random(1)
     g = lh.parse_lh(lh_text)
     comps = lh.read_components(g, juncs_text) if juncs_text else []
-    parts = lh.flatten(g, comps, junc_info)
+    parts = lh.flatten(g, comps, junc_info, unit)
     assert len(parts) == 1 and parts[0].problem is not None, name
     p = parts[0].problem
     nv = p.n * (p.n + 1)
     case = {"name": name, "inversions": {str(k): list(v) for k, v in parts[0].inversions.items()}, "lh": lh_text, "juncs": juncs_text, "junc_info": junc_info,
             "n": p.n, "seg_cn2": list(p.seg_cn2), "fbi_cn2": list(p.fbi_cn2), "loop_ub": p.effective_loop_ub(),
-            "bias": p.bias, "tgs_pairs": list(p.tgs_pairs), "start_id": p.start_id}
+            "bias": p.bias, "tgs_pairs": list(p.tgs_pairs), "start_id": p.start_id, "unit": unit}
     x, st = orc.solve(p, want_unique=True)
     case["oracle_score2"] = int(st.score2)
     case["oracle_unique"] = int(st.unique)
@@ -147,7 +147,8 @@ def make_case(name, lh_text, juncs_text="", junc_info=False, want_highs=True, rn
     lines = lpt.splitlines()
     case["lp_rows"], case["lp_cols"] = map(int, lines[1].split())
     pr = probes(p, x, rng)
-    case["probes"] = [{"x_nz": [[i, v] for i, v in enumerate(q) if v], "feasible": bool(f), "score2": s}
+    # score2 = 2 * unit * sum(eps) of the reference's rows (an integer when the copy numbers are multiples of 1/(2*unit))
+    case["probes"] = [{"x_nz": [[i, v] for i, v in enumerate(q) if v], "feasible": bool(f), "score2": int(round(unit * s))}
                       for q in pr for (f, s) in [lp_eval(lpt, q, nv)]]
     return case
 
@@ -304,7 +305,33 @@ def extra_multi():
     print("wrote", out, len(cases), "cases")
 
 
+def extra_fractional():
+    """copy numbers that are not half-integral (multiples of 1/8): the reference's LP takes any real right-hand side;
+    the oracle's *_units entry points search in units of 1/8 copy (unit = 4) -> tests/golden/cases_fractional.json"""
+    out = os.path.join(ROOT, "tests", "golden", "cases_fractional.json")
+    rng = random.Random(23)
+    cases = []
+    for n, folds, seed in [(4, 2, 0), (5, 3, 1), (6, 3, 2), (6, 3, 3), (8, 3, 4), (8, 3, 5), (10, 4, 6), (12, 4, 7)]:
+        lines = []
+        for ln in synth.generate(n, folds, seed, 0.0).lh_text().splitlines():
+            t = ln.split()
+            if t and t[0] == "SEG":
+                cn = max(0.125, float(t[3]) + rng.randint(-3, 3) / 8.0)
+                t[2], t[3] = str(15.0 * cn), str(cn)
+            elif t and t[0] == "JUNC":
+                cn = float(t[4]) + rng.randint(0, 3) / 8.0          # stays >= 1: no rounding of (0.5, 1) involved
+                t[3], t[4] = str(15.0 * cn), str(cn)
+            lines.append(" ".join(t))
+        c = make_case(f"fractional_n{n}_s{seed}", "\n".join(lines) + "\n", rng=rng, unit=4)
+        cases.append(c)
+        print(c["name"], c["seg_cn2"], c["fbi_cn2"], c["oracle_score2"], c.get("ref_highs_objective"), c["oracle_unique"], c["ref_inject_paths"][:1], flush=True)
+    json.dump({"generator": "tools/make_golden.py fractional", "cases": cases}, open(out, "w"), indent=0)
+    print("wrote", out, len(cases), "cases")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "fractional":
+        return extra_fractional()
     if len(sys.argv) > 1 and sys.argv[1] == "multi":
         return extra_multi()
     if len(sys.argv) > 1 and sys.argv[1] == "inputs":
