@@ -128,3 +128,13 @@ def test_target_cn_is_the_coverage_of_the_assignment():
                     want[s] += int(x[i]) + 2 * int(x[H + i])
                 i += 1
         assert capi.target_cn(n, x) == want
+
+
+def test_fractional_units_are_refused_by_the_library_binding():
+    """copy numbers in units other than halves exist for the oracle only: the binding must
+    not pass such a problem to the CUDA path as if it were half-integral"""
+    p = capi.Problem(n=3, seg_cn2=[8, 9, 10], fbi_cn2=[0, 4, 0], unit=4)
+    with pytest.raises(capi.AmbiError) as e:
+        capi._Packed([p])
+    assert e.value.status == -6
+    capi._Packed([capi.Problem(n=3, seg_cn2=[8, 9, 10], fbi_cn2=[0, 4, 0])])      # unit 1 marshals fine without a GPU
