@@ -131,9 +131,11 @@ extern "C" int ambi_init(ambi_ctx **out, const ambi_config *cfg)
     if ((e = cudaSetDevice(ctx->cfg.device)) != cudaSuccess) { delete ctx; return fail(nullptr, AMBI_ERR_CUDA, cudaGetErrorString(e)); }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, AMBI_ERR_CUDA, cudaGetErrorString(e)); }
     if (ctx->sa.init(ctx->stream, ctx->cfg.node_capacity, ctx->cfg.beam_width, ctx->cfg.rank, ctx->cfg.world, ctx->cfg.shard_level)) {
-        std::string m = ctx->sa.error(); delete ctx; return fail(nullptr, AMBI_ERR_CUDA, m);
+        std::string m = ctx->sa.error(); ctx->sa.release(); cudaStreamDestroy(ctx->stream); delete ctx; return fail(nullptr, AMBI_ERR_CUDA, m);
     }
-    if (ctx->sb.init(ctx->stream)) { std::string m = ctx->sb.error(); delete ctx; return fail(nullptr, AMBI_ERR_CUDA, m); }
+    if (ctx->sb.init(ctx->stream)) {
+        std::string m = ctx->sb.error(); ctx->sa.release(); ctx->sb.release(); cudaStreamDestroy(ctx->stream); delete ctx; return fail(nullptr, AMBI_ERR_CUDA, m);
+    }
     *out = ctx;
     return AMBI_OK;
 }
@@ -201,6 +203,7 @@ extern "C" int ambi_comm_init(ambi_ctx *ctx, const void *id128)
     if (!ctx || !id128) return AMBI_ERR_BAD_ARG;
     if (!g_nccl.load()) return fail(ctx, AMBI_ERR_NCCL, "cannot load libnccl.so.2");
     cudaSetDevice(ctx->cfg.device);
+    if (ctx->comm) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_comm_init: this context already has a communicator");
     ncclUniqueId id; memcpy(&id, id128, 128);
     ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, ctx->cfg.world, id, ctx->cfg.rank);
     if (r != 0) return fail(ctx, AMBI_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
@@ -227,7 +230,7 @@ static int to_dev(const ambi_bfb_problem &p, DevProblem &d, std::string &why)
     long long z = 0;
     for (int i = 0; i < p.n; ++i) {
         if (p.seg_cn2[i] < 0 || p.fbi_cn2[i] < 0) { why = "negative copy number"; return AMBI_ERR_BAD_ARG; }
-        if (p.seg_cn2[i] > 65535 || p.fbi_cn2[i] > 65535) { why = "copy number above 32767"; return AMBI_ERR_BAD_ARG; }
+        if (p.seg_cn2[i] > 65535 || p.fbi_cn2[i] > 65535) { why = "2*copy number above 65535 (copy numbers are staged as 16-bit halves)"; return AMBI_ERR_TOO_LARGE; }
         d.c2[i] = p.seg_cn2[i]; d.j2[i] = p.fbi_cn2[i];
         d.cj[i] = (uint32_t)p.seg_cn2[i] | ((uint32_t)p.fbi_cn2[i] << 16);
         z += (long long)p.seg_cn2[i] + p.fbi_cn2[i];
@@ -248,6 +251,10 @@ static int to_dev(const ambi_bfb_problem &p, DevProblem &d, std::string &why)
         for (int t = 0; t < p.n_tgs; ++t) {
             int s = p.tgs_pairs[2 * t] - p.start_id, e = p.tgs_pairs[2 * t + 1] - p.start_id;
             if (s > e) std::swap(s, e);
+            // Documented divergence: for a span that leaves the partition the reference indexes variableIdx with a
+            // key that does not exist (std::map creates it with value 0, so P[s,s] of the partition lands in the row
+            // twice, LGM:4692-4697) -- an accident of operator[], not a model.  Such a span constrains no variable of
+            // this partition and is dropped here, as in the oracle (orc_solve_units).
             if (s < 0 || e >= p.n) continue;
             if (s == 0 && e == p.n - 1) continue;                 // LGM:4690
             d.tgs_mask[s] |= 1u << e; d.has_tgs = 1;
@@ -322,7 +329,7 @@ extern "C" int ambi_batch_upload(ambi_ctx *ctx, int32_t count, const ambi_bfb_pr
         }
     });
     if (bad_rc) { delete b; return fail(ctx, bad_rc, "problem " + std::to_string(bad_i.load()) + ": " + bad_why); }
-    if (ctx->sa.upload(stage, count)) { delete b; return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error()); }
+    if (int urc = ctx->sa.upload(stage, count)) { delete b; return fail(ctx, urc == -5 ? AMBI_ERR_FRONTIER_OVERFLOW : AMBI_ERR_CUDA, ctx->sa.error()); }
     cudaStreamSynchronize(ctx->stream);
     ctx->resident = b;
     *out = b;
@@ -446,15 +453,19 @@ extern "C" int ambi_bfb_solve(ambi_ctx *ctx, const ambi_bfb_problem *problem, am
     std::vector<int32_t> x((size_t)n * (n + 1));
     ambi_bfb_solution local = *solution;
     local.element_cn = x.data();
-    int rc = ambi_bfb_solve_shard(ctx, problem, &local);
-    if (rc) return rc;
+    // The call is collective: a rank whose shard failed (frontier overflow, bad argument, ...) still takes part in
+    // the all-gather and carries its status in word 38 of its record, so that no peer is left waiting in the
+    // collective and every rank returns the same error.
+    const int rc_local = ambi_bfb_solve_shard(ctx, problem, &local);
+    const std::string err_local = rc_local ? ctx->err : std::string();
     const int W = ctx->cfg.world;
     // pack: [score, n rows re-encoded from element_cn in search order]
     std::vector<uint32_t> rec(40, 0), all((size_t)W * 40);
-    rec[0] = (uint32_t)local.score2;
+    rec[0] = rc_local ? 0x7fffffffu : (uint32_t)local.score2;
+    rec[38] = (uint32_t)rc_local;
     // per-row keys comparable as integers: recompute the row codes from x
     const int H = n * (n + 1) / 2;
-    for (int a = 0; a < n && n > 1; ++a) {
+    for (int a = 0; a < n && n > 1 && !rc_local; ++a) {
         int p[2] = {-1, -1}, l[2] = {-1, -1}, np = 0, nl = 0;
         for (int b2 = a; b2 < n; ++b2) {
             if (x[pair_index(n, a, b2)] && np < 2) p[np++] = b2;
@@ -464,16 +475,21 @@ extern "C" int ambi_bfb_solve(ambi_ctx *ctx, const ambi_bfb_problem *problem, am
         int il = nl == 0 ? 0 : (nl == 1 ? ambi_il_code(n - 1 - l[0], -1) : ambi_il_code(n - 1 - l[0], n - 1 - l[1]));
         rec[1 + a] = ((uint32_t)ip << 10) | (uint32_t)il;
     }
-    if (n == 1) { rec[1] = 0x80000000u | ((uint32_t)x[0] << 20) | (uint32_t)x[1]; }
+    if (n == 1 && !rc_local) { rec[1] = 0x80000000u | ((uint32_t)x[0] << 20) | (uint32_t)x[1]; }
     rec[34] = (uint32_t)(local.candidates_scored & 0xffffffffu); rec[35] = (uint32_t)(local.candidates_scored >> 32);
     rec[36] = (uint32_t)(local.nodes_expanded & 0xffffffffu); rec[37] = (uint32_t)(local.nodes_expanded >> 32);
     cudaSetDevice(ctx->cfg.device);
     uint32_t *d_send = ctx->d_gather, *d_recv = ctx->d_gather + 40;
-    cudaMemcpyAsync(d_send, rec.data(), 160, cudaMemcpyHostToDevice, ctx->stream);
+    if (cudaMemcpyAsync(d_send, rec.data(), 160, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return fail(ctx, AMBI_ERR_CUDA, "all-gather: H2D failed");
     ncclResult_t r = g_nccl.AllGather(d_send, d_recv, 40, kNcclUint32, ctx->comm, ctx->stream);
     if (r != 0) return fail(ctx, AMBI_ERR_NCCL, "ncclAllGather failed");
-    cudaMemcpyAsync(all.data(), d_recv, (size_t)W * 160, cudaMemcpyDeviceToHost, ctx->stream);
+    if (cudaMemcpyAsync(all.data(), d_recv, (size_t)W * 160, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return fail(ctx, AMBI_ERR_CUDA, "all-gather: D2H failed");
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(ctx, AMBI_ERR_CUDA, "all-gather sync failed");
+    if (rc_local) return fail(ctx, rc_local, err_local);
+    for (int w = 0; w < W; ++w) {
+        const int rc_w = (int)(int32_t)all[(size_t)w * 40 + 38];
+        if (rc_w) return fail(ctx, rc_w, "prefix-sharded solve: rank " + std::to_string(w) + " failed: " + ambi_status_string(rc_w));
+    }
     int best = 0; uint64_t cands = 0, nodes = 0;
     for (int w = 0; w < W; ++w) {
         const uint32_t *q = &all[(size_t)w * 40], *bq = &all[(size_t)best * 40];
@@ -577,7 +593,8 @@ extern "C" int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int
     bool trunc = false;
     const int fwd0 = reversed ? 0 : 1;
     int rc = ctx->sb.run_all(*dag, fwd0, max_orders, first, bfirst, &tested, &trunc);
-    if (rc) return fail(ctx, rc == -2 ? AMBI_ERR_TOO_LARGE : AMBI_ERR_CUDA, ctx->sb.error());
+    auto sb_status = [](int r) { return r == -2 ? AMBI_ERR_BAD_ARG : (r == -3 ? AMBI_ERR_TOO_LARGE : AMBI_ERR_CUDA); };
+    if (rc) return fail(ctx, sb_status(rc), ctx->sb.error());
     if (trunc) return fail(ctx, AMBI_ERR_TOO_LARGE, "more valid orders than max_orders");
     // lexicographically last topological order: always take the highest free index
     std::vector<int32_t> last;
@@ -596,7 +613,7 @@ extern "C" int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int
     const bool last_valid = have_orders && std::binary_search(first.begin(), first.end(), last);
     if (have_orders && !last_valid) {
         rc = ctx->sb.run_all(*dag, 1 - fwd0, max_orders - (int32_t)first.size() > 0 ? max_orders - (int32_t)first.size() : 1, second, bsecond, &tested, &trunc);
-        if (rc) return fail(ctx, AMBI_ERR_CUDA, ctx->sb.error());
+        if (rc) return fail(ctx, sb_status(rc), ctx->sb.error());
         if (trunc) return fail(ctx, AMBI_ERR_TOO_LARGE, "more valid orders than max_orders");
     }
     if ((int64_t)first.size() + (int64_t)second.size() > max_orders) return fail(ctx, AMBI_ERR_TOO_LARGE, "more valid orders than max_orders");

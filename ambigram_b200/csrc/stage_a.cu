@@ -1235,6 +1235,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
         pool_bytes_ = std::min<size_t>(free_b / 2, 8 * buf_bytes_);
+        if (const char *e = getenv("AMBI_POOL_BYTES")) { long long v = atoll(e); if (v > 0) pool_bytes_ = std::min<size_t>(pool_bytes_, (size_t)v); }   // test knob: force "pool exhausted"
         CK(cudaMalloc(&pool_, pool_bytes_));
     }
     int sw = sharded ? world_ : 1;
@@ -1341,6 +1342,7 @@ __global__ void k_reset_best(const DevProblem *probs, int count, int32_t *best_s
 
 int StageA::fetch_raw(Fetched *F)
 {
+    chunked_failed_ = false;
     {   // a level of the breadth-first exact pass did not fit: continue depth-first in chunks
         uint32_t over = 0;
         CK(cudaMemcpyAsync(&over, counters_ + CTR_OVERFLOW, 4, cudaMemcpyDeviceToHost, stream_));
@@ -1362,7 +1364,11 @@ int StageA::fetch_raw(Fetched *F)
             const int lvl = (int)over - 1;
             const bool resume = lvl >= 1 && getenv("AMBI_CHUNKED_FROM_ROOT") == nullptr;
             if (!resume) { k_reset_best<<<(count_ + 127) / 128, 128, 0, stream_>>>(d_probs_, count_, d_best_score_); ++launches_; }
-            if (int rc = run_chunked(last_sharded_, resume ? lvl : 0, exchange)) { if (rc != -5) return rc; }
+            // -5 = the depth-first pass itself ran out of room (frontier pool exhausted / too small, or one record's
+            // children exceed a buffer): whatever partial best exists is NOT proven optimal, so the failure is
+            // reported as a frontier overflow (run_chunked_core clears the device flag per chunk; this host flag
+            // is what fetch reports)
+            if (int rc = run_chunked(last_sharded_, resume ? lvl : 0, exchange)) { if (rc != -5) return rc; chunked_failed_ = true; }
         } else if (exchange) {
             k_fold_best_into_limit<<<(count_ + 127) / 128, 128, 0, stream_>>>(count_, d_limit_, d_best_score_); ++launches_;
             int total = 1;
@@ -1395,8 +1401,8 @@ int StageA::fetch_raw(Fetched *F)
         for (size_t i = 0; i + 1 < prof_used_; i += 2) { float m = 0; cudaEventElapsedTime(&m, prof_ev_[i], prof_ev_[i + 1]); prof_expand_ms_ += m; }
     }
     F->score = h_score; F->incumbent = h_inc; F->rows = h_rows; F->rows_stride = rs; F->cand = h_cand; F->node = h_node;
-    F->overflow = ctr[CTR_OVERFLOW] != 0; F->seconds = ms_all * 1e-3; F->seconds_beam = ms_beam * 1e-3; F->used_graph = used_graph_;
-    if (F->overflow) snprintf(err_, sizeof err_, "frontier overflow: more than %u candidate records in one level", cap_);
+    F->overflow = ctr[CTR_OVERFLOW] != 0 || chunked_failed_; F->seconds = ms_all * 1e-3; F->seconds_beam = ms_beam * 1e-3; F->used_graph = used_graph_;
+    if (F->overflow && !chunked_failed_) snprintf(err_, sizeof err_, "frontier overflow: more than %u candidate records in one level", cap_);
     return 0;
 }
 

@@ -28,7 +28,8 @@ constexpr int MAXPATH = 1024;
 struct DevDag {
     int32_t k, base, reversed, pad;
     int8_t kind[MAXK];
-    int8_t a[MAXK], b[MAXK], cn[MAXK];     // relative ids (id - base + 1 >= 1)
+    int8_t a[MAXK], b[MAXK];               // relative ids (id - base + 1 >= 1)
+    int16_t cn[MAXK];                      // a one-segment partition may hold a loop of multiplicity up to loop_ub
     uint64_t adj[MAXK];
 };
 
@@ -96,7 +97,7 @@ __device__ __forceinline__ void seed(const DevDag &D, int v, bool forward, int8_
         if (forward) { B[0] = (int8_t)a; B[1] = (int8_t)b; } else { B[0] = (int8_t)-b; B[1] = (int8_t)-a; }
         len = 2;
     } else {
-        for (int c = 0; c < D.cn[v]; ++c) {
+        for (int c = 0; c < D.cn[v] && len + 4 <= MAXPATH; ++c) {   // the host refuses 4*cn > MAXPATH (to_devdag)
             if (forward) { B[len] = (int8_t)a; B[len + 1] = (int8_t)b; B[len + 2] = (int8_t)-b; B[len + 3] = (int8_t)-a; }
             else         { B[len] = (int8_t)-b; B[len + 1] = (int8_t)-a; B[len + 2] = (int8_t)a; B[len + 3] = (int8_t)b; }
             len += 4;
@@ -326,8 +327,8 @@ StageB::StageB() { err_[0] = 0; }
 StageB::~StageB() { release(); }
 void StageB::release()
 {
-    cudaFree(d_dags_); cudaFree(d_out_); cudaFree(d_work_); cudaFreeHost(h_dags_); cudaFreeHost(h_out_);
-    d_dags_ = d_out_ = d_work_ = h_dags_ = h_out_ = nullptr; cap_ = 0;
+    cudaFree(d_dags_); cudaFree(d_out_); cudaFree(d_work_); cudaFree(d_all_); cudaFreeHost(h_dags_); cudaFreeHost(h_out_);
+    d_dags_ = d_out_ = d_work_ = d_all_ = h_dags_ = h_out_ = nullptr; cap_ = 0; all_bytes_ = 0;
 }
 
 int StageB::init(cudaStream_t stream)
@@ -353,26 +354,33 @@ int StageB::ensure(int count)
     return 0;
 }
 
+// Host-side narrowing of one ambi_dag into the device layout, with every range the kernels rely on checked:
+// -2 bad argument, -3 too large (span of more than 120 segments, a loop whose 4*cn vertices exceed the path buffer).
+int StageB::to_devdag(const ambi_dag &g, int reversed, DevDag &d, int index)
+{
+    memset(&d, 0, sizeof d);
+    if (g.k < 0 || g.k > MAXK) { snprintf(err_, sizeof err_, "dag %d: k=%d out of range", index, g.k); return -2; }
+    int base = 0x7fffffff, top = 0;
+    for (int v = 0; v < g.k; ++v) { if (g.a[v] < base) base = g.a[v]; if (g.b[v] > top) top = g.b[v]; }
+    if (g.k == 0) base = 1;
+    if (g.k > 0 && top - base + 1 > 120) { snprintf(err_, sizeof err_, "dag %d: segment span too large", index); return -3; }
+    d.k = g.k; d.base = base; d.reversed = reversed;
+    for (int v = 0; v < g.k; ++v) {
+        if (g.cn[v] < 1 || g.a[v] > g.b[v]) { snprintf(err_, sizeof err_, "dag %d: node %d has cn %d, span %d..%d", index, v, g.cn[v], g.a[v], g.b[v]); return -2; }
+        if (g.kind[v] != 0 && 4 * (int)g.cn[v] > MAXPATH) { snprintf(err_, sizeof err_, "dag %d: loop multiplicity %d exceeds the path buffer", index, g.cn[v]); return -3; }
+        d.kind[v] = g.kind[v]; d.a[v] = (int8_t)(g.a[v] - base + 1); d.b[v] = (int8_t)(g.b[v] - base + 1);
+        d.cn[v] = g.cn[v]; d.adj[v] = g.adj[v];
+    }
+    return 0;
+}
+
 int StageB::run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_order_result *results)
 {
     if (count <= 0) return 0;
     if (int rc = ensure(count)) return rc;
     DevDag *h = reinterpret_cast<DevDag *>(h_dags_);
-    for (int i = 0; i < count; ++i) {
-        const ambi_dag &g = dags[i];
-        DevDag &d = h[i];
-        memset(&d, 0, sizeof d);
-        if (g.k < 0 || g.k > MAXK) { snprintf(err_, sizeof err_, "dag %d: k=%d out of range", i, g.k); return -2; }
-        int base = 0x7fffffff, top = 0;
-        for (int v = 0; v < g.k; ++v) { if (g.a[v] < base) base = g.a[v]; if (g.b[v] > top) top = g.b[v]; }
-        if (g.k == 0) base = 1;
-        if (g.k > 0 && top - base + 1 > 120) { snprintf(err_, sizeof err_, "dag %d: segment span too large", i); return -3; }
-        d.k = g.k; d.base = base; d.reversed = reversed ? reversed[i] : 0;
-        for (int v = 0; v < g.k; ++v) {
-            d.kind[v] = g.kind[v]; d.a[v] = (int8_t)(g.a[v] - base + 1); d.b[v] = (int8_t)(g.b[v] - base + 1);
-            d.cn[v] = (int8_t)g.cn[v]; d.adj[v] = g.adj[v];
-        }
-    }
+    for (int i = 0; i < count; ++i)
+        if (int rc = to_devdag(dags[i], reversed ? reversed[i] : 0, h[i], i)) return rc;
     CKB(cudaMemcpyAsync(d_dags_, h, (size_t)count * sizeof(DevDag), cudaMemcpyHostToDevice, stream_));
     CKB(cudaMemsetAsync(d_work_, 0, 64, stream_));
     int blocks = (count + 3) / 4; if (blocks > sms_ * 8) blocks = sms_ * 8;
@@ -394,19 +402,6 @@ int StageB::run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_o
     return 0;
 }
 
-static void to_devdag(const ambi_dag &g, int reversed, DevDag &d)
-{
-    memset(&d, 0, sizeof d);
-    int base = 0x7fffffff;
-    for (int v = 0; v < g.k; ++v) if (g.a[v] < base) base = g.a[v];
-    if (g.k == 0) base = 1;
-    d.k = g.k; d.base = base; d.reversed = reversed;
-    for (int v = 0; v < g.k; ++v) {
-        d.kind[v] = g.kind[v]; d.a[v] = (int8_t)(g.a[v] - base + 1); d.b[v] = (int8_t)(g.b[v] - base + 1);
-        d.cn[v] = (int8_t)g.cn[v]; d.adj[v] = g.adj[v];
-    }
-}
-
 // every valid order of one orientation, sorted lexicographically (the reference's print order)
 int StageB::run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::vector<std::vector<int32_t>> &out,
                     std::vector<std::vector<int32_t>> &bkp_out, unsigned long long *tested, bool *truncated)
@@ -415,17 +410,26 @@ int StageB::run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::v
     if (dag.k <= 0) return 0;
     if (dag.k > MAXK) return -2;
     if (int rc = ensure(1)) return rc;
-    DevDag h; to_devdag(dag, 0, h);
-    int32_t *d_orders = nullptr, *d_lens = nullptr; uint32_t *d_cnt = nullptr; int8_t *d_bkps = nullptr;
-    CKB(cudaMalloc(&d_orders, (size_t)max_orders * dag.k * sizeof(int32_t)));
-    CKB(cudaMalloc(&d_bkps, (size_t)max_orders * MAXPATH));
-    CKB(cudaMalloc(&d_lens, (size_t)max_orders * sizeof(int32_t)));
-    CKB(cudaMalloc(&d_cnt, 16));
+    DevDag h;
+    if (int rc = to_devdag(dag, 0, h, 0)) return rc;
+    // grow-only scratch kept in the object (no per-call cudaMalloc, nothing to leak on the error paths)
+    const size_t need = (size_t)max_orders * ((size_t)dag.k * sizeof(int32_t) + MAXPATH + sizeof(int32_t)) + 64;
+    if (need > all_bytes_) {
+        cudaFree(d_all_); d_all_ = nullptr; all_bytes_ = 0;
+        CKB(cudaMalloc(&d_all_, need));
+        all_bytes_ = need;
+    }
+    uint8_t *base = static_cast<uint8_t *>(d_all_);
+    uint32_t *d_cnt = reinterpret_cast<uint32_t *>(base);
+    int32_t *d_orders = reinterpret_cast<int32_t *>(base + 64);
+    int32_t *d_lens = d_orders + (size_t)max_orders * dag.k;
+    int8_t *d_bkps = reinterpret_cast<int8_t *>(d_lens + max_orders);
     CKB(cudaMemsetAsync(d_cnt, 0, 16, stream_));
     CKB(cudaMemcpyAsync(d_dags_, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
     k_all_valid_orders<<<sms_, 128, 0, stream_>>>((const DevDag *)d_dags_, forward, d_orders, d_bkps, d_lens, (uint32_t)max_orders, d_cnt,
                                                    (unsigned long long *)(d_cnt + 2));
     ++launches_;
+    CKB(cudaGetLastError());
     uint32_t cnt[4] = {0, 0, 0, 0};
     CKB(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, stream_));
     CKB(cudaStreamSynchronize(stream_));
@@ -434,11 +438,11 @@ int StageB::run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::v
     std::vector<int32_t> flat((size_t)n * dag.k), lens(n);
     std::vector<int8_t> paths((size_t)n * MAXPATH);
     if (n) {
-        CKB(cudaMemcpy(flat.data(), d_orders, flat.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        CKB(cudaMemcpy(lens.data(), d_lens, lens.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        CKB(cudaMemcpy(paths.data(), d_bkps, paths.size(), cudaMemcpyDeviceToHost));
+        CKB(cudaMemcpyAsync(flat.data(), d_orders, flat.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        CKB(cudaMemcpyAsync(lens.data(), d_lens, lens.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        CKB(cudaMemcpyAsync(paths.data(), d_bkps, paths.size(), cudaMemcpyDeviceToHost, stream_));
+        CKB(cudaStreamSynchronize(stream_));
     }
-    cudaFree(d_orders); cudaFree(d_cnt); cudaFree(d_bkps); cudaFree(d_lens);
     // the lanes append in any order: sort lexicographically (the order the reference prints)
     std::vector<uint32_t> perm(n);
     for (uint32_t i = 0; i < n; ++i) perm[i] = i;

@@ -7,6 +7,8 @@
 
 namespace ambi {
 
+struct DevDag;
+
 class StageB {
 public:
     StageB();
@@ -22,9 +24,12 @@ public:
 
 private:
     int ensure(int count);
+    int to_devdag(const ambi_dag &g, int reversed, DevDag &d, int index);
     cudaStream_t stream_ = nullptr;
     int cap_ = 0, sms_ = 148;
     void *d_dags_ = nullptr, *d_out_ = nullptr, *d_work_ = nullptr, *h_dags_ = nullptr, *h_out_ = nullptr;
+    void *d_all_ = nullptr;            // --all scratch: counters | orders | lengths | paths (grow-only)
+    size_t all_bytes_ = 0;
     unsigned long long launches_ = 0;
     char err_[256];
 };

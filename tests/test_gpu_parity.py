@@ -194,6 +194,23 @@ def test_overflow_is_reported_loudly(monkeypatch):
         assert e.value.status == -5
 
 
+def test_exhausted_frontier_pool_is_an_error_never_a_silent_answer(monkeypatch):
+    """the chunked depth-first pass itself can run out of room (frontier pool exhausted): the partial best it
+    holds is not proven optimal, so the call must return AMBI_ERR_FRONTIER_OVERFLOW, never AMBI_OK"""
+    monkeypatch.setenv("AMBI_POOL_BYTES", "65536")
+    p = lh.problem_from_lh(synth.generate(20, 6, 1, 0.5).lh_text())
+    with capi.Context(device=0, node_capacity=4096) as c:
+        with pytest.raises(capi.AmbiError) as e:
+            c.solve(p)
+        assert e.value.status == -5
+        with pytest.raises(capi.AmbiError) as e:
+            c.solve_batch([p, p])
+        assert e.value.status == -5
+    monkeypatch.delenv("AMBI_POOL_BYTES")
+    with capi.Context(device=0, node_capacity=4096) as c:        # same buffers, default pool: exact answer
+        check_against_oracle(p, c.solve(p))
+
+
 def test_bad_arguments(ctx):
     with pytest.raises(capi.AmbiError):
         ctx.solve(Problem(n=33, seg_cn2=[2] * 33, fbi_cn2=[0] * 33))
