@@ -32,7 +32,7 @@ class AmbiError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32), ("beam_width", C.c_int32),
-                ("node_capacity", C.c_int64), ("shard_level", C.c_int32), ("reserved", C.c_int32)]
+                ("node_capacity", C.c_int64), ("shard_level", C.c_int32), ("flags", C.c_uint32)]
 
 
 class _Problem(C.Structure):
@@ -52,7 +52,8 @@ class _Profile(C.Structure):
     _fields_ = [("expand_ms", C.c_double), ("expand_launches", C.c_uint64), ("total_ms", C.c_double),
                 ("incumbent_pass_ms", C.c_double), ("record_stride", C.c_uint64), ("configs_enumerated", C.c_uint64),
                 ("bounds_evaluated", C.c_uint64), ("children_written", C.c_uint64), ("bound_batches", C.c_uint64), ("exchange_rounds", C.c_uint64),
-                ("chunked_runs", C.c_uint64)]
+                ("chunked_runs", C.c_uint64), ("small_ms", C.c_double), ("small_solved", C.c_uint64), ("global_solved", C.c_uint64),
+                ("small_capacity", C.c_uint64)]
 
 
 class _Peaks(C.Structure):
@@ -279,9 +280,10 @@ class Context:
     """ambi_ctx: one per process / GPU."""
 
     def __init__(self, device: int = 0, rank: int = 0, world: int = 1, beam_width: int = 0,
-                 node_capacity: int = 0, shard_level: int = 0, lib_path: Optional[str] = None):
+                 node_capacity: int = 0, shard_level: int = 0, lib_path: Optional[str] = None, small_kernel: bool = True):
         self.lib = load_library(lib_path)
-        cfg = _Config(device, rank, world, beam_width, node_capacity, shard_level, 0)
+        # small_kernel=False (AMBI_CFG_NO_SMALL): every partition takes the level-synchronous global-memory path
+        cfg = _Config(device, rank, world, beam_width, node_capacity, shard_level, 0 if small_kernel else 1)
         self.handle = C.c_void_p()
         rc = self.lib.ambi_init(C.byref(self.handle), C.byref(cfg))
         if rc != 0:
@@ -352,7 +354,8 @@ class Context:
                 "incumbent_pass_ms": p.incumbent_pass_ms, "record_stride": int(p.record_stride),
                 "configs_enumerated": int(p.configs_enumerated), "bounds_evaluated": int(p.bounds_evaluated),
                 "children_written": int(p.children_written), "bound_batches": int(p.bound_batches), "exchange_rounds": int(p.exchange_rounds),
-                "chunked_runs": int(p.chunked_runs)}
+                "chunked_runs": int(p.chunked_runs), "small_ms": p.small_ms, "small_solved": int(p.small_solved),
+                "global_solved": int(p.global_solved), "small_capacity": int(p.small_capacity)}
 
     def measure_peaks(self) -> dict:
         """on-box INT32 issue rate (alu pipe; alu + fma pipes) and shared-memory bandwidth"""

@@ -7,7 +7,9 @@
 //   dedup table         u64 open-addressing slots (generation<<32 | record idx)
 #pragma once
 #include <stdint.h>
+#ifndef AMBI_EMU            // tests/emu compiles the shared definitions with g++ (no CUDA headers)
 #include <cuda_runtime.h>
+#endif
 
 #define AMBI_MAXN 32
 #define AMBI_BUD_INF 3          // "no cap yet" column budget (row 0 only)
@@ -37,6 +39,10 @@ __host__ __device__ inline int ambi_il_code(int q1, int q2) {   // q1 >= q2; q2=
     if (q2 == q1) return base + 1 + q1;
     return base + 1 + q2;
 }
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 
 struct DevProblem {
     int32_t n;

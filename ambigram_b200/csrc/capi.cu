@@ -8,6 +8,7 @@
 #include "ambi_common.cuh"
 #include "stage_a.h"
 #include "stage_b.h"
+#include "host_flatten.h"
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -130,7 +131,7 @@ extern "C" int ambi_init(ambi_ctx **out, const ambi_config *cfg)
     if (ctx->cfg.device < 0 || ctx->cfg.device >= ndev) { delete ctx; return fail(nullptr, AMBI_ERR_BAD_ARG, "ambi_init: bad device ordinal"); }
     if ((e = cudaSetDevice(ctx->cfg.device)) != cudaSuccess) { delete ctx; return fail(nullptr, AMBI_ERR_CUDA, cudaGetErrorString(e)); }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, AMBI_ERR_CUDA, cudaGetErrorString(e)); }
-    if (ctx->sa.init(ctx->stream, ctx->cfg.node_capacity, ctx->cfg.beam_width, ctx->cfg.rank, ctx->cfg.world, ctx->cfg.shard_level)) {
+    if (ctx->sa.init(ctx->stream, ctx->cfg.node_capacity, ctx->cfg.beam_width, ctx->cfg.rank, ctx->cfg.world, ctx->cfg.shard_level, (ctx->cfg.flags & AMBI_CFG_NO_SMALL) == 0)) {
         std::string m = ctx->sa.error(); ctx->sa.release(); cudaStreamDestroy(ctx->stream); delete ctx; return fail(nullptr, AMBI_ERR_CUDA, m);
     }
     if (ctx->sb.init(ctx->stream)) {
@@ -174,6 +175,8 @@ extern "C" int ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out)
     const unsigned long long *f = ctx->sa.funnel();
     out->configs_enumerated = f[0]; out->bounds_evaluated = f[1]; out->children_written = f[2]; out->bound_batches = f[3];
     out->exchange_rounds = ctx->sa.exchange_rounds(); out->chunked_runs = ctx->sa.chunked_runs();
+    out->small_ms = ctx->sa.small_ms(); out->small_solved = (uint64_t)ctx->sa.small_solved(); out->global_solved = (uint64_t)ctx->sa.global_solved();
+    out->small_capacity = (uint64_t)ctx->sa.small_capacity();
     return AMBI_OK;
 }
 namespace ambi { int measure_peaks(cudaStream_t st, ambi_peaks *out); }
@@ -215,87 +218,6 @@ extern "C" int ambi_comm_init(ambi_ctx *ctx, const void *id128)
         return g_nccl.AllReduce(d_buf, d_buf, (size_t)count, kNcclInt32, nccl_op[op], c->comm, c->stream) != 0;
     }, ctx);
     return AMBI_OK;
-}
-
-// ---- problem flattening ----------------------------------------------------
-static int to_dev(const ambi_bfb_problem &p, DevProblem &d, std::string &why)
-{
-    memset(&d, 0, sizeof d);
-    if (p.n < 1) { why = "n < 1"; return AMBI_ERR_BAD_ARG; }
-    if (p.n > AMBI_MAX_SEGMENTS) { why = "n > AMBI_MAX_SEGMENTS"; return AMBI_ERR_TOO_LARGE; }
-    if (!p.seg_cn2 || !p.fbi_cn2) { why = "null copy-number arrays"; return AMBI_ERR_BAD_ARG; }
-    d.n = p.n;
-    d.loop_ub = p.loop_ub < 0 ? 0 : p.loop_ub;
-    d.lmax = d.loop_ub < 2 ? d.loop_ub : 2;
-    long long z = 0;
-    for (int i = 0; i < p.n; ++i) {
-        if (p.seg_cn2[i] < 0 || p.fbi_cn2[i] < 0) { why = "negative copy number"; return AMBI_ERR_BAD_ARG; }
-        if (p.seg_cn2[i] > 65535 || p.fbi_cn2[i] > 65535) { why = "2*copy number above 65535 (copy numbers are staged as 16-bit halves)"; return AMBI_ERR_TOO_LARGE; }
-        d.c2[i] = p.seg_cn2[i]; d.j2[i] = p.fbi_cn2[i];
-        d.cj[i] = (uint32_t)p.seg_cn2[i] | ((uint32_t)p.fbi_cn2[i] << 16);
-        z += (long long)p.seg_cn2[i] + p.fbi_cn2[i];
-    }
-    if (z > 0x3fffffff) { why = "copy numbers too large"; return AMBI_ERR_BAD_ARG; }
-    d.zero_score = (int32_t)z;
-    {   // bound before any row is fixed: every column may still take 2 patterns + 2 loops (cap 6),
-        // every row adds at most 6 (child_bound() with a = -1 and an empty state)
-        long long lb = 0;
-        for (int j = 0; j < p.n; ++j) {
-            int fmax = std::min(6 * (j + 1), 6 * (p.n - j));
-            lb += std::max(0, p.seg_cn2[j] - 2 * fmax);
-            lb += std::max(0, p.fbi_cn2[j] - (6 + std::min(6 * (p.n - j), 6)));
-        }
-        d.root_lb = (int32_t)std::min<long long>(lb, z);
-    }
-    if (p.n_tgs > 0 && (p.flags & AMBI_FLAG_JUNC_INFO) && p.tgs_pairs) {
-        for (int t = 0; t < p.n_tgs; ++t) {
-            int s = p.tgs_pairs[2 * t] - p.start_id, e = p.tgs_pairs[2 * t + 1] - p.start_id;
-            if (s > e) std::swap(s, e);
-            // Documented divergence: for a span that leaves the partition the reference indexes variableIdx with a
-            // key that does not exist (std::map creates it with value 0, so P[s,s] of the partition lands in the row
-            // twice, LGM:4692-4697) -- an accident of operator[], not a model.  Such a span constrains no variable of
-            // this partition and is dropped here, as in the oracle (orc_solve_units).
-            if (s < 0 || e >= p.n) continue;
-            if (s == 0 && e == p.n - 1) continue;                 // LGM:4690
-            d.tgs_mask[s] |= 1u << e; d.has_tgs = 1;
-        }
-    }
-    return AMBI_OK;
-}
-
-static void decode_codes(uint32_t code, int n, int out[4])
-{
-    // inverse of ambi_ip_code / ambi_il_code: columns p1<p2, l1<=l2 (or -1)
-    out[0] = out[1] = out[2] = out[3] = -1;
-    int ip = code >> 10, il = code & 1023;
-    if (ip) {
-        int q1 = 0; while (ambi_ip_code(q1 + 1, -1) <= ip) ++q1;
-        int off = ip - ambi_ip_code(q1, -1);
-        out[0] = n - 1 - q1;
-        if (off > 0) out[1] = n - 1 - (off - 1);
-    }
-    if (il) {
-        int q1 = 0; while (ambi_il_code(q1 + 1, -1) <= il) ++q1;
-        int off = il - ambi_il_code(q1, -1);
-        out[2] = n - 1 - q1;
-        if (off > 0) out[3] = (off - 1 == q1) ? out[2] : n - 1 - (off - 1);
-    }
-}
-
-static inline int pair_index(int n, int a, int b) { return a * n - a * (a - 1) / 2 + (b - a); }
-
-static void rows_to_element_cn(int n, const uint32_t *rows, int32_t *x)
-{
-    const int H = n * (n + 1) / 2;
-    memset(x, 0, sizeof(int32_t) * 2 * H);
-    if (n == 1) { x[0] = (rows[0] >> 20) & 1; x[1] = rows[0] & 0xfffff; return; }
-    for (int a = 0; a < n; ++a) {
-        int c[4]; decode_codes(rows[a], n, c);
-        if (c[0] >= 0) x[pair_index(n, a, c[0])] += 1;
-        if (c[1] >= 0) x[pair_index(n, a, c[1])] += 1;
-        if (c[2] >= 0) x[H + pair_index(n, a, c[2])] += 1;
-        if (c[3] >= 0) x[H + pair_index(n, a, c[3])] += 1;
-    }
 }
 
 extern "C" int ambi_bfb_better(int32_t n, int64_t sa, const int32_t *xa, int64_t sb, const int32_t *xb)
@@ -363,7 +285,7 @@ static int fetch_into(ambi_ctx *ctx, ambi_batch *b, ambi_bfb_solution *sol, bool
             s.objective2 = sc - 2ll * b->bias[i];
             s.candidates_scored = F.cand[i]; s.nodes_expanded = F.node[i];
             s.incumbent_score2 = F.incumbent[i];
-            s.seconds = F.seconds; s.seconds_to_best = (F.incumbent[i] == sc && !F.used_graph) ? F.seconds_beam : F.seconds;
+            s.seconds = F.t_proof[i]; s.seconds_to_best = F.t_best[i];
             if (s.element_cn) {
                 if (sc != 0x7fffffff) rows_to_element_cn(n, F.rows + (size_t)i * F.rows_stride, s.element_cn);
                 else memset(s.element_cn, 0, sizeof(int32_t) * n * (n + 1));
@@ -449,7 +371,7 @@ extern "C" int ambi_bfb_solve(ambi_ctx *ctx, const ambi_bfb_problem *problem, am
     if (ctx->cfg.world <= 1 || !ctx->comm) return ambi_bfb_solve_batch(ctx, 1, problem, solution);
     // prefix-sharded: every rank explores the subtrees hashed to it, then one all-gather of the
     // (score, row codes) records over NVLink picks the global arg-min in (score, search order)
-    const int n = problem->n;
+    const int n = std::max(1, std::min((int)problem->n, (int)AMBI_MAX_SEGMENTS));   // an out-of-range n fails in the shard call below
     std::vector<int32_t> x((size_t)n * (n + 1));
     ambi_bfb_solution local = *solution;
     local.element_cn = x.data();

@@ -679,6 +679,8 @@ struct FinalizeArgs {
     int merge_best;             // chunked mode: keep the better of (stored best, this chunk's best)
     int build_list;             // append the surviving open records to next_list (else expand reads the buffer itself)
     const uint32_t *overflow;
+    int32_t *seen;              // [prob] best completed score seen so far in any pass ...
+    unsigned long long *stamps; // ... and when (%globaltimer) it was first seen: [prob][4], word 1
 };
 
 __global__ void k_finalize(FinalizeArgs A)
@@ -705,6 +707,7 @@ __global__ void k_finalize(FinalizeArgs A)
                 }
             }
             if (take) {
+                if (A.stamps && h->score < A.seen[h->prob]) { A.seen[h->prob] = h->score; A.stamps[(size_t)h->prob * 4 + 1] = globaltimer_ns(); }
                 A.best_score[h->prob] = h->score;
                 for (int k = 0; k < n; ++k) o[k] = r[k];
                 if (A.limit && h->score < A.limit[h->prob]) A.limit[h->prob] = h->score;
@@ -789,11 +792,14 @@ __global__ void k_beam_select(BeamArgs A)
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
+// `active`: partitions this (global-memory) path still has to solve; the others were solved by the
+// warp-per-partition kernel (stage_small.cu) and keep their results
 __global__ void k_init_roots(const DevProblem *probs, int count, uint8_t *recs, int stride, int nmax,
-                             uint32_t *list, uint32_t *lcount, int32_t *limit, int32_t *best_score, int first)
+                             uint32_t *list, uint32_t *lcount, int32_t *limit, int32_t *best_score, int first,
+                             const uint8_t *active)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= count) return;
+    if (p >= count || !active[p]) return;
     const DevProblem &P = probs[p];
     if (first) { limit[p] = P.zero_score; best_score[p] = 0x7fffffff; }
     if (P.n < 2) return;                  // n == 1 handled by k_solve_n1
@@ -828,11 +834,22 @@ __global__ void k_solve_n1(const DevProblem *probs, int count, int32_t *best_sco
 
 __global__ void k_bump_gen(uint32_t *gen) { *gen += 128u; }
 
-__global__ void k_set_limit(const DevProblem *probs, int count, int32_t *limit, const int32_t *best_score,
-                            int32_t *incumbent)
+// start of a search: nothing solved yet, statistics cleared, the partitions that take the global-memory path flagged
+__global__ void k_prepare(const DevProblem *probs, int count, int32_t *best_score, int32_t *seen, int32_t *incumbent, unsigned long long *stamps, unsigned long long *cand,
+                          unsigned long long *node, uint8_t *active, const uint8_t *active_base)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= count) return;
+    best_score[p] = 0x7fffffff; seen[p] = 0x7fffffff; incumbent[p] = probs[p].zero_score; cand[p] = 0; node[p] = 0; active[p] = active_base[p];
+    stamps[(size_t)p * 4] = 0; stamps[(size_t)p * 4 + 1] = 0; stamps[(size_t)p * 4 + 2] = 0; stamps[(size_t)p * 4 + 3] = 0;
+}
+
+__global__ void k_set_limit(const DevProblem *probs, int count, int32_t *limit, const int32_t *best_score,
+                            int32_t *incumbent, const uint8_t *active, int32_t *seen, unsigned long long *stamps)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= count || !active[p]) return;
+    if (best_score[p] < seen[p]) { seen[p] = best_score[p]; stamps[(size_t)p * 4 + 1] = globaltimer_ns(); }   // incumbent of the pass that just ended
     int z = limit[p], b = best_score[p];       // limit starts at the all-zero score (k_init_roots)
     int l = b < z ? b : z;
     limit[p] = l; incumbent[p] = l;
@@ -847,7 +864,7 @@ __global__ void k_set_limit(const DevProblem *probs, int count, int32_t *limit, 
 static uint32_t next_pow2(uint64_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
 // device counters: one set per level so that a whole pass needs a single clear
-enum { CTR_OVERFLOW = 0, CTR_GEN = 1, CTR_WORK = 8, CTR_CHILD = 8 + 40, CTR_FRONT = 8 + 80, CTR_TOTAL = 8 + 128 };
+enum { CTR_OVERFLOW = 0, CTR_GEN = 1, CTR_SMALL_WORK = 2, CTR_SMALL_FB = 3, CTR_WORK = 8, CTR_CHILD = 8 + 40, CTR_FRONT = 8 + 80, CTR_TOTAL = 8 + 128 };
 
 StageA::StageA() { err_[0] = 0; }
 StageA::~StageA() { release(); }
@@ -856,6 +873,8 @@ void StageA::release()
 {
     cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]);
     cudaFree(table_); cudaFree(counters_); cudaFree(d_funnel_); cudaFree(d_flag_); cudaFree(pool_); pool_ = nullptr; d_funnel_ = nullptr; d_flag_ = nullptr;
+    cudaFree(d_arena_); d_arena_ = nullptr; cudaFree(d_stamp0_); d_stamp0_ = nullptr; cudaFreeHost(h_flag_); h_flag_ = nullptr;
+    for (int i = 0; i < 2; ++i) if (ev_small_[i]) { cudaEventDestroy(ev_small_[i]); ev_small_[i] = nullptr; }
     buf_[0] = buf_[1] = nullptr; list_[0] = list_[1] = nullptr; table_ = nullptr;
     counters_ = nullptr;
     free_problem_arrays();
@@ -872,12 +891,14 @@ void StageA::free_problem_arrays()
     cudaFree(d_beam_score_); cudaFree(d_beam_rows_); cudaFree(d_cand_); cudaFree(d_node_);
     cudaFree(d_fmin_); cudaFree(d_hist_); cudaFree(d_ticket_); cudaFree(d_cutq_); cudaFree(d_incumbent_); d_cutq_ = nullptr;
     cudaFreeHost(h_probs_); cudaFreeHost(h_res_); h_probs_ = nullptr; h_res_ = nullptr; h_cap_ = 0;
+    cudaFree(d_small_list_); cudaFree(d_active_); cudaFree(d_active_base_); cudaFree(d_seen_); cudaFree(d_stamps_);
+    d_small_list_ = nullptr; d_active_ = d_active_base_ = nullptr; d_seen_ = nullptr; d_stamps_ = nullptr;
     d_probs_ = nullptr; d_limit_ = d_best_score_ = d_beam_score_ = d_fmin_ = d_incumbent_ = nullptr;
     d_best_rows_ = d_beam_rows_ = d_hist_ = d_ticket_ = nullptr; d_cand_ = d_node_ = nullptr;
     prob_cap_ = 0;
 }
 
-int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int rank, int world, int shard_level)
+int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int rank, int world, int shard_level, bool use_small)
 {
     stream_ = stream;
     stride_ = (int)ambi_node_stride(AMBI_MAXN);
@@ -922,6 +943,18 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     int per_sm = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand, WPB * 32, expand_smem_));
     expand_blocks_ = sms_ * (per_sm > 0 ? per_sm : 1);
+    // warp-per-partition kernel for partitions of up to 16 segments (AMBI_NO_SMALL=1: everything takes the
+    // global-memory path; AMBI_SMALL_C: records per level and warp)
+    small_on_ = use_small && getenv("AMBI_NO_SMALL") == nullptr;
+    int C = 256;
+    if (const char *e = getenv("AMBI_SMALL_C")) C = std::max(32, atoi(e));
+    if (small_on_) {
+        if (small_configure(&small_cfg_, C, sms_)) { snprintf(err_, sizeof err_, "small_configure(%d) failed: %s", C, cudaGetErrorString(cudaGetLastError())); return -4; }
+        CK(cudaMalloc(&d_arena_, small_cfg_.arena_words * 4));
+    }
+    CK(cudaMalloc(&d_stamp0_, 8));
+    CK(cudaMallocHost(&h_flag_, 16));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&ev_small_[i]));
     return 0;
 }
 
@@ -939,8 +972,10 @@ int StageA::ensure_problem_arrays(int count)
     CK(cudaMalloc(&d_fmin_, (size_t)c * 4 * AMBI_MAXN)); CK(cudaMalloc(&d_hist_, (size_t)c * BEAM_BINS * 4));       // one level's histograms, cleared per beam level
     CK(cudaMalloc(&d_ticket_, (size_t)c * 4 * AMBI_MAXN));
     CK(cudaMalloc(&d_cutq_, (size_t)c * 4 * AMBI_MAXN));
+    CK(cudaMalloc(&d_small_list_, (size_t)c * 4)); CK(cudaMalloc(&d_active_, (size_t)c)); CK(cudaMalloc(&d_active_base_, (size_t)c));
+    CK(cudaMalloc(&d_seen_, (size_t)c * 4)); CK(cudaMalloc(&d_stamps_, (size_t)c * 32));
     CK(cudaMallocHost(&h_probs_, (size_t)c * sizeof(DevProblem)));
-    CK(cudaMallocHost(&h_res_, (size_t)c * (4 + 4 + 8 + 8 + 4 * AMBI_MAXN)));
+    CK(cudaMallocHost(&h_res_, (size_t)c * (4 + 4 + 8 + 8 + 4 * AMBI_MAXN + 32 + 1) + 64));
     h_cap_ = c;
     prob_cap_ = c;
     return 0;
@@ -975,6 +1010,22 @@ int StageA::upload(const DevProblem *host_probs, int count)
     cap_ = (uint32_t)std::min<uint64_t>(cap_max_, buf_bytes_ / stride_);
     if ((uint64_t)count > cap_) { snprintf(err_, sizeof err_, "batch of %d partitions exceeds node capacity %u", count, cap_); return -5; }
     CK(cudaMemcpyAsync(d_probs_, host_probs, (size_t)count * sizeof(DevProblem), cudaMemcpyHostToDevice, stream_));
+    {   // partitions of 2..16 segments go to the warp-per-partition kernel first; the others are active for the
+        // global-memory path from the start (single-segment partitions are solved in closed form)
+        std::vector<uint32_t> lst; std::vector<uint8_t> act((size_t)count, 0);
+        n_large_ = 0;
+        for (int i = 0; i < count; ++i) {
+            const int n = host_probs[i].n;
+            if (small_on_ && n >= 2 && n <= 16) lst.push_back((uint32_t)i);
+            else if (n >= 2) { act[i] = 1; ++n_large_; }
+        }
+        n_small_ = (int)lst.size();
+        // heaviest first would be better still; longest partitions first keeps the tail of the launch short
+        std::stable_sort(lst.begin(), lst.end(), [&](uint32_t x, uint32_t y) { return host_probs[x].n > host_probs[y].n; });
+        if (n_small_) CK(cudaMemcpyAsync(d_small_list_, lst.data(), (size_t)n_small_ * 4, cudaMemcpyHostToDevice, stream_));
+        CK(cudaMemcpyAsync(d_active_base_, act.data(), (size_t)count, cudaMemcpyHostToDevice, stream_));
+        CK(cudaStreamSynchronize(stream_));      // the host vectors go out of scope
+    }
     return 0;
 }
 
@@ -1021,7 +1072,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     F.next_list = list_[cur ^ 1]; F.next_count = c_nxt;
     F.best_score = mode == 2 ? d_best_score_ : d_beam_score_; F.best_rows = mode == 2 ? d_best_rows_ : d_beam_rows_;
     F.fmin = nullptr; F.stride = stride_; F.level = level;
-    F.limit = nullptr; F.merge_best = 0; F.build_list = 0; F.overflow = c_over;
+    F.limit = nullptr; F.merge_best = 0; F.build_list = 0; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
     // this kernel only collects completed assignments: skip the levels where no problem ends
     if ((leaf_levels_ >> level) & 1u) { k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_; }
     if (beam) {
@@ -1048,7 +1099,7 @@ int StageA::run_pass(int mode, int shard_world, bool first)
         CK(cudaMemsetAsync(d_ticket_, 0, (size_t)count_ * 4 * nmax_, stream_));
     }
     k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, buf_[0], stride_, nmax_, list_[0],
-                                              counters_ + CTR_FRONT, d_limit_, d_best_score_, first ? 1 : 0); ++launches_;
+                                              counters_ + CTR_FRONT, d_limit_, d_best_score_, first ? 1 : 0, d_active_); ++launches_;
     int cur = 0;
     for (int a = 0; a < nmax_; ++a) { if (int rc = run_level(a, cur, mode, shard_world)) return rc; cur ^= 1; }
     return 0;
@@ -1063,15 +1114,11 @@ int StageA::enqueue_incumbent(bool coop)
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
     CK(cudaMemsetAsync(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t), stream_));
     k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
-    CK(cudaMemsetAsync(d_cand_, 0, (size_t)count_ * 8, stream_));
-    CK(cudaMemsetAsync(d_node_, 0, (size_t)count_ * 8, stream_));
-    CK(cudaMemsetAsync(d_funnel_, 0, 4 * sizeof(unsigned long long), stream_));
     CK(cudaMemsetAsync(d_beam_score_, 0x7f, (size_t)count_ * 4, stream_));
     shard_level_eff_ = -1;
     // ---- pass 0: greedy dive -> first incumbent (limit starts at the all-zero score)
     if (int rc = run_pass(0, 1, true)) return rc;
-    k_solve_n1<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_best_score_, d_best_rows_, d_cand_); ++launches_;
-    k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_); ++launches_;
+    k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_, d_active_, d_seen_, d_stamps_); ++launches_;
     // ---- pass 1: beam of width W inside that limit -> tighter incumbent
     if (beam_ > 1) {
         CK(cudaMemsetAsync(d_beam_score_, 0x7f, (size_t)count_ * 4, stream_));
@@ -1091,7 +1138,7 @@ int StageA::enqueue_incumbent(bool coop)
 int StageA::enqueue_exact(bool sharded)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
-    if (beam_ > 1) { k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_); ++launches_; }
+    if (beam_ > 1) { k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_, d_active_, d_seen_, d_stamps_); ++launches_; }
     if (!capturing_) CK(cudaEventRecord(ev_[1], stream_));
     int sw = sharded ? world_ : 1;
     shard_level_eff_ = -1;
@@ -1128,11 +1175,48 @@ int StageA::capture(cudaGraphExec_t *exec, unsigned long long *nlaunch, int part
     return 0;
 }
 
+// Start of every search (plain launches, not part of the replayed graph): results and statistics cleared,
+// single-segment partitions solved in closed form, the reference time stamp taken.
+int StageA::prepare()
+{
+    const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
+    k_prepare<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_best_score_, d_seen_, d_incumbent_, d_stamps_, d_cand_, d_node_, d_active_, d_active_base_); ++launches_;
+    CK(cudaMemsetAsync(d_funnel_, 0, 4 * sizeof(unsigned long long), stream_));
+    CK(cudaMemsetAsync(counters_ + CTR_SMALL_WORK, 0, 2 * sizeof(uint32_t), stream_));
+    CK(cudaMemsetAsync(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t), stream_));
+    k_solve_n1<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_best_score_, d_best_rows_, d_cand_); ++launches_;
+    stamp_launch(d_stamp0_, stream_); ++launches_;
+    return 0;
+}
+
 int StageA::run(bool sharded)
 {
     prof_used_ = 0;
     last_sharded_ = sharded;
     CK(cudaEventRecord(ev_[0], stream_));
+    if (int rc = prepare()) return rc;
+    // ---- partitions of up to 16 segments: one warp each, the whole search in shared memory (stage_small.cu).
+    // Whatever does not fit there is flagged active and joins the longer partitions on the global-memory path.
+    global_count_ = n_large_; small_solved_ = 0; ran_global_ = false;
+    h_flag_[0] = 0;
+    if (small_on_ && n_small_ > 0) {
+        SmallLaunch L;
+        L.probs = d_probs_; L.plist = d_small_list_; L.count = (uint32_t)n_small_; L.work = counters_ + CTR_SMALL_WORK;
+        L.best_score = d_best_score_; L.best_rows = d_best_rows_; L.incumbent = d_incumbent_;
+        L.cand = d_cand_; L.node = d_node_; L.funnel = d_funnel_; L.fb_count = counters_ + CTR_SMALL_FB; L.active = d_active_;
+        L.arena = d_arena_; L.stamps = d_stamps_; L.beam_width = beam_; L.beam_growth = beam_growth_; L.beam_delta = beam_delta_; L.beam_shift = beam_shift_;
+        CK(cudaEventRecord(ev_small_[0], stream_));
+        small_launch(small_cfg_, L, stream_); ++launches_;
+        CK(cudaEventRecord(ev_small_[1], stream_));
+        CK(cudaGetLastError());
+        // how many partitions were handed on decides whether the global-memory path runs at all (one host round trip)
+        CK(cudaMemcpyAsync(h_flag_, counters_ + CTR_SMALL_FB, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        global_count_ += (int)h_flag_[0];
+        small_solved_ = n_small_ - (int)h_flag_[0];
+    }
+    if (global_count_ == 0) { used_graph_ = false; CK(cudaEventRecord(ev_[1], stream_)); CK(cudaEventRecord(ev_[2], stream_)); return 0; }
+    ran_global_ = true;
     const bool coop = sharded && world_ > 1 && allreduce_ != nullptr && beam_ > 1 && getenv("AMBI_REPLICATED_BEAM") == nullptr;
     const bool use_graph = !profile_ && getenv("AMBI_NO_GRAPH") == nullptr;
     const int mode = coop ? 2 : (sharded ? 1 : 0);
@@ -1261,7 +1345,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         // roots -> pool
         CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
         k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, pool_, stride_, nmax_, list_[0],
-                                                  counters_ + CTR_FRONT, d_limit_, d_best_score_, 0); ++launches_;
+                                                  counters_ + CTR_FRONT, d_limit_, d_best_score_, 0, d_active_); ++launches_;
         CK(cudaMemcpyAsync(&nroots, counters_ + CTR_FRONT, 4, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
         if (nroots > 0) stack.push_back({0, 0, nroots, 0});
@@ -1315,7 +1399,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         FinalizeArgs F;
         F.probs = d_probs_; F.recs = buf_[0]; F.count = c_child; F.cap = cap_;
         F.next_list = list_[1]; F.next_count = c_next; F.best_score = d_best_score_; F.best_rows = d_best_rows_;
-        F.fmin = nullptr; F.limit = d_limit_; F.stride = stride_; F.level = level; F.merge_best = 1; F.build_list = 1; F.overflow = c_over;
+        F.fmin = nullptr; F.limit = d_limit_; F.stride = stride_; F.level = level; F.merge_best = 1; F.build_list = 1; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
         k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_;
         uint32_t nnext = 0;
         CK(cudaMemcpyAsync(&nnext, c_next, 4, cudaMemcpyDeviceToHost, stream_));
@@ -1334,16 +1418,16 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
     return 0;
 }
 
-__global__ void k_reset_best(const DevProblem *probs, int count, int32_t *best_score)
+__global__ void k_reset_best(const DevProblem *probs, int count, int32_t *best_score, const uint8_t *active)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < count && probs[p].n >= 2) best_score[p] = 0x7fffffff;
+    if (p < count && probs[p].n >= 2 && active[p]) best_score[p] = 0x7fffffff;
 }
 
 int StageA::fetch_raw(Fetched *F)
 {
     chunked_failed_ = false;
-    {   // a level of the breadth-first exact pass did not fit: continue depth-first in chunks
+    if (ran_global_) {   // a level of the breadth-first exact pass did not fit: continue depth-first in chunks
         uint32_t over = 0;
         CK(cudaMemcpyAsync(&over, counters_ + CTR_OVERFLOW, 4, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
@@ -1363,7 +1447,7 @@ int StageA::fetch_raw(Fetched *F)
             // `over` = 1 + the level of the exact pass that did not fit
             const int lvl = (int)over - 1;
             const bool resume = lvl >= 1 && getenv("AMBI_CHUNKED_FROM_ROOT") == nullptr;
-            if (!resume) { k_reset_best<<<(count_ + 127) / 128, 128, 0, stream_>>>(d_probs_, count_, d_best_score_); ++launches_; }
+            if (!resume) { k_reset_best<<<(count_ + 127) / 128, 128, 0, stream_>>>(d_probs_, count_, d_best_score_, d_active_); ++launches_; }
             // -5 = the depth-first pass itself ran out of room (frontier pool exhausted / too small, or one record's
             // children exceed a buffer): whatever partial best exists is NOT proven optimal, so the failure is
             // reported as a frontier overflow (run_chunked_core clears the device flag per chunk; this host flag
@@ -1391,16 +1475,35 @@ int StageA::fetch_raw(Fetched *F)
     CK(cudaMemcpyAsync(h_node, d_node_, c * 8, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(ctr, counters_, sizeof ctr, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(funnel_, d_funnel_, sizeof funnel_, cudaMemcpyDeviceToHost, stream_));
+    unsigned long long *h_stamps = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(h_rows) + (((size_t)h_cap_ * AMBI_MAXN * 4 + 15) & ~(size_t)15));
+    uint8_t *h_act = reinterpret_cast<uint8_t *>(h_stamps + (size_t)h_cap_ * 4);
+    unsigned long long stamp0 = 0;
+    CK(cudaMemcpyAsync(h_stamps, d_stamps_, c * 32, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(h_act, d_active_, c, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(&stamp0, d_stamp0_, 8, cudaMemcpyDeviceToHost, stream_));
     CK(cudaStreamSynchronize(stream_));
-    float ms_beam = 0, ms_all = 0;
+    float ms_beam = 0, ms_all = 0, ms_small = 0;
     if (!used_graph_) cudaEventElapsedTime(&ms_beam, ev_[0], ev_[1]);
     cudaEventElapsedTime(&ms_all, ev_[0], ev_[2]);
+    if (small_on_ && n_small_ > 0) cudaEventElapsedTime(&ms_small, ev_small_[0], ev_small_[1]);
+    prof_small_ms_ = ms_small;
+    // per-partition times from the device clock: word 1 = when the returned optimum was first seen as a completed
+    // assignment (any pass), word 2 = when the warp-per-partition kernel finished the partition; partitions of the
+    // global-memory path are proven when the whole pass ends
+    h_tbest_.resize(c); h_tproof_.resize(c);
+    for (size_t p = 0; p < c; ++p) {
+        const unsigned long long *st = h_stamps + p * 4;
+        h_tbest_[p] = st[1] > stamp0 ? (double)(st[1] - stamp0) * 1e-9 : 0.0;
+        h_tproof_[p] = (!h_act[p] && st[2] > stamp0) ? (double)(st[2] - stamp0) * 1e-9 : (double)ms_all * 1e-3;
+        if (h_tbest_[p] > h_tproof_[p]) h_tbest_[p] = h_tproof_[p];
+    }
     prof_total_ms_ = ms_all; prof_beam_ms_ = ms_beam;
     if (profile_) {
         prof_expand_ms_ = 0; prof_expand_launches_ = prof_used_ / 2;
         for (size_t i = 0; i + 1 < prof_used_; i += 2) { float m = 0; cudaEventElapsedTime(&m, prof_ev_[i], prof_ev_[i + 1]); prof_expand_ms_ += m; }
     }
     F->score = h_score; F->incumbent = h_inc; F->rows = h_rows; F->rows_stride = rs; F->cand = h_cand; F->node = h_node;
+    F->t_best = h_tbest_.data(); F->t_proof = h_tproof_.data();
     F->overflow = ctr[CTR_OVERFLOW] != 0 || chunked_failed_; F->seconds = ms_all * 1e-3; F->seconds_beam = ms_beam * 1e-3; F->used_graph = used_graph_;
     if (F->overflow && !chunked_failed_) snprintf(err_, sizeof err_, "frontier overflow: more than %u candidate records in one level", cap_);
     return 0;
@@ -1415,7 +1518,7 @@ int StageA::fetch(HostResult *out)
         out[p].candidates = F.cand[p]; out[p].nodes = F.node[p];
         memset(out[p].rows, 0, sizeof out[p].rows);
         memcpy(out[p].rows, F.rows + (size_t)p * F.rows_stride, (size_t)F.rows_stride * 4);
-        out[p].seconds = F.seconds; out[p].seconds_to_best = (F.incumbent[p] == F.score[p] && !F.used_graph) ? F.seconds_beam : F.seconds;
+        out[p].seconds = F.t_proof[p]; out[p].seconds_to_best = F.t_best[p];
         out[p].status = F.overflow ? -5 : (F.score[p] == 0x7fffffff ? -4 : 0);
     }
     return F.overflow ? -5 : 0;

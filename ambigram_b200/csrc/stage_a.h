@@ -1,6 +1,7 @@
 // stage_a.h -- host driver of the Stage-A device search (see stage_a.cu).
 #pragma once
 #include "ambi_common.cuh"
+#include "stage_small.h"
 #include <vector>
 
 namespace ambi {
@@ -18,7 +19,7 @@ class StageA {
 public:
     StageA();
     ~StageA();
-    int init(cudaStream_t stream, int64_t node_capacity, int beam_width, int rank, int world, int shard_level);
+    int init(cudaStream_t stream, int64_t node_capacity, int beam_width, int rank, int world, int shard_level, bool use_small = true);
     void release();
     // pinned staging for `count` problem descriptors; the caller fills it and then calls upload(ptr, count)
     DevProblem *staging(int count);
@@ -30,6 +31,9 @@ public:
     struct Fetched {
         const int32_t *score, *incumbent; const uint32_t *rows; int rows_stride;   // rows_stride words per problem
         const unsigned long long *cand, *node; bool overflow; double seconds, seconds_beam; bool used_graph;
+        // per partition, seconds since the search was enqueued (device %globaltimer): when the returned optimum was first
+        // seen as a completed assignment (time to best) and when it was proven (time to proof)
+        const double *t_best, *t_proof;
     };
     int fetch_raw(Fetched *out);
     int fetch(HostResult *out);
@@ -38,6 +42,11 @@ public:
     int count() const { return count_; }
     uint32_t capacity_base() const { return cap_base_; }
     unsigned long long chunked_runs() const { return chunked_runs_; }
+    // partitions of the last run solved by the warp-per-partition kernel / handed on to the global-memory path
+    int small_solved() const { return small_solved_; }
+    int global_solved() const { return global_count_; }
+    double small_ms() const { return prof_small_ms_; }
+    int small_capacity() const { return small_cfg_.C; }
     // per-kernel timing (CUDA events around every k_expand launch; adds launch gaps, so only
     // enabled for the bench's roofline pass)
     void set_profile(bool on) { profile_ = on; }
@@ -111,6 +120,20 @@ private:
     AllReduceFn allreduce_ = nullptr;
     void *allreduce_user_ = nullptr;
     int32_t *d_flag_ = nullptr;
+    // warp-per-partition kernel (stage_small.cu): partitions of 2..16 segments
+    bool small_on_ = true;
+    SmallConfig small_cfg_;
+    uint32_t *d_small_list_ = nullptr, *d_arena_ = nullptr;
+    uint8_t *d_active_ = nullptr, *d_active_base_ = nullptr;     // active: still to be solved by the global-memory path
+    int32_t *d_seen_ = nullptr;
+    unsigned long long *d_stamps_ = nullptr, *d_stamp0_ = nullptr;
+    uint32_t *h_flag_ = nullptr;                                 // pinned: partitions the small kernel handed on
+    std::vector<double> h_tbest_, h_tproof_;
+    int n_small_ = 0, n_large_ = 0, small_solved_ = 0, global_count_ = 0;
+    bool ran_global_ = false;
+    double prof_small_ms_ = 0;
+    cudaEvent_t ev_small_[2] = {nullptr, nullptr};
+    int prepare();
     unsigned long long exchange_rounds_ = 0;
     char err_[256];
 };

@@ -64,8 +64,12 @@ typedef struct {
     int64_t node_capacity;     /* candidate records per frontier buffer (0 = auto) */
     int32_t shard_level;       /* rows expanded redundantly before the frontier
                                   is split by prefix across shards (0 = auto)  */
-    int32_t reserved;
+    uint32_t flags;            /* AMBI_CFG_*                                    */
 } ambi_config;
+
+/* ambi_config.flags */
+#define AMBI_CFG_NO_SMALL 1u   /* do not use the warp-per-partition kernel for partitions of <= 16 segments:
+                                  every partition takes the level-synchronous global-memory path (tests, profiling) */
 
 /* One partition's Stage-A problem: what BFB_ILP reads from the graph.
  *   seg_cn2[i] = 2*c_i  (segment copy number after getIndelBias,
@@ -105,8 +109,9 @@ typedef struct {
     uint64_t nodes_expanded;   /* partial assignments expanded                  */
     int32_t status;
     int32_t incumbent_score2;  /* score2 found by the beam (incumbent) pass     */
-    double seconds;            /* device time of the whole batch this problem was in */
-    double seconds_to_best;    /* device time until the returned optimum was first seen */
+    double seconds;            /* time to proof: device time (%globaltimer) from the start of the search of the batch until
+                                  this partition's optimum was proven                                          */
+    double seconds_to_best;    /* time to best: ... until the returned optimum was first seen as a completed assignment */
 } ambi_bfb_solution;
 
 /* Stage-B inputs: the DAG of active components (constructDAG, LGM:3276-3378). */
@@ -228,6 +233,10 @@ typedef struct {
     uint64_t bound_batches;      /* 32-lane batches the bound ran in (lane use = bounds_evaluated / (32*bound_batches)) */
     uint64_t exchange_rounds;    /* bound-exchange rounds (NCCL all-reduce of the pruning limits) since ambi_init */
     uint64_t chunked_runs;       /* searches that continued depth-first because a level did not fit, since ambi_init */
+    double small_ms;             /* duration of the warp-per-partition kernel (partitions of <= 16 segments) of the last run */
+    uint64_t small_solved;       /* partitions it solved in the last run ...                                   */
+    uint64_t global_solved;      /* ... and partitions that took the global-memory path (longer, or frontier too wide) */
+    uint64_t small_capacity;     /* records per level and warp of the warp-per-partition kernel               */
 } ambi_profile;
 int  ambi_ctx_set_profile(ambi_ctx *ctx, int enable);
 int  ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out);

@@ -41,3 +41,18 @@ def ctx():
     c = capi.Context(device=0)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session")
+def ctx_global():
+    """every partition on the level-synchronous global-memory path (AMBI_CFG_NO_SMALL): the path of partitions with
+    more than 16 segments, exercised here on small ones as well"""
+    from ambigram_b200 import capi
+    c = capi.Context(device=0, small_kernel=False)
+    yield c
+    c.close()
+
+
+@pytest.fixture(params=["small", "global"])
+def any_ctx(request, ctx, ctx_global):
+    return ctx if request.param == "small" else ctx_global

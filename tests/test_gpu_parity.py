@@ -51,7 +51,8 @@ def test_readme_known_answer(ctx):
         "6-5-4-3-2-1-|1+2+3+4+5+6+|6-5-4-3-2-|2+3+4+|4-3-|3+4+|4-3-2-|2+3+4+5+6+"
 
 
-def test_golden_cases_batch(ctx):
+def test_golden_cases_batch(any_ctx):
+    ctx = any_ctx
     """every committed fixture (reference-generated) in one device batch"""
     probs = [problem_of(c) for c in CASES]
     sols = ctx.solve_batch(probs)
@@ -74,7 +75,8 @@ def test_golden_cases_batch(ctx):
 
 @pytest.mark.parametrize("n,folds,noise,count", [(2, 2, 0.5, 12), (3, 2, 0.5, 16), (5, 3, 0.5, 24), (8, 3, 0.5, 24),
                                                  (12, 4, 0.0, 32), (12, 4, 0.5, 32), (16, 5, 0.5, 8), (20, 6, 0.5, 4)])
-def test_seeded_synthetic_vs_oracle(ctx, n, folds, noise, count):
+def test_seeded_synthetic_vs_oracle(any_ctx, n, folds, noise, count):
+    ctx = any_ctx
     probs = [lh.problem_from_lh(synth.generate(n, folds, 100 + s, noise).lh_text()) for s in range(count)]
     sols = ctx.solve_batch(probs)
     for p, s in zip(probs, sols):
@@ -84,7 +86,8 @@ def test_seeded_synthetic_vs_oracle(ctx, n, folds, noise, count):
     assert one.score2 == sols[0].score2 and np.array_equal(one.element_cn, sols[0].element_cn)
 
 
-def test_random_profiles_ragged_batch(ctx):
+def test_random_profiles_ragged_batch(any_ctx):
+    ctx = any_ctx
     """ragged batch: n from 1 to 10, arbitrary (non-BFB) profiles, zeros, third-generation rows"""
     rng = random.Random(5)
     probs = []
@@ -102,7 +105,8 @@ def test_random_profiles_ragged_batch(ctx):
         check_against_oracle(p, s)
 
 
-def test_small_n_vs_bruteforce(ctx):
+def test_small_n_vs_bruteforce(any_ctx):
+    ctx = any_ctx
     rng = random.Random(9)
     probs = [Problem(n=n, seg_cn2=[rng.randint(0, 12) for _ in range(n)], fbi_cn2=[rng.randint(0, 6) for _ in range(n)],
                      loop_ub=rng.choice([1, 2, 3])) for n in [1, 2, 3] * 20]
@@ -162,7 +166,7 @@ def test_prefix_sharded_solve_combines_to_the_same_optimum():
     for world in (2, 4):
         shard_sols = []
         for rank in range(world):
-            with capi.Context(device=0, rank=rank, world=world) as c:
+            with capi.Context(device=0, rank=rank, world=world, small_kernel=False) as c:   # sharding is a property of the global-memory path
                 shard_sols.append([c.solve_shard(p) for p in probs])
         for i, p in enumerate(probs):
             best = None
@@ -178,17 +182,18 @@ def test_small_buffers_fall_back_to_chunked_depth_first_pass():
     same answer, bit for bit"""
     probs = [lh.problem_from_lh(synth.generate(n, f, s, 0.5).lh_text()) for (n, f, s) in
              [(12, 4, 1), (16, 5, 0), (16, 5, 3), (20, 6, 1)]]
-    with capi.Context(device=0, node_capacity=4096) as c:
-        for p in probs:
-            check_against_oracle(p, c.solve(p))
-        for p, s in zip(probs, c.solve_batch(probs)):
-            check_against_oracle(p, s)
+    for small in (False, True):
+        with capi.Context(device=0, node_capacity=4096, small_kernel=small) as c:
+            for p in probs:
+                check_against_oracle(p, c.solve(p))
+            for p, s in zip(probs, c.solve_batch(probs)):
+                check_against_oracle(p, s)
 
 
 def test_overflow_is_reported_loudly(monkeypatch):
     monkeypatch.setenv("AMBI_NO_CHUNKED", "1")
     p = lh.problem_from_lh(synth.generate(16, 5, 0, 0.5).lh_text())
-    with capi.Context(device=0, node_capacity=64) as c:
+    with capi.Context(device=0, node_capacity=64, small_kernel=False) as c:
         with pytest.raises(capi.AmbiError) as e:
             c.solve(p)
         assert e.value.status == -5
@@ -209,6 +214,32 @@ def test_exhausted_frontier_pool_is_an_error_never_a_silent_answer(monkeypatch):
     monkeypatch.delenv("AMBI_POOL_BYTES")
     with capi.Context(device=0, node_capacity=4096) as c:        # same buffers, default pool: exact answer
         check_against_oracle(p, c.solve(p))
+
+
+def test_small_kernel_hands_wide_frontiers_to_the_global_path(monkeypatch):
+    """a tiny per-warp record capacity: most partitions do not fit the warp-per-partition kernel and are handed on
+    to the global-memory path inside the same call; answers are the oracle's either way"""
+    monkeypatch.setenv("AMBI_SMALL_C", "32")
+    probs = [lh.problem_from_lh(synth.generate(n, f, 60 + s, 0.5).lh_text()) for (n, f) in [(8, 3), (12, 4), (14, 4), (16, 5)] for s in range(6)]
+    with capi.Context(device=0) as c:
+        b = c.upload(probs)
+        b.run(); c.sync()
+        sols = b.fetch()
+        pr = c.profile()
+        b.free()
+        assert pr["small_capacity"] == 32 and pr["small_solved"] + pr["global_solved"] == len(probs)
+        assert pr["global_solved"] > 0 and pr["small_solved"] > 0
+        for p, s in zip(probs, sols):
+            check_against_oracle(p, s)
+
+
+def test_time_to_best_and_time_to_proof_per_partition(any_ctx):
+    """per-partition device-clock times (BASELINE metric, second half): 0 <= time to best <= time to proof"""
+    probs = [lh.problem_from_lh(synth.generate(12, 4, 800 + s, 0.5).lh_text()) for s in range(64)]
+    sols = any_ctx.solve_batch(probs)
+    for s in sols:
+        assert 0.0 <= s.seconds_to_best <= s.seconds and 0.0 < s.seconds < 10.0
+    assert len({round(s.seconds_to_best * 1e9) for s in sols}) > 1        # not one number for the whole batch
 
 
 def test_bad_arguments(ctx):

@@ -329,7 +329,111 @@ def extra_fractional():
     print("wrote", out, len(cases), "cases")
 
 
+REF_FIXED = os.path.join(ROOT, "oracle", "_ref", "Ambigram_ref_fixedsort")
+
+
+def run_binary(binary, lh_text, inject, reversed_=False, timeout=120):
+    """one reference binary with an injected Stage-A assignment; -> (rc or None on timeout, paths, lp text).
+    The model dump (p.lp) is written before `cbc` is called, so it exists even when Stage B hangs."""
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "in.lh"), "w").write(lh_text)
+        cmd = [binary, "--op", "bfb", "--in_lh", "in.lh", "--lp_prefix", "p"] + (["--reversed"] if reversed_ else [])
+        with open(os.path.join(d, "inject.txt"), "w") as f:
+            for i, v in enumerate(inject):
+                if v:
+                    f.write(f"{i} {int(v)}\n")
+        env = dict(os.environ, PATH=BIN + ":" + os.environ["PATH"], AMBI_CBC_MODE="inject", AMBI_CBC_SOL=os.path.join(d, "inject.txt"))
+        try:
+            r = subprocess.run(cmd, cwd=d, env=env, capture_output=True, text=True, timeout=timeout)
+            rc, out = r.returncode, r.stdout
+        except subprocess.TimeoutExpired as e:
+            rc, out = None, (e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or ""))
+        paths = [ln.strip() for ln in out.splitlines() if PATH_RE.match(ln.strip())]
+        lp = open(os.path.join(d, "p.lp")).read() if os.path.exists(os.path.join(d, "p.lp")) else ""
+        return rc, paths, lp
+
+
+def highs_on_dump(lp_text, time_limit):
+    """HiGHS (the cbc stand-in, oracle/cbc_standin.py) on a model the reference dumped -> (objective, x, proven)"""
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.lp"), "w").write(lp_text)
+        env = dict(os.environ, AMBI_CBC_MODE="highs", AMBI_CBC_TIME=str(time_limit))
+        t0 = __import__("time").time()
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cbc_standin.py"), "p.lp", "solve", "solu", "p.sol"],
+                       cwd=d, env=env, timeout=time_limit + 600)
+        dt = __import__("time").time() - t0
+        sol = open(os.path.join(d, "p.sol")).read()
+        return sol, dt
+
+
+def extra_large(which):
+    """headline sizes (BASELINE configs 3/4 and the top of config 5): n = 25 / 7 folds and n = 30 / 8 folds, clean and noisy.
+    Per case: the optimum of the reference's own dumped LP by HiGHS (value parity of Stage A at these sizes), the
+    reference's rows on probe assignments, and the path printed for our Stage-A assignment by (a) the unmodified
+    reference (only meaningful for k <= 16) and (b) the reference with compareLoops fixed
+    (oracle/_ref/Ambigram_ref_fixedsort, tools/patches/reference_fixed_sort.patch), forward and --reversed
+    -> tests/golden/cases_large.json (appended case by case, so an interrupted run keeps what it has)"""
+    out = os.path.join(ROOT, "tests", "golden", "cases_large.json")
+    doc = json.load(open(out)) if os.path.exists(out) else {"generator": "tools/make_golden.py large", "cases": []}
+    have = {c["name"] for c in doc["cases"]}
+    rng = random.Random(29)
+    spec = [(25, 7, 0.0, 0), (25, 7, 0.0, 1), (25, 7, 0.5, 2), (25, 7, 0.5, 3),
+            (30, 8, 0.0, 0), (30, 8, 0.5, 0), (30, 8, 0.5, 1), (30, 8, 0.5, 3),
+            (20, 6, 0.5, 4), (20, 6, 0.5, 5), (30, 8, 0.0, 4), (25, 7, 0.5, 6)]
+    if which:
+        spec = [sp for sp in spec if f"n{sp[0]}" in which]
+    for n, folds, noise, seed in spec:
+        name = f"large_n{n}_f{folds}_noise{noise}_s{seed}"
+        if name in have:
+            continue
+        text = synth.generate(n, folds, seed, noise).lh_text()
+        part = lh.flatten(lh.parse_lh(text), [], False)[0]
+        p = part.problem
+        nv = p.n * (p.n + 1)
+        import time
+        t0 = time.time()
+        x, st = orc.solve(p, want_unique=True)
+        t_orc = time.time() - t0
+        case = {"name": name, "inversions": {str(k): list(v) for k, v in part.inversions.items()}, "lh": text, "juncs": "", "junc_info": False,
+                "n": p.n, "seg_cn2": list(p.seg_cn2), "fbi_cn2": list(p.fbi_cn2), "loop_ub": p.effective_loop_ub(), "bias": p.bias,
+                "tgs_pairs": [], "start_id": p.start_id, "unit": 1, "oracle_score2": int(st.score2), "oracle_unique": int(st.unique),
+                "oracle_x_nz": [[int(i), int(v)] for i, v in enumerate(x) if v], "oracle_seconds": t_orc}
+        k = len(case["oracle_x_nz"])
+        lpt = ""
+        for rev in (False, True):
+            rc, paths, lp1 = run_binary(REF, text, x, rev, timeout=60)
+            lpt = lpt or lp1
+            case["ref_inject_paths_rev" if rev else "ref_inject_paths"] = paths if rc == 0 else []
+            case["ref_inject_rc_rev" if rev else "ref_inject_rc"] = rc
+            rc, paths, _ = run_binary(REF_FIXED, text, x, rev, timeout=300)
+            case["ref_fixed_paths_rev" if rev else "ref_fixed_paths"] = paths if rc == 0 else []
+            case["ref_fixed_rc_rev" if rev else "ref_fixed_rc"] = rc
+        lines = lpt.splitlines()
+        case["lp_rows"], case["lp_cols"] = map(int, lines[1].split())
+        sol, dt = highs_on_dump(lpt, 3000)
+        obj, xh = parse_sol(sol, nv)
+        case["ref_highs_objective"] = obj
+        case["ref_highs_seconds"] = dt
+        case["ref_highs_x_nz"] = [[i, v] for i, v in enumerate(xh) if v]
+        pr = probes(p, x, rng, k=12)
+        case["probes"] = [{"x_nz": [[i, v] for i, v in enumerate(q) if v], "feasible": bool(f), "score2": int(round(s))}
+                          for q in pr for (f, s) in [lp_eval(lpt, q, nv)]]
+        import fcntl
+        with open(out + ".lock", "w") as lk:          # several generator processes may run side by side
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            doc = json.load(open(out)) if os.path.exists(out) else {"generator": "tools/make_golden.py large", "cases": []}
+            if name not in {c["name"] for c in doc["cases"]}:
+                doc["cases"].append(case)
+            doc["cases"].sort(key=lambda c: c["name"])
+            json.dump(doc, open(out, "w"), indent=0)
+        print(name, "k", k, "oracle", case["oracle_score2"], f"{t_orc:.1f}s", "highs", obj, f"{dt:.0f}s", "bias", p.bias,
+              "ref rc", case["ref_inject_rc"], "fixed rc", case["ref_fixed_rc"], case["ref_fixed_paths"][:1], flush=True)
+    print("wrote", out, len(doc["cases"]), "cases")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "large":
+        return extra_large(sys.argv[2:])
     if len(sys.argv) > 1 and sys.argv[1] == "fractional":
         return extra_fractional()
     if len(sys.argv) > 1 and sys.argv[1] == "multi":
