@@ -713,7 +713,7 @@ __device__ __noinline__ int solve_one(const Params &P, Fixed &S, const Arr &R, u
         }
         if (result) {
             if (P.active) P.active[prob] = 1;
-            if (P.fb_list) { const uint32_t s = atomicAdd(P.fb_count, 1u); P.fb_list[s] = prob; }
+            if (P.fb_count) { const uint32_t s = atomicAdd(P.fb_count, 1u); if (P.fb_list) P.fb_list[s] = prob; }
         }
     }
     __syncwarp();

@@ -3,7 +3,7 @@
  *
  * Lets the C++ `--op bfb` host driver (ambigram_b200/host/ambigram_bfb.cpp) run on a box without a GPU: preloaded
  * in front of libambigram_b200.so (LD_PRELOAD), it answers the few entry points that need the device --
- * ambi_init / ambi_destroy / ambi_bfb_solve_batch / ambi_bfb_first_valid_order_batch -- with the CPU oracle
+ * ambi_init / ambi_destroy / ambi_bfb_solve[_batch] / ambi_bfb_first_valid_order[_batch] / ambi_bfb_all_valid_orders -- with the CPU oracle
  * (oracle/ambi_oracle.c).  Everything else the driver calls (ambi_bfb_construct_dag, ambi_bfb_imperfect_fbi,
  * ambi_bfb_expand_path: host code of the library) is the library's own.  What is under test is the driver: its
  * .lh / .juncs readers, depth -> copy number, getJuncCN / getIndelBias flattening, indelBFB and printing, against
@@ -57,5 +57,57 @@ int ambi_bfb_first_valid_order_batch(ambi_ctx *ctx, int32_t count, const ambi_da
         if (!r->found) r->bkp_len = 0;
         r->orders_tested = (uint64_t)tested;
     }
+    return AMBI_OK;
+}
+
+/* the single-call seams the reference's own main() binds (tools/patches/localhap_seams.patch) */
+int ambi_bfb_solve(ambi_ctx *ctx, const ambi_bfb_problem *problem, ambi_bfb_solution *solution)
+{
+    return ambi_bfb_solve_batch(ctx, 1, problem, solution);
+}
+
+int ambi_bfb_first_valid_order(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, ambi_order_result *result)
+{
+    return ambi_bfb_first_valid_order_batch(ctx, 1, dag, &reversed, result);
+}
+
+/* --all: the valid orders of the initial orientation, then -- if the lexicographically last topological order
+ * fails there (LGM:3691-3695) -- those of the flipped orientation (orders only; the host replays them) */
+int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, int32_t max_orders,
+                              int32_t *orders_out, int32_t *bkp_out, int32_t bkp_stride, int32_t *bkp_len_out,
+                              int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested)
+{
+    (void)ctx; (void)bkp_out; (void)bkp_stride; (void)bkp_len_out;
+    orc_dag d;
+    memset(&d, 0, sizeof d);
+    d.k = dag->k;
+    for (int v = 0; v < d.k; v++) { d.kind[v] = dag->kind[v]; d.a[v] = dag->a[v]; d.b[v] = dag->b[v]; d.cn[v] = dag->cn[v]; d.adj[v] = dag->adj[v]; }
+    *n_initial = *n_flipped = 0;
+    if (n_tested) *n_tested = 0;
+    if (d.k <= 0) return AMBI_OK;
+    const int fwd0 = reversed ? 0 : 1;
+    int64_t n1 = orc_all_valid_orders(&d, fwd0, orders_out, max_orders);
+    if (n1 > max_orders) { g_err = "shim: more valid orders than max_orders"; return AMBI_ERR_TOO_LARGE; }
+    /* lexicographically last topological order and whether it assembles in the initial orientation */
+    int32_t last[AMBI_MAX_COMPONENTS]; int indeg[AMBI_MAX_COMPONENTS] = {0}; char used[AMBI_MAX_COMPONENTS] = {0};
+    for (int i = 0; i < d.k; i++) for (int j = 0; j < d.k; j++) if ((d.adj[i] >> j) & 1) indeg[j]++;
+    int len = 0;
+    for (int step = 0; step < d.k; step++) {
+        int pick = -1;
+        for (int i = d.k - 1; i >= 0; i--) if (!used[i] && indeg[i] == 0) { pick = i; break; }
+        if (pick < 0) break;
+        used[pick] = 1; last[len++] = pick;
+        for (int j = 0; j < d.k; j++) if ((d.adj[pick] >> j) & 1) indeg[j]--;
+    }
+    int64_t n2 = 0;
+    if (len == d.k) {
+        int32_t bkp[4096]; int32_t bl = 0;
+        const int placed = orc_assemble_order(&d, last, fwd0, bkp, &bl);
+        if (placed < d.k) {
+            n2 = orc_all_valid_orders(&d, 1 - fwd0, orders_out + n1 * d.k, max_orders - n1);
+            if (n1 + n2 > max_orders) { g_err = "shim: more valid orders than max_orders"; return AMBI_ERR_TOO_LARGE; }
+        }
+    }
+    *n_initial = (int32_t)n1; *n_flipped = (int32_t)n2;
     return AMBI_OK;
 }
