@@ -280,10 +280,10 @@ class Context:
     """ambi_ctx: one per process / GPU."""
 
     def __init__(self, device: int = 0, rank: int = 0, world: int = 1, beam_width: int = 0,
-                 node_capacity: int = 0, shard_level: int = 0, lib_path: Optional[str] = None, small_kernel: bool = True):
+                 node_capacity: int = 0, shard_level: int = 0, lib_path: Optional[str] = None, small_kernel: bool = False):
         self.lib = load_library(lib_path)
-        # small_kernel=False (AMBI_CFG_NO_SMALL): every partition takes the level-synchronous global-memory path
-        cfg = _Config(device, rank, world, beam_width, node_capacity, shard_level, 0 if small_kernel else 1)
+        # small_kernel=True (AMBI_CFG_SMALL_KERNEL): partitions of <= 16 segments go through the warp-per-partition kernel first
+        cfg = _Config(device, rank, world, beam_width, node_capacity, shard_level, 2 if small_kernel else 0)
         self.handle = C.c_void_p()
         rc = self.lib.ambi_init(C.byref(self.handle), C.byref(cfg))
         if rc != 0:

@@ -131,7 +131,7 @@ extern "C" int ambi_init(ambi_ctx **out, const ambi_config *cfg)
     if (ctx->cfg.device < 0 || ctx->cfg.device >= ndev) { delete ctx; return fail(nullptr, AMBI_ERR_BAD_ARG, "ambi_init: bad device ordinal"); }
     if ((e = cudaSetDevice(ctx->cfg.device)) != cudaSuccess) { delete ctx; return fail(nullptr, AMBI_ERR_CUDA, cudaGetErrorString(e)); }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, AMBI_ERR_CUDA, cudaGetErrorString(e)); }
-    if (ctx->sa.init(ctx->stream, ctx->cfg.node_capacity, ctx->cfg.beam_width, ctx->cfg.rank, ctx->cfg.world, ctx->cfg.shard_level, (ctx->cfg.flags & AMBI_CFG_NO_SMALL) == 0)) {
+    if (ctx->sa.init(ctx->stream, ctx->cfg.node_capacity, ctx->cfg.beam_width, ctx->cfg.rank, ctx->cfg.world, ctx->cfg.shard_level, (ctx->cfg.flags & AMBI_CFG_SMALL_KERNEL) != 0)) {
         std::string m = ctx->sa.error(); ctx->sa.release(); cudaStreamDestroy(ctx->stream); delete ctx; return fail(nullptr, AMBI_ERR_CUDA, m);
     }
     if (ctx->sb.init(ctx->stream)) {

@@ -1,0 +1,165 @@
+// decode_common.cuh -- enumeration of a frontier record's row configurations, shared by the two Stage-A kernels
+// (k_expand in stage_a.cu: level-synchronous, records in HBM; k_solve_small in stage_small.cu: one warp per
+// partition, records in shared memory).  Reference model: BFB_ILP rows 1-6, src/LocalGenomicMap.cpp:4547-4703.
+//
+// A record at row a has, per open column j, the counters nP | nL<<2 | bP<<4 | bL<<6 (DESIGN.md "Search
+// formulation").  From them phase 1 derives six column masks, and the row configurations that satisfy the
+// budgets and the parent rows 1/3 are numbered 0..T-1:
+//   [0, nl0)          empty pattern set x class-0 loop multisets (parents already in the column): {}, singles in
+//                     A1 = okL1 & par1, doubles in A2 = okL2 & par2, pairs with the high end in A1 and the low end
+//                     any budgeted column below it
+//   then one block per pattern high end hi in okP & parP, (1 + k_hi) x (nl0 + e_hi) configurations:
+//                     pattern sets {hi} and {lo, hi} (lo any budgeted column below hi -- hi is lo's parent) times the
+//                     class-0 multisets plus the singles at E & below(hi), E = okL1 & ~par1 (their only parent is
+//                     this row's hi; two entries below hi are cut by rows 4/5 anyway).
+// Decoding a number back into (pattern ends, loop ends) used to be a population-count search per part
+// (17 % of k_expand's instructions in round 1).  Here phase 1 lists, once per record, the positions of the set
+// bits of okP and E and the class-0 multisets themselves, so the decode is a table read: the k-th budgeted column
+// below hi is the k-th set bit of okP whatever hi is, and likewise for E.
+#pragma once
+#include <stdint.h>
+
+namespace ambi {
+namespace dec {
+
+constexpr int L0CAP = 16;               // class-0 loop multisets listed per record (more: decoded the slow way)
+constexpr int CFGN = 63;                // "no column" in a packed configuration
+
+__device__ __forceinline__ uint32_t below(int b) { return (1u << b) - 1u; }
+__device__ __forceinline__ int nth_bit_slow(uint32_t m, int k) { for (; k > 0; --k) m &= m - 1; return __ffs((int)m) - 1; }
+// packed row configuration: p1 | p2<<6 | l1<<12 | l2<<18 (columns, CFGN = absent; p1<p2, l1<=l2)
+__device__ __forceinline__ uint32_t pack_cfg(int p1, int p2, int l1, int l2)
+{
+    return (uint32_t)(p1 & 63) | ((uint32_t)(p2 & 63) << 6) | ((uint32_t)(l1 & 63) << 12) | ((uint32_t)(l2 & 63) << 18);
+}
+__device__ __forceinline__ void unpack_cfg(uint32_t c, int &p1, int &p2, int &l1, int &l2)
+{
+    p1 = c & 63; p2 = (c >> 6) & 63; l1 = (c >> 12) & 63; l2 = (c >> 18) & 63;
+    p1 = p1 == CFGN ? -1 : p1; p2 = p2 == CFGN ? -1 : p2; l1 = l1 == CFGN ? -1 : l1; l2 = l2 == CFGN ? -1 : l2;
+}
+
+// Phase 1, lane = record: number of configurations of a record with these masks (nl0 = class-0 loop multisets).
+__device__ __forceinline__ uint32_t count_configs(uint32_t okP, uint32_t parP, uint32_t okL1, uint32_t okL2, uint32_t par1,
+                                                  uint32_t par2, uint32_t *nl0_out)
+{
+    const uint32_t A1 = okL1 & par1, A2 = okL2 & par2, E = okL1 & ~par1;
+    uint32_t nl0 = 1 + __popc(A1) + __popc(A2);
+    for (uint32_t m = A1; m; m &= m - 1) nl0 += __popc(okL1 & below(__ffs((int)m) - 1));
+    uint32_t total = nl0;
+    for (uint32_t m = okP & parP; m; m &= m - 1) {
+        const int hi = __ffs((int)m) - 1;
+        total += (1u + __popc(okP & below(hi))) * (nl0 + __popc(E & below(hi)));
+    }
+    *nl0_out = nl0;
+    return total;
+}
+
+// ... and its masks and decode lists, written to staging slot `slot`.  SH needs okP/parP/okL1/A2m/par1/nl0 [32],
+// posP/posE [NCOL][32] (uint8), L0 [L0CAP][32] (uint16).
+template <class SH>
+__device__ __forceinline__ void write_lists(SH &S, int slot, uint32_t okP, uint32_t parP, uint32_t okL1, uint32_t okL2,
+                                            uint32_t par1, uint32_t par2, uint32_t nl0)
+{
+    const uint32_t A1 = okL1 & par1, A2 = okL2 & par2, E = okL1 & ~par1;
+    if (nl0 >= 1 && nl0 <= (uint32_t)L0CAP) {          // nl0 == 0: a record without configurations (nothing is decoded)
+        int k = 1;
+        for (uint32_t m = A1; m; m &= m - 1) S.L0[k++][slot] = (uint16_t)((__ffs((int)m) - 1) | 0xff00);
+        for (uint32_t m = A2; m; m &= m - 1) { const int c = __ffs((int)m) - 1; S.L0[k++][slot] = (uint16_t)(c | (c << 8)); }
+        for (uint32_t m = A1; m; m &= m - 1) {
+            const int hi = __ffs((int)m) - 1;
+            for (uint32_t q = okL1 & below(hi); q; q &= q - 1) S.L0[k++][slot] = (uint16_t)((__ffs((int)q) - 1) | (hi << 8));
+        }
+    }
+    if (nl0 >= 1) {
+        int k = 0;
+        for (uint32_t m = okP; m; m &= m - 1, ++k) S.posP[k][slot] = (uint8_t)(__ffs((int)m) - 1);
+        k = 0;
+        for (uint32_t m = E; m; m &= m - 1, ++k) S.posE[k][slot] = (uint8_t)(__ffs((int)m) - 1);
+    }
+    S.okP[slot] = okP; S.parP[slot] = parP; S.okL1[slot] = okL1; S.A2m[slot] = A2; S.par1[slot] = par1; S.nl0[slot] = nl0;
+}
+
+// Lane = candidate: decode configuration number r of record `slot` and run the light test (rows 2/4/5 inside the
+// row, third-generation row `tm` with the record's running count, exact deviation of segment a through the
+// record's d0 = 2 cov_a - 2c_a and f0 = fb_a - 2J_a, and the O(1) prefilter lslack = slack - own bound).
+// Returns slot << 24 | cfg, or 0 when structurally infeasible; *pass = within the limit.
+template <class SH>
+__device__ __forceinline__ uint32_t decode_light(const SH &S, int slot, uint32_t r, uint32_t tm, bool *pass)
+{
+    const uint32_t okP = S.okP[slot], okL1 = S.okL1[slot], par1 = S.par1[slot];
+    const uint32_t nl0 = S.nl0[slot];
+    int p1 = -1, p2 = -1, l1 = -1, l2 = -1;
+    uint32_t li = r;
+    if (r >= nl0) {
+        r -= nl0;
+        const uint32_t E = okL1 & ~par1;
+        int hi = 0;
+        uint32_t width = 1;
+        for (uint32_t m = okP & S.parP[slot]; m; m &= m - 1) {
+            hi = __ffs((int)m) - 1;
+            width = nl0 + __popc(E & below(hi));
+            const uint32_t blk = (1u + __popc(okP & below(hi))) * width;
+            if (r < blk) break;
+            r -= blk;
+        }
+        // r < 2^16 and width < 2^11: (r + 0.5) / width is at least 2^-12 away from every integer, far more than the
+        // error of the approximate float division, so truncation gives the exact quotient
+        const uint32_t pi = __float2uint_rz(__fdividef((float)r + 0.5f, (float)width));
+        li = r - pi * width;
+        if (pi == 0) p1 = hi;
+        else { p2 = hi; p1 = (int)S.posP[pi - 1][slot]; }
+    }
+    if (li >= nl0) l1 = (int)S.posE[li - nl0][slot];
+    else if (li > 0) {
+        if (nl0 <= (uint32_t)L0CAP) {
+            const uint32_t e = S.L0[li][slot];
+            l1 = (int)(e & 0xffu); l2 = (int)(e >> 8); if (l2 == 0xff) l2 = -1;
+        } else {                                        // rare: more class-0 multisets than the list holds
+            --li;
+            const uint32_t M1 = okL1 & par1, M2 = S.A2m[slot];
+            const uint32_t n1 = __popc(M1), n2 = __popc(M2);
+            if (li < n1) l1 = nth_bit_slow(M1, (int)li);
+            else if (li - n1 < n2) { l1 = nth_bit_slow(M2, (int)(li - n1)); l2 = l1; }
+            else {
+                li -= n1 + n2;
+                for (uint32_t m = M1; m; m &= m - 1) {
+                    const int hi = __ffs((int)m) - 1;
+                    const uint32_t lm = okL1 & below(hi);
+                    const uint32_t k = __popc(lm);
+                    if (li < k) { l2 = hi; l1 = nth_bit_slow(lm, (int)li); break; }
+                    li -= k;
+                }
+            }
+        }
+    }
+    const int nl = (l1 >= 0) + (l2 >= 0);
+    const int lhi = l2 >= 0 ? l2 : l1;
+    const int pmax = p2 >= 0 ? p2 : p1;
+    bool feas = !(nl == 2 && pmax > lhi);            // a pattern end right of both loop entries (rows 4/5)
+    if (feas && tm) {
+        const int hits = (p1 >= 0 && ((tm >> p1) & 1)) + (p2 >= 0 && ((tm >> p2) & 1)) +
+                         (l1 >= 0 && ((tm >> l1) & 1)) + (l2 >= 0 && ((tm >> l2) & 1));
+        if (S.ptgs[slot] + hits > 5) feas = false;
+    }
+    if (!feas) { *pass = false; return 0u; }
+    const int w = (p1 >= 0) + (p2 >= 0) + 2 * nl;
+    const int err = abs(S.d0[slot] + 2 * w) + abs(S.f0[slot] + w);
+    *pass = err <= S.lslack[slot];
+    return ((uint32_t)slot << 24) | pack_cfg(p1, p2, l1, l2);
+}
+
+// Owner of candidate cb0 + lane by a run-length walk over the records' candidate ranges: s0 = record that owns
+// candidate cb0; bit (e - cb0 - 1) of the returned mask marks a record that ends at e, so the owner of lane k is
+// s0 + popc(mask & below(k)) and the next chunk starts at record s0 + popc(mask).  Every staged record must have at
+// least one configuration (ends are then distinct); entries of cstart beyond the last record hold the total.
+template <class SH>
+__device__ __forceinline__ uint32_t owner_mask(const SH &S, uint32_t s0, uint32_t cb0, int lane)
+{
+    const uint32_t idx = s0 + 1u + (uint32_t)lane;
+    const uint32_t e = S.cstart[idx <= 32u ? idx : 32u];
+    const uint32_t d = e - cb0 - 1u;
+    return __reduce_or_sync(0xffffffffu, (idx <= 32u && d < 32u) ? 1u << d : 0u);
+}
+
+}  // namespace dec
+}  // namespace ambi

@@ -22,15 +22,17 @@
 // against the oracle on a box without a GPU.
 #pragma once
 #include <stdint.h>
+#include "decode_common.cuh"
 
 namespace ambi {
 namespace small {
 
 constexpr int MAXN_SMALL = 16;          // one uint4 of column bytes
-constexpr int L0CAP = 16;               // class-0 loop multisets listed per record (more: decoded the slow way)
-constexpr int L0STRIDE = 18;            // u16 per row (odd number of words: rows land in different banks)
+using dec::L0CAP;
+using dec::below;
+using dec::pack_cfg;
+using dec::unpack_cfg;
 constexpr uint32_t T_EMPTY = 0xffffffffu;
-constexpr int CFGN = 63;                // "no column" in a packed configuration
 constexpr int MAXC = 4096;              // rank / parent index have 12 bits in key and back-pointer
 constexpr int NBINS = 64;
 enum { M_GREEDY = 0, M_BEAM = 1, M_EXACT = 2 };
@@ -59,8 +61,8 @@ struct Fixed {
     uint32_t okP[32], parP[32], okL1[32], A2m[32], par1[32];
     int32_t  score[32], slack[32], lslack[32], d0[32], f0[32], ptgs[32], frec[32];
     uint32_t nl0[32], cstart[33], rank[32];
-    uint32_t posPlo[32], posPhi[32], posElo[32], posEhi[32];
-    uint16_t L0[32][L0STRIDE];
+    uint8_t  posP[MAXN_SMALL][32], posE[MAXN_SMALL][32];    // positions of the set bits of okP / E, lowest first
+    uint16_t L0[L0CAP][32];                                 // class-0 loop multisets: low | high << 8 (0xff: none)
     uint32_t qh[64], qw_cfg[64];
     int32_t  qw_err[64], qw_tot[64];
     unsigned long long best;            // greedy: min (tot << 32 | code)
@@ -97,23 +99,11 @@ __device__ __forceinline__ Arr carve(uint8_t *base, int C, int tsize)
     return R;
 }
 
-__device__ __forceinline__ uint32_t below(int b) { return (1u << b) - 1u; }
 __device__ __forceinline__ uint32_t mix32s(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
-__device__ __forceinline__ uint32_t nib(uint32_t lo, uint32_t hi, int k) { return ((k < 8 ? lo : hi) >> (4 * (k & 7))) & 15u; }
-__device__ __forceinline__ int nth_bit_slow(uint32_t m, int k) { for (; k > 0; --k) m &= m - 1; return __ffs((int)m) - 1; }
 __device__ __forceinline__ uint32_t colbyte(const uint4 &s, int j)
 {
     const uint32_t w = (j >> 2) == 0 ? s.x : ((j >> 2) == 1 ? s.y : ((j >> 2) == 2 ? s.z : s.w));
     return (w >> (8 * (j & 3))) & 0xffu;
-}
-__device__ __forceinline__ uint32_t pack_cfg(int p1, int p2, int l1, int l2)
-{
-    return (uint32_t)(p1 & 63) | ((uint32_t)(p2 & 63) << 6) | ((uint32_t)(l1 & 63) << 12) | ((uint32_t)(l2 & 63) << 18);
-}
-__device__ __forceinline__ void unpack_cfg(uint32_t c, int &p1, int &p2, int &l1, int &l2)
-{
-    p1 = c & 63; p2 = (c >> 6) & 63; l1 = (c >> 12) & 63; l2 = (c >> 18) & 63;
-    p1 = p1 == CFGN ? -1 : p1; p2 = p2 == CFGN ? -1 : p2; l1 = l1 == CFGN ? -1 : l1; l2 = l2 == CFGN ? -1 : l2;
 }
 // search-order code of a row configuration (ambi_common.cuh): ip << 10 | il
 __device__ __forceinline__ uint32_t cfg_code(int n, int p1, int p2, int l1, int l2)
@@ -201,41 +191,11 @@ __device__ __noinline__ uint32_t phase1(Fixed &S, const Arr &R, int lane)
     const int pf = bound_cols(S, s, a, n, 0u, 0u, 0u, n - a, 0, false, false);
     const uint32_t cja = S.cj[a];
     uint32_t total = 0, nl0 = 0;
-    const uint32_t A1 = okL1 & par1, A2 = okL2 & par2, E = okL1 & ~par1;
-    if (have && slack >= 0) {
-        // class-0 loop multisets (parents already in the column): {}, singles in A1, doubles in A2, pairs with the
-        // high end in A1 and the low end any budgeted column below it -- listed once per record
-        nl0 = 1 + __popc(A1) + __popc(A2);
-        for (uint32_t m = A1; m; m &= m - 1) nl0 += __popc(okL1 & below(__ffs((int)m) - 1));
-        total = nl0;
-        // one block per pattern high end hi in okP & parP: pattern sets {hi}, {lo, hi} (lo any budgeted column
-        // below hi) times class-0 multisets plus the singles at E & below(hi) (their only parent is this row's hi)
-        for (uint32_t m = okP & parP; m; m &= m - 1) {
-            const int hi = __ffs((int)m) - 1;
-            total += (1u + __popc(okP & below(hi))) * (nl0 + __popc(E & below(hi)));
-        }
-        if (nl0 <= (uint32_t)L0CAP) {
-            uint16_t *L = S.L0[lane];
-            int k = 1;
-            for (uint32_t m = A1; m; m &= m - 1) L[k++] = (uint16_t)((__ffs((int)m) - 1) | 0xff00);
-            for (uint32_t m = A2; m; m &= m - 1) { const int c = __ffs((int)m) - 1; L[k++] = (uint16_t)(c | (c << 8)); }
-            for (uint32_t m = A1; m; m &= m - 1) {
-                const int hi = __ffs((int)m) - 1;
-                for (uint32_t q = okL1 & below(hi); q; q &= q - 1) L[k++] = (uint16_t)((__ffs((int)q) - 1) | (hi << 8));
-            }
-        }
-        unsigned long long lp = 0, le = 0;
-        int k = 0;
-        for (uint32_t m = okP; m; m &= m - 1, ++k) lp |= (unsigned long long)(__ffs((int)m) - 1) << (4 * k);
-        k = 0;
-        for (uint32_t m = E; m; m &= m - 1, ++k) le |= (unsigned long long)(__ffs((int)m) - 1) << (4 * k);
-        S.posPlo[lane] = (uint32_t)lp; S.posPhi[lane] = (uint32_t)(lp >> 32);
-        S.posElo[lane] = (uint32_t)le; S.posEhi[lane] = (uint32_t)(le >> 32);
-    }
-    S.okP[lane] = okP; S.parP[lane] = parP; S.okL1[lane] = okL1; S.A2m[lane] = A2; S.par1[lane] = par1;
+    if (have && slack >= 0) total = dec::count_configs(okP, parP, okL1, okL2, par1, par2, &nl0);
+    dec::write_lists(S, lane, okP, parP, okL1, okL2, par1, par2, nl0);
     S.score[lane] = score; S.slack[lane] = slack; S.lslack[lane] = slack - pf; S.frec[lane] = frec;
     S.d0[lane] = 2 * covC - (int)(cja & 0xffffu); S.f0[lane] = fbC - (int)(cja >> 16);
-    S.ptgs[lane] = ptgs; S.nl0[lane] = nl0;
+    S.ptgs[lane] = ptgs;
     S.rank[lane] = have ? (uint32_t)R.rank[idx] : 0u;
     uint32_t incl = total;
 #pragma unroll
@@ -245,74 +205,6 @@ __device__ __noinline__ uint32_t phase1(Fixed &S, const Arr &R, int lane)
     const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
     __syncwarp();
     return T;
-}
-
-// Decode candidate number r of record `slot` into a row configuration and run the light test (rows 2/4/5 inside
-// the row, third-generation row, exact deviation of segment a, O(1) prefilter).  Returns slot << 24 | cfg, or 0 when
-// structurally infeasible; *pass = within the limit.  Enumeration order as in stage_a.cu light_test().
-__device__ __forceinline__ uint32_t decode_light(const Fixed &S, int slot, uint32_t r, bool *pass)
-{
-    const uint32_t okP = S.okP[slot], okL1 = S.okL1[slot], par1 = S.par1[slot];
-    const uint32_t nl0 = S.nl0[slot];
-    int p1 = -1, p2 = -1, l1 = -1, l2 = -1;
-    uint32_t li = r;
-    if (r >= nl0) {
-        r -= nl0;
-        const uint32_t E = okL1 & ~par1;
-        int hi = 0;
-        uint32_t width = 1;
-        for (uint32_t m = okP & S.parP[slot]; m; m &= m - 1) {
-            hi = __ffs((int)m) - 1;
-            width = nl0 + __popc(E & below(hi));
-            const uint32_t blk = (1u + __popc(okP & below(hi))) * width;
-            if (r < blk) break;
-            r -= blk;
-        }
-        // r < 2^16 and width < 2^11: (r + 0.5) / width is at least 2^-12 away from every integer, far more than the
-        // error of the approximate float division, so truncation gives the exact quotient
-        const uint32_t pi = __float2uint_rz(__fdividef((float)r + 0.5f, (float)width));
-        li = r - pi * width;
-        if (pi == 0) p1 = hi;
-        else { p2 = hi; p1 = (int)nib(S.posPlo[slot], S.posPhi[slot], (int)pi - 1); }
-    }
-    if (li >= nl0) l1 = (int)nib(S.posElo[slot], S.posEhi[slot], (int)(li - nl0));
-    else if (li > 0) {
-        if (nl0 <= (uint32_t)L0CAP) {
-            const uint32_t e = S.L0[slot][li];
-            l1 = (int)(e & 0xffu); l2 = (int)(e >> 8); if (l2 == 0xff) l2 = -1;
-        } else {                                        // rare: more class-0 multisets than the list holds
-            --li;
-            const uint32_t M1 = okL1 & par1, M2 = S.A2m[slot];
-            const uint32_t n1 = __popc(M1), n2 = __popc(M2);
-            if (li < n1) l1 = nth_bit_slow(M1, (int)li);
-            else if (li - n1 < n2) { l1 = nth_bit_slow(M2, (int)(li - n1)); l2 = l1; }
-            else {
-                li -= n1 + n2;
-                for (uint32_t m = M1; m; m &= m - 1) {
-                    const int hi = __ffs((int)m) - 1;
-                    const uint32_t lm = okL1 & below(hi);
-                    const uint32_t k = __popc(lm);
-                    if (li < k) { l2 = hi; l1 = nth_bit_slow(lm, (int)li); break; }
-                    li -= k;
-                }
-            }
-        }
-    }
-    const int nl = (l1 >= 0) + (l2 >= 0);
-    const int lhi = l2 >= 0 ? l2 : l1;
-    const int pmax = p2 >= 0 ? p2 : p1;
-    bool feas = !(nl == 2 && pmax > lhi);            // a pattern end right of both loop entries (rows 4/5)
-    const uint32_t tm = S.tmask_row;
-    if (feas && tm) {
-        const int hits = (p1 >= 0 && ((tm >> p1) & 1)) + (p2 >= 0 && ((tm >> p2) & 1)) +
-                         (l1 >= 0 && ((tm >> l1) & 1)) + (l2 >= 0 && ((tm >> l2) & 1));
-        if (S.ptgs[slot] + hits > 5) feas = false;
-    }
-    if (!feas) { *pass = false; return 0u; }
-    const int w = (p1 >= 0) + (p2 >= 0) + 2 * nl;
-    const int err = abs(S.d0[slot] + 2 * w) + abs(S.f0[slot] + w);
-    *pass = err <= S.lslack[slot];
-    return ((uint32_t)slot << 24) | pack_cfg(p1, p2, l1, l2);
 }
 
 // One batch of light-test survivors through the O(n) bound; survivors are queued for the merge (beam / exact) or
@@ -486,7 +378,7 @@ __device__ __noinline__ void expand_level(Fixed &S, const Arr &R, int C, uint32_
             uint32_t entry = 0;
             if (c < T) {
                 const int slot = (int)(s0 + __popc(bm & lt_mask));
-                entry = decode_light(S, slot, c - S.cstart[slot], &pass);
+                entry = dec::decode_light(S, slot, c - S.cstart[slot], S.tmask_row, &pass);
             }
             n_infeas += __popc(__ballot_sync(0xffffffffu, c < T && !entry));
             s0 += __popc(bm);

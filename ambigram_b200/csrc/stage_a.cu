@@ -18,6 +18,7 @@
 //   k_beam_*    K3c    per-problem top-W selection by f-histogram (incumbent pass)
 #include "ambi_common.cuh"
 #include "stage_a.h"
+#include "decode_common.cuh"
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -65,50 +66,39 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     return x;
 }
 
-// position of the k-th (0-based) set bit of m
-__device__ __forceinline__ int nth_bit(uint32_t m, int k) {
-    int pos = 0;                         // branch-free binary search on population counts (a rolled loop
-#pragma unroll                           // over only the open columns measured slower: r01 notes)
-    for (int w = 16; w; w >>= 1) {
-        const int c = __popc(m & (((1u << w) - 1u) << pos));
-        const bool up = k >= c;
-        k -= up ? c : 0; pos += up ? w : 0;
-    }
-    return pos;
-}
 __device__ __forceinline__ uint32_t below(int b) { return (1u << b) - 1u; }
 
-// Per-warp staging of a group of GRP frontier records.  Column arrays are laid out
-// [column][slot] so that lanes working on different records hit different banks and
-// lanes working on the same record broadcast.
+// Per-warp staging of a group of up to GRP frontier records (only records that have at least one
+// configuration take a slot).  Column arrays are laid out [column][slot] so that lanes working on different
+// records hit different banks and lanes working on the same record broadcast.  NMAX = 16 or 32 columns: a batch
+// whose longest partition has at most 16 segments runs the narrow instantiation, whose staging is small enough
+// for 4 blocks of 8 warps per SM (the 2c|2J words of the partitions are read through the read-only cache
+// instead of being copied per slot).
+template <int NMAX>
 struct GroupShared {
-    uint8_t  colb[AMBI_MAXN][GRP];      // nP | nL<<2 | bP<<4 | bL<<6 of column j of record slot
-    uint32_t cj[AMBI_MAXN][GRP];        // 2c_j | 2J_j << 16 of the record's problem
+    uint8_t  colb[NMAX][GRP];           // nP | nL<<2 | bP<<4 | bL<<6 of column j of the record in the slot
+    uint8_t  posP[NMAX][GRP], posE[NMAX][GRP];   // decode lists (decode_common.cuh)
+    uint16_t L0[dec::L0CAP][GRP];
     uint32_t okP[GRP], parP[GRP];       // column may take a pattern end / has a pattern parent (row 1)
-    uint32_t okL1[GRP], okL2[GRP];      // column may take one / two loop ends
-    uint32_t par1[GRP], par2[GRP];      // column already holds >= 1 / >= 2 parents for a loop (row 3)
+    uint32_t okL1[GRP], A2m[GRP];       // column may take one loop end / two loop ends and has two parents
+    uint32_t par1[GRP];                 // column already holds >= 1 parent for a loop (row 3)
     uint32_t tmask[GRP];                // third-generation cells of this row
-    int32_t  score[GRP], slack[GRP], covC[GRP], fbC[GRP], ptgs[GRP], prob[GRP];
+    int32_t  score[GRP], slack[GRP], ptgs[GRP], prob[GRP];
+    int32_t  d0[GRP], f0[GRP];          // 2 cov_a - 2c_a and fb_a - 2J_a before the row's own entries
     int32_t  lslack[GRP];               // slack minus the record's own bound on segments > a (light-test limit)
     uint32_t pidx[GRP];
     uint32_t nl0[GRP];                  // loop multisets whose parents already exist (class 0)
     uint32_t cstart[GRP + 1];           // exclusive prefix of candidate counts
     uint8_t  n[GRP];
     uint32_t cnt[GRP];                  // structurally infeasible configurations per record (not scored)
+    const uint32_t *cjp[GRP];           // 2c_j | 2J_j << 16 of the record's partition (DevProblem::cj)
     unsigned long long best[GRP];       // EMIT_BEST: min (tot<<32 | cfg-order key)
     uint32_t qh[64];                    // light-test survivors awaiting the bound: slot<<24 | cfg
     uint32_t qw_cfg[64]; int32_t qw_err[64]; int32_t qw_tot[64];   // children awaiting the write
 };
 
-// packed row configuration: p1 | p2<<6 | l1<<12 | l2<<18 (columns, CFG_NONE = absent; p1<p2, l1<=l2)
-__device__ __forceinline__ uint32_t pack_cfg(int p1, int p2, int l1, int l2) {
-    return (uint32_t)(p1 & 63) | ((uint32_t)(p2 & 63) << 6) | ((uint32_t)(l1 & 63) << 12) | ((uint32_t)(l2 & 63) << 18);
-}
-__device__ __forceinline__ void unpack_cfg(uint32_t c, int &p1, int &p2, int &l1, int &l2) {
-    p1 = c & 63; p2 = (c >> 6) & 63; l1 = (c >> 12) & 63; l2 = (c >> 18) & 63;
-    p1 = p1 == CFG_NONE ? -1 : p1; p2 = p2 == CFG_NONE ? -1 : p2;
-    l1 = l1 == CFG_NONE ? -1 : l1; l2 = l2 == CFG_NONE ? -1 : l2;
-}
+using dec::pack_cfg;
+using dec::unpack_cfg;
 // search-order code of a configuration (see ambi_common.cuh)
 __device__ __forceinline__ uint32_t cfg_code(int n, int p1, int p2, int l1, int l2) {
     int ip = p1 < 0 ? 0 : ambi_ip_code(n - 1 - p1, p2 < 0 ? -1 : n - 1 - p2);
@@ -120,7 +110,8 @@ __device__ __forceinline__ uint32_t cfg_code(int n, int p1, int p2, int l1, int 
 // Mirrors oracle/ambi_oracle.c future_bound(): committed coverage / fold-back can only grow; what
 // can still be added is capped by the column budgets and by 6 per remaining row.
 // All lanes walk the same columns (jtop-1 .. a+1) so the shared-memory reads stay conflict free.
-__device__ __forceinline__ int child_bound(const GroupShared &S, int slot, int jtop, int a,
+template <int NMAX>
+__device__ __forceinline__ int child_bound(const GroupShared<NMAX> &S, int slot, int jtop, int a,
                                            int p1, int p2, int l1, int l2, int budget, bool active)
 {
     int lb = 0, cov = 0, capsum = 0;
@@ -133,11 +124,13 @@ __device__ __forceinline__ int child_bound(const GroupShared &S, int slot, int j
     // ends at or below the current column (the walk goes right to left, every end is < jtop)
     int rp_le = __popc(pm), rl_le = __popc(lm1) + __popc(lm2);
     int six = 6 * (jtop - 1 - a);                                // 6 * (j - a)
-    const uint16_t *cjh = reinterpret_cast<const uint16_t *>(&S.cj[0][0]);
+    const uint32_t *cjp = S.cjp[slot];
+    const int nrec = S.n[slot];
 #pragma unroll 2
     for (int j = jtop - 1; j > a; --j) {
         const uint32_t cb = S.colb[j][slot];
-        const int c2 = cjh[2 * (j * GRP + slot)], j2 = cjh[2 * (j * GRP + slot) + 1];
+        const uint32_t cjw = j < nrec ? __ldg(cjp + j) : 0u;   // columns beyond the record's partition are empty
+        const int c2 = (int)(cjw & 0xffffu), j2 = (int)(cjw >> 16);
         const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = cb >> 6;
         const int pab = pm >> 31, lab = (lm1 >> 31) + (lm2 >> 31);
         pm <<= 1; lm1 <<= 1; lm2 <<= 1;
@@ -163,7 +156,8 @@ __device__ __forceinline__ int child_bound(const GroupShared &S, int slot, int j
 
 // One batch of light-test survivors through the O(n) bound; survivors are queued for the write
 // (EMIT_ALL) or folded into the per-record arg-min (EMIT_BEST).  Returns the new write-queue fill.
-__device__ __noinline__ int heavy_batch(GroupShared &S, const LevelArgs &A, int count, int jtop, int qw)
+template <int NMAX>
+__device__ __noinline__ int heavy_batch(GroupShared<NMAX> &S, const LevelArgs &A, int count, int jtop, int qw)
 {
     const int lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -177,10 +171,9 @@ __device__ __noinline__ int heavy_batch(GroupShared &S, const LevelArgs &A, int 
     const int slack = S.slack[slot];
     if (act) {
         const int w = (p1 >= 0) + (p2 >= 0) + 2 * ((l1 >= 0) + (l2 >= 0));
-        const uint32_t cja = S.cj[a][slot];
-        err = abs(2 * (S.covC[slot] + w) - (int)(cja & 0xffff)) + abs(S.fbC[slot] + w - (int)(cja >> 16));
+        err = abs(S.d0[slot] + 2 * w) + abs(S.f0[slot] + w);
     }
-    const int lb = child_bound(S, slot, jtop, a, p1, p2, l1, l2, slack - err, act);
+    const int lb = child_bound<NMAX>(S, slot, jtop, a, p1, p2, l1, l2, slack - err, act);
     if (act) { tot = err + lb; keep = tot <= slack; }
     if (A.emit == EMIT_BEST) {
         if (keep) atomicMin(&S.best[slot], ((unsigned long long)(uint32_t)tot << 32) | cfg_code(S.n[slot], p1, p2, l1, l2));
@@ -192,7 +185,8 @@ __device__ __noinline__ int heavy_batch(GroupShared &S, const LevelArgs &A, int 
 }
 
 // Children are written by one thread each (`count` queued entries from the head of the queue).
-__device__ __noinline__ void write_batch(GroupShared &S, const LevelArgs &A, int count)
+template <int NMAX>
+__device__ __noinline__ void write_batch(GroupShared<NMAX> &S, const LevelArgs &A, int count)
 {
     const int lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -228,21 +222,25 @@ __device__ __noinline__ void write_batch(GroupShared &S, const LevelArgs &A, int
         return;
     }
     uint8_t *crec = A.children + (size_t)cslot * A.stride;
-    uint8_t *ccol = crec + offsetof(NodeHdr, col);
-    reinterpret_cast<uint4 *>(ccol)[0] = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4 *>(ccol)[1] = make_uint4(0, 0, 0, 0);
-#pragma unroll 1
-    for (int j = a + 1; j < n; ++j) {
-        const uint32_t cb = S.colb[j][slot];
-        const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = (cb >> 6) & 3;
-        const int pab = (j == p1) + (j == p2), lab = (j == l1) + (j == l2);
-        const int rp = (p1 >= 0 && p1 < j) + (p2 >= 0 && p2 < j);
-        const int rl = (l1 >= 0 && l1 < j) + (l2 >= 0 && l2 < j);
-        const int kP = 2 - pab - max(rp, rl);
-        const int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
-        const int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
-        ccol[j] = (uint8_t)((nP + pab) | ((nL + lab) << 2) | (nbP << 4) | (nbL << 6));
+    // the 32 column bytes are built in registers and leave as two 16-byte stores
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 1; j < NMAX; ++j) {
+        if (j > a && j < n) {
+            const uint32_t cb = S.colb[j][slot];
+            const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = (cb >> 6) & 3;
+            const int pab = (j == p1) + (j == p2), lab = (j == l1) + (j == l2);
+            const int rp = (p1 >= 0 && p1 < j) + (p2 >= 0 && p2 < j);
+            const int rl = (l1 >= 0 && l1 < j) + (l2 >= 0 && l2 < j);
+            const int kP = 2 - pab - max(rp, rl);
+            const int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
+            const int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
+            w[j >> 2] |= (uint32_t)(((nP + pab) | ((nL + lab) << 2) | (nbP << 4) | (nbL << 6)) & 0xff) << (8 * (j & 3));
+        }
     }
+    uint8_t *ccol = crec + offsetof(NodeHdr, col);
+    reinterpret_cast<uint4 *>(ccol)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4 *>(ccol)[1] = make_uint4(w[4], w[5], w[6], w[7]);
     const uint32_t tm = S.tmask[slot];
     int hits = 0;
     if (tm) hits = (p1 >= 0 && ((tm >> p1) & 1)) + (p2 >= 0 && ((tm >> p2) & 1)) +
@@ -261,91 +259,8 @@ __device__ __noinline__ void write_batch(GroupShared &S, const LevelArgs &A, int
     }
 }
 
-// Decode candidate number r of record `slot` into a row configuration and run the light test
-// (rows 2/4/5 inside the row, third-generation row, exact deviation of segment a).
-//
-// Enumeration of a record's row configurations (every one satisfies budgets and parent rows 1/3):
-//   [0, nl0)            empty pattern set x class-0 loop multisets (parents already in the column:
-//                       {}, singles in A1, doubles in A2, pairs with the high end in A1)
-//   then, for each pattern high end hi in S1 = okP & parP, a block of (1 + k_hi) x (nl0 + e_hi):
-//       pattern sets {hi} and {lo, hi}, lo any budgeted column below hi (hi is lo's parent), times
-//       class-0 multisets plus the singles at E(hi) = okL1 & ~par1 & below(hi), whose only parent
-//       is a pattern end of this row.  (A multiset of two entries below hi is cut by rows 4/5
-//       anyway, so nothing else can use the row's pattern ends as parents.)
-// Returns the queue entry (slot<<24 | cfg) or 0 if structurally infeasible; *pass = within the limit.
-__device__ __forceinline__ uint32_t light_test(const GroupShared &S, int a, int slot, uint32_t r, bool *pass)
-{
-    const uint32_t okP = S.okP[slot], okL1 = S.okL1[slot];
-    const uint32_t par1 = S.par1[slot];
-    const uint32_t nl0 = S.nl0[slot];
-    int p1 = -1, p2 = -1, l1 = -1, l2 = -1;
-    uint32_t li = r;
-    uint32_t extra = 0;                    // E(hi) of the chosen pattern high end
-    if (r >= nl0) {
-        r -= nl0;
-        int hi = 0;
-        uint32_t lows = 0, width = 1;
-        for (uint32_t m = okP & S.parP[slot]; m; m &= m - 1) {
-            hi = __ffs(m) - 1;
-            lows = okP & below(hi);
-            extra = okL1 & ~par1 & below(hi);
-            width = nl0 + __popc(extra);
-            const uint32_t blk = (1u + __popc(lows)) * width;
-            if (r < blk) break;
-            r -= blk;
-        }
-        // r < 2^16 and width < 2^11: (r + 0.5) / width is at least 2^-12 away from every integer, far more
-        // than the error of the approximate float division, so truncation gives the exact quotient
-        const uint32_t pi = __float2uint_rz(__fdividef((float)r + 0.5f, (float)width));
-        li = r - pi * width;
-        if (pi == 0) p1 = hi;
-        else { p2 = hi; p1 = nth_bit(lows, pi - 1); }
-    }
-    if (li >= nl0) l1 = nth_bit(extra, li - nl0);
-    else if (li > 0) {
-        --li;
-        const uint32_t M1 = okL1 & par1;
-        const uint32_t M2 = S.okL2[slot] & S.par2[slot];
-        const uint32_t n1 = __popc(M1), n2 = __popc(M2);
-        uint32_t lm = M1;                  // mask the low (or only) end is drawn from, and its rank in it
-        bool dbl = false;
-        if (li >= n1) {
-            li -= n1;
-            if (li < n2) { lm = M2; dbl = true; }
-            else {
-                li -= n2;                  // pairs: high end in M1, low end any budgeted column below it
-                for (uint32_t m = M1; m; m &= m - 1) {
-                    const int hi = __ffs(m) - 1;
-                    lm = okL1 & below(hi);
-                    const uint32_t k = __popc(lm);
-                    if (li < k) { l2 = hi; break; }
-                    li -= k;
-                }
-            }
-        }
-        l1 = nth_bit(lm, li);
-        if (dbl) l2 = l1;
-    }
-    bool feas = true;
-    const int nl = (l1 >= 0) + (l2 >= 0);
-    const int lhi = l2 >= 0 ? l2 : l1;
-    const int pmax = p2 >= 0 ? p2 : p1;
-    if (nl == 2 && pmax > lhi) feas = false;     // a pattern end right of both loop entries (rows 4/5)
-    const uint32_t tm = S.tmask[slot];
-    if (feas && tm) {
-        const int hits = (p1 >= 0 && ((tm >> p1) & 1)) + (p2 >= 0 && ((tm >> p2) & 1)) +
-                         (l1 >= 0 && ((tm >> l1) & 1)) + (l2 >= 0 && ((tm >> l2) & 1));
-        if (S.ptgs[slot] + hits > 5) feas = false;
-    }
-    if (!feas) { *pass = false; return 0u; }
-    const int w = (p1 >= 0) + (p2 >= 0) + 2 * nl;
-    const uint32_t cja = S.cj[a][slot];
-    const int err = abs(2 * (S.covC[slot] + w) - (int)(cja & 0xffff)) + abs(S.fbC[slot] + w - (int)(cja >> 16));
-    *pass = err <= S.lslack[slot];
-    return ((uint32_t)slot << 24) | pack_cfg(p1, p2, l1, l2);
-}
-
-__global__ void __launch_bounds__(WPB * 32)
+template <int NMAX>
+__global__ void __launch_bounds__(WPB * 32, NMAX <= 16 ? 4 : 3)
 k_expand(LevelArgs A_param)
 {
     extern __shared__ __align__(16) uint8_t s_raw[];
@@ -354,7 +269,7 @@ k_expand(LevelArgs A_param)
     __syncthreads();
     const LevelArgs &A = s_args;
     if (*A.overflow) return;                // an earlier level of this pass did not fit (block-uniform)
-    GroupShared &S = reinterpret_cast<GroupShared *>(s_raw)[threadIdx.x >> 5];
+    GroupShared<NMAX> &S = reinterpret_cast<GroupShared<NMAX> *>(s_raw)[threadIdx.x >> 5];
     const int lane = lane_id();
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int a = A.level;
@@ -370,18 +285,26 @@ k_expand(LevelArgs A_param)
         if (base >= pcount) break;          // no work left, or this level has overflowed: stop early
         __syncwarp();
 
-        // ---- phase 1: lane = record slot; stage column state and problem data, count candidates
+        // ---- phase 1: lane = record; column state in registers, masks, the record's own bound, candidate count.
+        //      Records with at least one configuration are then staged in consecutive slots.
         const bool have = (uint32_t)lane < grp_n && base + lane < pcount;
-        const uint8_t *prec = nullptr;
         const DevProblem *P = nullptr;
         int my_n = 0, slack = -1, lmax = 0;
-        S.best[lane] = ~0ull; S.cnt[lane] = 0;
+        uint32_t pidx = 0;
+        int4 hd = make_int4(0, 0, 0, 0);
+        uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (have) {
             // no list: the frontier is the previous level's child buffer itself, minus the records the
             // merge dropped (their header is flagged) and the completed assignments (n == level)
-            const uint32_t pidx = A.plist ? A.plist[base + lane] : base + lane;
-            prec = A.parents + (size_t)pidx * A.stride;
-            int4 hd = reinterpret_cast<const int4 *>(prec)[0];             // score, f, prob, tgs
+            pidx = A.plist ? A.plist[base + lane] : base + lane;
+            const uint8_t *prec = A.parents + (size_t)pidx * A.stride;
+            hd = reinterpret_cast<const int4 *>(prec)[0];                   // score, f, prob, tgs
+            const uint4 c0 = reinterpret_cast<const uint4 *>(prec + offsetof(NodeHdr, col))[0];
+            w[0] = c0.x; w[1] = c0.y; w[2] = c0.z; w[3] = c0.w;
+            if (NMAX > 16) {
+                const uint4 c1 = reinterpret_cast<const uint4 *>(prec + offsetof(NodeHdr, col))[1];
+                w[4] = c1.x; w[5] = c1.y; w[6] = c1.z; w[7] = c1.w;
+            }
             const bool dropped = (uint32_t)hd.w & 0x80000000u;
             hd.w &= 0x7fffffff;
             P = &A.probs[hd.z];
@@ -390,91 +313,90 @@ k_expand(LevelArgs A_param)
             // heuristic band (the beam only feeds the incumbent): a child may exceed its parent's f by
             // beam_delta, or by half of what is left up to the current limit if that is more
             if (A.beam_delta >= 0) slack = min(slack, hd.y - hd.x + max(A.beam_delta, (A.limit[hd.z] - hd.y) >> A.beam_shift));
-            S.pidx[lane] = pidx; S.score[lane] = hd.x; S.prob[lane] = hd.z; S.ptgs[lane] = hd.w;
-            S.slack[lane] = slack; S.n[lane] = (uint8_t)my_n;
-            S.tmask[lane] = P->has_tgs ? P->tgs_mask[a] : 0u;
         }
-        int jtop = my_n;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) jtop = max(jtop, __shfl_xor_sync(0xffffffffu, jtop, o));
         uint32_t okP = 0, parP = 0, okL1 = 0, okL2 = 0, par1 = 0, par2 = 0;
         int covC = 0, fbC = 0;
-#pragma unroll 1
-        for (int j = a; j < jtop; ++j) {
-            uint32_t b = 0, cjv = 0;
-            if (have && j < my_n) { b = prec[offsetof(NodeHdr, col) + j]; cjv = P->cj[j]; }
-            S.colb[j][lane] = (uint8_t)b;
-            S.cj[j][lane] = cjv;
-            const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
-            if (have && j < my_n) {
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            if (j >= a) {
+                const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;       // zero beyond the record's partition
+                const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
+                const bool inpart = j < my_n;
                 const bool root = (a == 0 && j == my_n - 1);
                 covC += nP + 2 * nL;
                 if (j == a) fbC = nP + 2 * nL;
-                okP |= (uint32_t)(bP >= 1) << j;
-                parP |= (uint32_t)(nP >= 1 || root) << j;
-                okL1 |= (uint32_t)(bL >= 1 && lmax >= 1) << j;
-                okL2 |= (uint32_t)(bL >= 2 && lmax >= 2) << j;
-                par1 |= (uint32_t)(nP + nL >= 1 || root) << j;
-                par2 |= (uint32_t)(nP + nL >= 2 || root) << j;
+                okP |= (uint32_t)(inpart && bP >= 1) << j;
+                parP |= (uint32_t)(inpart && (nP >= 1 || root)) << j;
+                okL1 |= (uint32_t)(inpart && bL >= 1 && lmax >= 1) << j;
+                okL2 |= (uint32_t)(inpart && bL >= 2 && lmax >= 2) << j;
+                par1 |= (uint32_t)(inpart && (nP + nL >= 1 || root)) << j;
+                par2 |= (uint32_t)(inpart && (nP + nL >= 2 || root)) << j;
             }
         }
         // The record's own bound on segments > a (what its parent level charged for them): every child's
         // bound on those segments is at least this (coverage only grows, budgets only shrink), so
         // err + pf > slack cuts a configuration before the O(n) bound is evaluated for it.
         int pf = 0;
-        if (have && slack >= 0) {
+        uint32_t cja = 0;
+        if (have && slack >= 0 && my_n > a) {
+            cja = __ldg(&P->cj[a]);
             int cov = 0, capsum = 0;
-#pragma unroll 1
-            for (int j = my_n - 1; j > a; --j) {
-                const uint32_t b = S.colb[j][lane];
-                const uint32_t cjw = S.cj[j][lane];
-                const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
-                const int cap = min(bP, 2) + 2 * min(bL, 2);
-                const int wn = nP + 2 * nL;
-                cov += wn; capsum += cap;
-                const int fmax = min(6 * (j - a + 1), capsum);
-                const int d = 2 * cov - (int)(cjw & 0xffff);
-                pf += d > 0 ? d : max(0, -d - 2 * fmax);
-                const int f = wn - (int)(cjw >> 16);
-                pf += f > 0 ? f : max(0, -f - (cap + min(capsum, 6)));
+#pragma unroll
+            for (int j = NMAX - 1; j >= 1; --j) {
+                if (j > a && j < my_n) {
+                    const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    const uint32_t cjw = __ldg(&P->cj[j]);
+                    const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
+                    const int cap = min(bP, 2) + 2 * min(bL, 2);
+                    const int wn = nP + 2 * nL;
+                    cov += wn; capsum += cap;
+                    const int fmax = min(6 * (j - a + 1), capsum);
+                    const int d = 2 * cov - (int)(cjw & 0xffff);
+                    pf += d > 0 ? d : max(0, -d - 2 * fmax);
+                    const int f = wn - (int)(cjw >> 16);
+                    pf += f > 0 ? f : max(0, -f - (cap + min(capsum, 6)));
+                }
             }
         }
-        S.lslack[lane] = slack - pf;
-        uint32_t total = 0;
-        if (have && my_n > a && slack >= 0) {
-            // class-0 loop multisets (parents already exist): {}, singles, doubles, pairs
-            const uint32_t A1 = okL1 & par1, A2 = okL2 & par2;
-            uint32_t nl0 = 1 + __popc(A1) + __popc(A2);
-            for (uint32_t m = A1; m; m &= m - 1) nl0 += __popc(okL1 & below(__ffs(m) - 1));
-            S.nl0[lane] = nl0;
-            total = nl0;
-            // one block per pattern high end (see light_test)
-            for (uint32_t m = okP & parP; m; m &= m - 1) {
-                const int hi = __ffs(m) - 1;
-                total += (1u + __popc(okP & below(hi))) * (nl0 + __popc(okL1 & ~par1 & below(hi)));
-            }
-        }
-        S.okP[lane] = okP; S.parP[lane] = parP; S.okL1[lane] = okL1; S.okL2[lane] = okL2;
-        S.par1[lane] = par1; S.par2[lane] = par2; S.covC[lane] = covC; S.fbC[lane] = fbC;
-        // exclusive prefix of candidate counts
+        uint32_t total = 0, nl0 = 0;
+        if (have && my_n > a && slack >= 0) total = dec::count_configs(okP, parP, okL1, okL2, par1, par2, &nl0);
+        const uint32_t nzm = __ballot_sync(0xffffffffu, total > 0);
+        const int ns = __popc(nzm);                       // staged records
+        const int slot = __popc(nzm & lt_mask);
+        // exclusive prefix of candidate counts over the staged records
         uint32_t incl = total;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        S.cstart[lane + 1] = incl;
-        if (lane == 0) S.cstart[0] = 0;
         const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
+        int jtop = total > 0 ? my_n : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) jtop = max(jtop, __shfl_xor_sync(0xffffffffu, jtop, o));
+        if (total > 0) {
+            dec::write_lists(S, slot, okP, parP, okL1, okL2, par1, par2, nl0);
+#pragma unroll
+            for (int j = 0; j < NMAX; ++j) if (j >= a && j < jtop) S.colb[j][slot] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+            S.pidx[slot] = pidx; S.score[slot] = hd.x; S.prob[slot] = hd.z; S.ptgs[slot] = hd.w;
+            S.slack[slot] = slack; S.lslack[slot] = slack - pf; S.n[slot] = (uint8_t)my_n;
+            S.d0[slot] = 2 * covC - (int)(cja & 0xffffu); S.f0[slot] = fbC - (int)(cja >> 16);
+            S.tmask[slot] = P->has_tgs ? P->tgs_mask[a] : 0u;
+            S.cjp[slot] = P->cj;
+            S.cstart[slot + 1] = incl;
+        }
+        if (lane >= ns) S.cstart[lane + 1] = T;           // beyond the last staged record
+        if (lane == 0) S.cstart[0] = 0;
+        S.best[lane] = ~0ull; S.cnt[lane] = 0;
         __syncwarp();
 
         // ---- phase 2: lane = candidate (flattened over the group's records); three stages fed
         //      through two shared-memory queues so that each stage runs with full lanes
         int qh = 0, qw = 0;                 // queue fills (warp-uniform)
-        uint32_t cb0 = 0;
+        uint32_t cb0 = 0, s0 = 0;           // s0: staged record that owns candidate cb0
         uint32_t n_heavy = 0, n_write = 0, n_hcalls = 0;  // funnel statistics (warp-uniform)
         for (;;) {
             if (qw >= 32 || (cb0 >= T && qh == 0 && qw > 0)) {
                 const int cnt = min(qw, 32);
                 n_write += cnt;
-                write_batch(S, A, cnt);
+                write_batch<NMAX>(S, A, cnt);
                 __syncwarp();
                 qw -= cnt;
                 uint32_t m0 = 0; int m1 = 0, m2 = 0;
@@ -487,7 +409,7 @@ k_expand(LevelArgs A_param)
             if (qh >= 32 || (cb0 >= T && qh > 0)) {
                 const int cnt = min(qh, 32);
                 n_heavy += cnt; ++n_hcalls;
-                qw = heavy_batch(S, A, cnt, jtop, qw);
+                qw = heavy_batch<NMAX>(S, A, cnt, jtop, qw);
                 __syncwarp();
                 qh -= cnt;
                 const uint32_t mv = lane < qh ? S.qh[32 + lane] : 0u;
@@ -497,20 +419,19 @@ k_expand(LevelArgs A_param)
                 continue;
             }
             if (cb0 >= T) break;
+            const uint32_t bm = dec::owner_mask(S, s0, cb0, lane);
             const uint32_t c = cb0 + lane;
-            cb0 += 32;
             bool pass = false;
             uint32_t entry = 0;
-            int bad_slot = 0;
+            int own = 0;
             if (c < T) {
-                int slot = 0;                // owning record: largest slot with cstart[slot] <= c
-#pragma unroll
-                for (int o = 16; o; o >>= 1) if (S.cstart[slot + o] <= c) slot += o;
-                entry = light_test(S, a, slot, c - S.cstart[slot], &pass);
-                bad_slot = slot;
+                own = (int)(s0 + __popc(bm & lt_mask));
+                entry = dec::decode_light(S, own, c - S.cstart[own], S.tmask[own], &pass);
             }
             // candidates scored = enumerated minus the (few) structurally infeasible ones, per record
-            if (c < T && !entry) atomicAdd(&S.cnt[bad_slot], 1u);
+            if (c < T && !entry) atomicAdd(&S.cnt[own], 1u);
+            s0 += __popc(bm);
+            cb0 += 32;
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
             if (pass) S.qh[qh + __popc(bal & lt_mask)] = entry;
             qh += __popc(bal);
@@ -520,7 +441,7 @@ k_expand(LevelArgs A_param)
             // every record emits its arg-min child (tot, then search order)
             __syncwarp();
             const unsigned long long bk = S.best[lane];
-            const bool has = bk != ~0ull;
+            const bool has = lane < ns && bk != ~0ull;
             const uint32_t hm = __ballot_sync(0xffffffffu, has);
             if (has) {
                 const int n = S.n[lane];
@@ -532,19 +453,18 @@ k_expand(LevelArgs A_param)
                 if (il) { int q1 = 0; while (ambi_il_code(q1 + 1, -1) <= il) ++q1; const int off = il - ambi_il_code(q1, -1);
                           l1 = n - 1 - q1; if (off > 0) l2 = (off - 1 == q1) ? l1 : n - 1 - (off - 1); }
                 const int tot = (int)(bk >> 32);
-                const int w = (p1 >= 0) + (p2 >= 0) + 2 * ((l1 >= 0) + (l2 >= 0));
-                const uint32_t cja = S.cj[a][lane];
-                const int err = abs(2 * (S.covC[lane] + w) - (int)(cja & 0xffff)) + abs(S.fbC[lane] + w - (int)(cja >> 16));
+                const int w2 = (p1 >= 0) + (p2 >= 0) + 2 * ((l1 >= 0) + (l2 >= 0));
+                const int err = abs(S.d0[lane] + 2 * w2) + abs(S.f0[lane] + w2);
                 const int pos = __popc(hm & lt_mask);
                 S.qw_cfg[pos] = ((uint32_t)lane << 24) | pack_cfg(p1, p2, l1, l2); S.qw_err[pos] = err; S.qw_tot[pos] = tot;
             }
             __syncwarp();
-            if (hm) { n_write += __popc(hm); write_batch(S, A, __popc(hm)); __syncwarp(); }
+            if (hm) { n_write += __popc(hm); write_batch<NMAX>(S, A, __popc(hm)); __syncwarp(); }
         }
-        // ---- statistics (per problem of each record)
+        // ---- statistics (per problem of each staged record)
         __syncwarp();
         if (lane < 4 && T) atomicAdd(&A.funnel[lane], (unsigned long long)(lane == 0 ? T : (lane == 1 ? n_heavy : (lane == 2 ? n_write : n_hcalls))));
-        if (have && S.cstart[lane + 1] - S.cstart[lane] > 0) {
+        if (lane < ns) {
             atomicAdd(&A.cand_count[S.prob[lane]], (unsigned long long)(S.cstart[lane + 1] - S.cstart[lane] - S.cnt[lane]));
             atomicAdd(&A.node_count[S.prob[lane]], 1ull);
         }
@@ -938,14 +858,19 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     int dev = 0; CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev));
     gen_ = 1;
-    expand_smem_ = sizeof(GroupShared) * WPB;
-    CK(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_));
+    // two instantiations of the expansion kernel: staging for 16 columns (batches whose longest partition has at
+    // most 16 segments; 4 blocks per SM) and for 32
+    expand_smem_[0] = sizeof(GroupShared<16>) * WPB; expand_smem_[1] = sizeof(GroupShared<32>) * WPB;
+    CK(cudaFuncSetAttribute(k_expand<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[0]));
+    CK(cudaFuncSetAttribute(k_expand<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[1]));
     int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand, WPB * 32, expand_smem_));
-    expand_blocks_ = sms_ * (per_sm > 0 ? per_sm : 1);
-    // warp-per-partition kernel for partitions of up to 16 segments (AMBI_NO_SMALL=1: everything takes the
-    // global-memory path; AMBI_SMALL_C: records per level and warp)
-    small_on_ = use_small && getenv("AMBI_NO_SMALL") == nullptr;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand<16>, WPB * 32, expand_smem_[0]));
+    expand_blocks_[0] = sms_ * (per_sm > 0 ? per_sm : 1);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand<32>, WPB * 32, expand_smem_[1]));
+    expand_blocks_[1] = sms_ * (per_sm > 0 ? per_sm : 1);
+    // warp-per-partition kernel for partitions of up to 16 segments (opt-in: AMBI_CFG_SMALL_KERNEL or AMBI_SMALL=1;
+    // AMBI_SMALL_C: records per level and warp)
+    small_on_ = use_small || getenv("AMBI_SMALL") != nullptr;
     int C = 256;
     if (const char *e = getenv("AMBI_SMALL_C")) C = std::max(32, atoi(e));
     if (small_on_) {
@@ -1029,6 +954,13 @@ int StageA::upload(const DevProblem *host_probs, int count)
     return 0;
 }
 
+void StageA::launch_expand(const LevelArgs &L)
+{
+    if (nmax_ <= 16) k_expand<16><<<expand_blocks_[0], WPB * 32, expand_smem_[0], stream_>>>(L);
+    else k_expand<32><<<expand_blocks_[1], WPB * 32, expand_smem_[1], stream_>>>(L);
+    ++launches_;
+}
+
 // One level: expand -> (merge) -> finalize (-> beam selection).
 //   mode 0: greedy incumbent (every record emits its arg-min child)
 //   mode 1: beam incumbent (children within the limit, top-W per problem kept)
@@ -1054,7 +986,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
         if (prof_used_ + 2 > prof_ev_.size()) { cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); prof_ev_.push_back(e0); prof_ev_.push_back(e1); }
         CK(cudaEventRecord(prof_ev_[prof_used_], stream_));
     }
-    k_expand<<<expand_blocks_, WPB * 32, expand_smem_, stream_>>>(L); ++launches_;
+    launch_expand(L);
     if (prof) { CK(cudaEventRecord(prof_ev_[prof_used_ + 1], stream_)); prof_used_ += 2; }
     const bool beam = mode == 1;
     int32_t *fmin_cur = d_fmin_ + (size_t)level * count_;
@@ -1376,7 +1308,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         L.cand_count = d_cand_; L.node_count = d_node_; L.funnel = d_funnel_; L.work_counter = c_work; L.overflow = c_over;
         L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = EMIT_ALL; L.beam_delta = -1; L.beam_shift = 1;
         L.shard_world = sw; L.shard_rank = rank_; L.shard_level = shard_level_eff_; L.gpw = gpw_;
-        k_expand<<<expand_blocks_, WPB * 32, expand_smem_, stream_>>>(L); ++launches_;
+        launch_expand(L);
         uint32_t ctr[2] = {0, 0};
         CK(cudaMemcpyAsync(&ctr[0], c_over, 4, cudaMemcpyDeviceToHost, stream_));
         CK(cudaMemcpyAsync(&ctr[1], c_child, 4, cudaMemcpyDeviceToHost, stream_));

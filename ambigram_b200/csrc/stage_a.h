@@ -6,6 +6,8 @@
 
 namespace ambi {
 
+struct LevelArgs;
+
 struct HostResult {
     int64_t score2;
     int32_t incumbent;
@@ -19,7 +21,7 @@ class StageA {
 public:
     StageA();
     ~StageA();
-    int init(cudaStream_t stream, int64_t node_capacity, int beam_width, int rank, int world, int shard_level, bool use_small = true);
+    int init(cudaStream_t stream, int64_t node_capacity, int beam_width, int rank, int world, int shard_level, bool use_small = false);
     void release();
     // pinned staging for `count` problem descriptors; the caller fills it and then calls upload(ptr, count)
     DevProblem *staging(int count);
@@ -67,6 +69,7 @@ private:
     int ensure_problem_arrays(int count);
     void free_problem_arrays();
     int run_level(int level, int cur, int mode, int shard_world);
+    void launch_expand(const LevelArgs &L);
     int run_pass(int mode, int shard_world, bool first);
     int enqueue_incumbent(bool coop);
     int enqueue_exact(bool sharded);
@@ -95,8 +98,8 @@ private:
     uint32_t *list_[2] = {nullptr, nullptr};
     unsigned long long *table_ = nullptr;
     uint32_t *counters_ = nullptr;
-    size_t expand_smem_ = 0;
-    int expand_blocks_ = 148;
+    size_t expand_smem_[2] = {0, 0};
+    int expand_blocks_[2] = {148, 148};
     // per-problem arrays
     int prob_cap_ = 0, count_ = 0, nmax_ = 0;
     DevProblem *d_probs_ = nullptr, *h_probs_ = nullptr;   // device array, pinned host staging
@@ -121,7 +124,7 @@ private:
     void *allreduce_user_ = nullptr;
     int32_t *d_flag_ = nullptr;
     // warp-per-partition kernel (stage_small.cu): partitions of 2..16 segments
-    bool small_on_ = true;
+    bool small_on_ = false;
     SmallConfig small_cfg_;
     uint32_t *d_small_list_ = nullptr, *d_arena_ = nullptr;
     uint8_t *d_active_ = nullptr, *d_active_base_ = nullptr;     // active: still to be solved by the global-memory path

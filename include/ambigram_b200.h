@@ -68,8 +68,10 @@ typedef struct {
 } ambi_config;
 
 /* ambi_config.flags */
-#define AMBI_CFG_NO_SMALL 1u   /* do not use the warp-per-partition kernel for partitions of <= 16 segments:
-                                  every partition takes the level-synchronous global-memory path (tests, profiling) */
+#define AMBI_CFG_SMALL_KERNEL 2u /* partitions of <= 16 segments are first tried by the warp-per-partition kernel (whole search
+                                  in shared memory, one launch per batch; stage_small.cu); what does not fit its record
+                                  capacity joins the others on the level-synchronous global-memory path.  Off by default:
+                                  measured slower than the global-memory path on B200. */
 
 /* One partition's Stage-A problem: what BFB_ILP reads from the graph.
  *   seg_cn2[i] = 2*c_i  (segment copy number after getIndelBias,

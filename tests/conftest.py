@@ -44,15 +44,15 @@ def ctx():
 
 
 @pytest.fixture(scope="session")
-def ctx_global():
-    """every partition on the level-synchronous global-memory path (AMBI_CFG_NO_SMALL): the path of partitions with
-    more than 16 segments, exercised here on small ones as well"""
+def ctx_small():
+    """partitions of up to 16 segments through the warp-per-partition kernel first (AMBI_CFG_SMALL_KERNEL); whatever
+    does not fit its record capacity continues on the level-synchronous global-memory path"""
     from ambigram_b200 import capi
-    c = capi.Context(device=0, small_kernel=False)
+    c = capi.Context(device=0, small_kernel=True)
     yield c
     c.close()
 
 
-@pytest.fixture(params=["small", "global"])
-def any_ctx(request, ctx, ctx_global):
-    return ctx if request.param == "small" else ctx_global
+@pytest.fixture(params=["global", "small"])
+def any_ctx(request, ctx, ctx_small):
+    return ctx if request.param == "global" else ctx_small

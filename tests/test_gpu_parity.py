@@ -166,7 +166,7 @@ def test_prefix_sharded_solve_combines_to_the_same_optimum():
     for world in (2, 4):
         shard_sols = []
         for rank in range(world):
-            with capi.Context(device=0, rank=rank, world=world, small_kernel=False) as c:   # sharding is a property of the global-memory path
+            with capi.Context(device=0, rank=rank, world=world) as c:
                 shard_sols.append([c.solve_shard(p) for p in probs])
         for i, p in enumerate(probs):
             best = None
@@ -193,7 +193,7 @@ def test_small_buffers_fall_back_to_chunked_depth_first_pass():
 def test_overflow_is_reported_loudly(monkeypatch):
     monkeypatch.setenv("AMBI_NO_CHUNKED", "1")
     p = lh.problem_from_lh(synth.generate(16, 5, 0, 0.5).lh_text())
-    with capi.Context(device=0, node_capacity=64, small_kernel=False) as c:
+    with capi.Context(device=0, node_capacity=64) as c:
         with pytest.raises(capi.AmbiError) as e:
             c.solve(p)
         assert e.value.status == -5
@@ -221,7 +221,7 @@ def test_small_kernel_hands_wide_frontiers_to_the_global_path(monkeypatch):
     to the global-memory path inside the same call; answers are the oracle's either way"""
     monkeypatch.setenv("AMBI_SMALL_C", "32")
     probs = [lh.problem_from_lh(synth.generate(n, f, 60 + s, 0.5).lh_text()) for (n, f) in [(8, 3), (12, 4), (14, 4), (16, 5)] for s in range(6)]
-    with capi.Context(device=0) as c:
+    with capi.Context(device=0, small_kernel=True) as c:
         b = c.upload(probs)
         b.run(); c.sync()
         sols = b.fetch()
