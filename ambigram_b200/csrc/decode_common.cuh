@@ -55,7 +55,8 @@ __device__ __forceinline__ uint32_t count_configs(uint32_t okP, uint32_t parP, u
 }
 
 // ... and its masks and decode lists, written to staging slot `slot`.  SH needs okP/parP/okL1/A2m/par1/nl0 [32],
-// posP/posE [NCOL][32] (uint8), L0 [L0CAP][32] (uint16).
+// posP/posE [32][NCOL] (uint8), L0 [32][L0CAP] (uint16): a record's lists are contiguous, so lanes decoding
+// candidates of the same record read the same few words.
 template <class SH>
 __device__ __forceinline__ void write_lists(SH &S, int slot, uint32_t okP, uint32_t parP, uint32_t okL1, uint32_t okL2,
                                             uint32_t par1, uint32_t par2, uint32_t nl0)
@@ -63,18 +64,18 @@ __device__ __forceinline__ void write_lists(SH &S, int slot, uint32_t okP, uint3
     const uint32_t A1 = okL1 & par1, A2 = okL2 & par2, E = okL1 & ~par1;
     if (nl0 >= 1 && nl0 <= (uint32_t)L0CAP) {          // nl0 == 0: a record without configurations (nothing is decoded)
         int k = 1;
-        for (uint32_t m = A1; m; m &= m - 1) S.L0[k++][slot] = (uint16_t)((__ffs((int)m) - 1) | 0xff00);
-        for (uint32_t m = A2; m; m &= m - 1) { const int c = __ffs((int)m) - 1; S.L0[k++][slot] = (uint16_t)(c | (c << 8)); }
+        for (uint32_t m = A1; m; m &= m - 1) S.L0[slot][k++] = (uint16_t)((__ffs((int)m) - 1) | 0xff00);
+        for (uint32_t m = A2; m; m &= m - 1) { const int c = __ffs((int)m) - 1; S.L0[slot][k++] = (uint16_t)(c | (c << 8)); }
         for (uint32_t m = A1; m; m &= m - 1) {
             const int hi = __ffs((int)m) - 1;
-            for (uint32_t q = okL1 & below(hi); q; q &= q - 1) S.L0[k++][slot] = (uint16_t)((__ffs((int)q) - 1) | (hi << 8));
+            for (uint32_t q = okL1 & below(hi); q; q &= q - 1) S.L0[slot][k++] = (uint16_t)((__ffs((int)q) - 1) | (hi << 8));
         }
     }
     if (nl0 >= 1) {
         int k = 0;
-        for (uint32_t m = okP; m; m &= m - 1, ++k) S.posP[k][slot] = (uint8_t)(__ffs((int)m) - 1);
+        for (uint32_t m = okP; m; m &= m - 1, ++k) S.posP[slot][k] = (uint8_t)(__ffs((int)m) - 1);
         k = 0;
-        for (uint32_t m = E; m; m &= m - 1, ++k) S.posE[k][slot] = (uint8_t)(__ffs((int)m) - 1);
+        for (uint32_t m = E; m; m &= m - 1, ++k) S.posE[slot][k] = (uint8_t)(__ffs((int)m) - 1);
     }
     S.okP[slot] = okP; S.parP[slot] = parP; S.okL1[slot] = okL1; S.A2m[slot] = A2; S.par1[slot] = par1; S.nl0[slot] = nl0;
 }
@@ -107,12 +108,12 @@ __device__ __forceinline__ uint32_t decode_light(const SH &S, int slot, uint32_t
         const uint32_t pi = __float2uint_rz(__fdividef((float)r + 0.5f, (float)width));
         li = r - pi * width;
         if (pi == 0) p1 = hi;
-        else { p2 = hi; p1 = (int)S.posP[pi - 1][slot]; }
+        else { p2 = hi; p1 = (int)S.posP[slot][pi - 1]; }
     }
-    if (li >= nl0) l1 = (int)S.posE[li - nl0][slot];
+    if (li >= nl0) l1 = (int)S.posE[slot][li - nl0];
     else if (li > 0) {
         if (nl0 <= (uint32_t)L0CAP) {
-            const uint32_t e = S.L0[li][slot];
+            const uint32_t e = S.L0[slot][li];
             l1 = (int)(e & 0xffu); l2 = (int)(e >> 8); if (l2 == 0xff) l2 = -1;
         } else {                                        // rare: more class-0 multisets than the list holds
             --li;

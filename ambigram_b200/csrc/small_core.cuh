@@ -61,8 +61,8 @@ struct Fixed {
     uint32_t okP[32], parP[32], okL1[32], A2m[32], par1[32];
     int32_t  score[32], slack[32], lslack[32], d0[32], f0[32], ptgs[32], frec[32];
     uint32_t nl0[32], cstart[33], rank[32];
-    uint8_t  posP[MAXN_SMALL][32], posE[MAXN_SMALL][32];    // positions of the set bits of okP / E, lowest first
-    uint16_t L0[L0CAP][32];                                 // class-0 loop multisets: low | high << 8 (0xff: none)
+    uint8_t  posP[32][MAXN_SMALL], posE[32][MAXN_SMALL];    // positions of the set bits of okP / E, lowest first
+    uint16_t L0[32][L0CAP];                                 // class-0 loop multisets: low | high << 8 (0xff: none)
     uint32_t qh[64], qw_cfg[64];
     int32_t  qw_err[64], qw_tot[64];
     unsigned long long best;            // greedy: min (tot << 32 | code)

@@ -76,9 +76,10 @@ __device__ __forceinline__ uint32_t below(int b) { return (1u << b) - 1u; }
 // instead of being copied per slot).
 template <int NMAX>
 struct GroupShared {
-    uint8_t  colb[NMAX][GRP];           // nP | nL<<2 | bP<<4 | bL<<6 of column j of the record in the slot
-    uint8_t  posP[NMAX][GRP], posE[NMAX][GRP];   // decode lists (decode_common.cuh)
-    uint16_t L0[dec::L0CAP][GRP];
+    uint32_t colw[NMAX / 4][GRP];       // column bytes nP | nL<<2 | bP<<4 | bL<<6 of the record in the slot, 4 columns per word
+    __device__ __forceinline__ uint32_t colb(int j, int slot) const { return reinterpret_cast<const uint8_t *>(&colw[j >> 2][slot])[j & 3]; }
+    uint8_t  posP[GRP][NMAX], posE[GRP][NMAX];   // decode lists (decode_common.cuh)
+    uint16_t L0[GRP][dec::L0CAP];
     uint32_t okP[GRP], parP[GRP];       // column may take a pattern end / has a pattern parent (row 1)
     uint32_t okL1[GRP], A2m[GRP];       // column may take one loop end / two loop ends and has two parents
     uint32_t par1[GRP];                 // column already holds >= 1 parent for a loop (row 3)
@@ -128,7 +129,7 @@ __device__ __forceinline__ int child_bound(const GroupShared<NMAX> &S, int slot,
     const int nrec = S.n[slot];
 #pragma unroll 2
     for (int j = jtop - 1; j > a; --j) {
-        const uint32_t cb = S.colb[j][slot];
+        const uint32_t cb = S.colb(j, slot);
         const uint32_t cjw = j < nrec ? __ldg(cjp + j) : 0u;   // columns beyond the record's partition are empty
         const int c2 = (int)(cjw & 0xffffu), j2 = (int)(cjw >> 16);
         const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = cb >> 6;
@@ -222,25 +223,31 @@ __device__ __noinline__ void write_batch(GroupShared<NMAX> &S, const LevelArgs &
         return;
     }
     uint8_t *crec = A.children + (size_t)cslot * A.stride;
-    // the 32 column bytes are built in registers and leave as two 16-byte stores
-    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // the 32 column bytes leave one 4-column word at a time (the loop over words stays rolled: the kernel has to fit
+    // the instruction cache)
+    uint32_t *ccol = reinterpret_cast<uint32_t *>(crec + offsetof(NodeHdr, col));
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+        uint32_t wq = 0;
+        if (q < NMAX / 4 && 4 * q + 3 > a && 4 * q < n) {
+            const uint32_t pw = S.colw[q][slot];
 #pragma unroll
-    for (int j = 1; j < NMAX; ++j) {
-        if (j > a && j < n) {
-            const uint32_t cb = S.colb[j][slot];
-            const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = (cb >> 6) & 3;
-            const int pab = (j == p1) + (j == p2), lab = (j == l1) + (j == l2);
-            const int rp = (p1 >= 0 && p1 < j) + (p2 >= 0 && p2 < j);
-            const int rl = (l1 >= 0 && l1 < j) + (l2 >= 0 && l2 < j);
-            const int kP = 2 - pab - max(rp, rl);
-            const int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
-            const int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
-            w[j >> 2] |= (uint32_t)(((nP + pab) | ((nL + lab) << 2) | (nbP << 4) | (nbL << 6)) & 0xff) << (8 * (j & 3));
+            for (int k = 0; k < 4; ++k) {
+                const int j = 4 * q + k;
+                const uint32_t cb = (pw >> (8 * k)) & 0xffu;
+                const int nP = cb & 3, nL = (cb >> 2) & 3, bP = (cb >> 4) & 3, bL = (cb >> 6) & 3;
+                const int pab = (j == p1) + (j == p2), lab = (j == l1) + (j == l2);
+                const int rp = (p1 >= 0 && p1 < j) + (p2 >= 0 && p2 < j);
+                const int rl = (l1 >= 0 && l1 < j) + (l2 >= 0 && l2 < j);
+                const int kP = 2 - pab - max(rp, rl);
+                const int kL = 2 - max(lab + rl, max(pab + rl, pab + rp));
+                const int nbP = min(bP - pab, kP), nbL = min(bL - lab, kL);
+                const uint32_t nb = (uint32_t)(((nP + pab) | ((nL + lab) << 2) | (nbP << 4) | (nbL << 6)) & 0xff);
+                if (j > a && j < n) wq |= nb << (8 * k);
+            }
         }
+        ccol[q] = wq;
     }
-    uint8_t *ccol = crec + offsetof(NodeHdr, col);
-    reinterpret_cast<uint4 *>(ccol)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    reinterpret_cast<uint4 *>(ccol)[1] = make_uint4(w[4], w[5], w[6], w[7]);
     const uint32_t tm = S.tmask[slot];
     int hits = 0;
     if (tm) hits = (p1 >= 0 && ((tm >> p1) & 1)) + (p2 >= 0 && ((tm >> p2) & 1)) +
@@ -314,50 +321,35 @@ k_expand(LevelArgs A_param)
             // beam_delta, or by half of what is left up to the current limit if that is more
             if (A.beam_delta >= 0) slack = min(slack, hd.y - hd.x + max(A.beam_delta, (A.limit[hd.z] - hd.y) >> A.beam_shift));
         }
+        // masks of all columns at once, 4 column bytes per word (bytes of closed columns and beyond the partition are
+        // zero): a byte-wise "at least" test leaves bit 7 of each byte, one multiply gathers the four bits
         uint32_t okP = 0, parP = 0, okL1 = 0, okL2 = 0, par1 = 0, par2 = 0;
-        int covC = 0, fbC = 0;
+        int covC = 0;
 #pragma unroll
-        for (int j = 0; j < NMAX; ++j) {
-            if (j >= a) {
-                const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;       // zero beyond the record's partition
-                const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
-                const bool inpart = j < my_n;
-                const bool root = (a == 0 && j == my_n - 1);
-                covC += nP + 2 * nL;
-                if (j == a) fbC = nP + 2 * nL;
-                okP |= (uint32_t)(inpart && bP >= 1) << j;
-                parP |= (uint32_t)(inpart && (nP >= 1 || root)) << j;
-                okL1 |= (uint32_t)(inpart && bL >= 1 && lmax >= 1) << j;
-                okL2 |= (uint32_t)(inpart && bL >= 2 && lmax >= 2) << j;
-                par1 |= (uint32_t)(inpart && (nP + nL >= 1 || root)) << j;
-                par2 |= (uint32_t)(inpart && (nP + nL >= 2 || root)) << j;
-            }
+        for (int q = 0; q < NMAX / 4; ++q) {
+            const uint32_t x = w[q];
+            const uint32_t vP = x & 0x03030303u, vL = (x >> 2) & 0x03030303u;
+            const uint32_t g_okP = ((x & 0x30303030u) + 0x7f7f7f7fu) & 0x80808080u;          // bP >= 1
+            const uint32_t g_parP = (vP + 0x7f7f7f7fu) & 0x80808080u;                          // nP >= 1
+            const uint32_t g_okL1 = (((x >> 6) & 0x03030303u) + 0x7f7f7f7fu) & 0x80808080u;    // bL >= 1
+            const uint32_t g_okL2 = (x & 0x80808080u);                                          // bL >= 2
+            const uint32_t g_par1 = ((vP + vL) + 0x7f7f7f7fu) & 0x80808080u;                   // nP + nL >= 1
+            const uint32_t g_par2 = ((vP + vL) + 0x7e7e7e7eu) & 0x80808080u;                   // nP + nL >= 2
+            okP |= ((g_okP * 0x00204081u) >> 28) << (4 * q);
+            parP |= ((g_parP * 0x00204081u) >> 28) << (4 * q);
+            okL1 |= ((g_okL1 * 0x00204081u) >> 28) << (4 * q);
+            okL2 |= ((g_okL2 * 0x00204081u) >> 28) << (4 * q);
+            par1 |= ((g_par1 * 0x00204081u) >> 28) << (4 * q);
+            par2 |= ((g_par2 * 0x00204081u) >> 28) << (4 * q);
+            covC += (int)(((vP + 2 * vL) * 0x01010101u) >> 24);                                // committed coverage of segment a
         }
-        // The record's own bound on segments > a (what its parent level charged for them): every child's
-        // bound on those segments is at least this (coverage only grows, budgets only shrink), so
-        // err + pf > slack cuts a configuration before the O(n) bound is evaluated for it.
-        int pf = 0;
-        uint32_t cja = 0;
-        if (have && slack >= 0 && my_n > a) {
-            cja = __ldg(&P->cj[a]);
-            int cov = 0, capsum = 0;
-#pragma unroll
-            for (int j = NMAX - 1; j >= 1; --j) {
-                if (j > a && j < my_n) {
-                    const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    const uint32_t cjw = __ldg(&P->cj[j]);
-                    const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
-                    const int cap = min(bP, 2) + 2 * min(bL, 2);
-                    const int wn = nP + 2 * nL;
-                    cov += wn; capsum += cap;
-                    const int fmax = min(6 * (j - a + 1), capsum);
-                    const int d = 2 * cov - (int)(cjw & 0xffff);
-                    pf += d > 0 ? d : max(0, -d - 2 * fmax);
-                    const int f = wn - (int)(cjw >> 16);
-                    pf += f > 0 ? f : max(0, -f - (cap + min(capsum, 6)));
-                }
-            }
-        }
+        if (a == 0 && my_n > 0) { const uint32_t rb = 1u << (my_n - 1); parP |= rb; par1 |= rb; par2 |= rb; }   // the root pair needs no parent
+        if (lmax < 1) okL1 = 0;
+        if (lmax < 2) okL2 = 0;
+        const uint32_t wa = (a >> 2) == 0 ? w[0] : ((a >> 2) == 1 ? w[1] : ((a >> 2) == 2 ? w[2] : ((a >> 2) == 3 ? w[3] :
+                            ((a >> 2) == 4 ? w[4] : ((a >> 2) == 5 ? w[5] : ((a >> 2) == 6 ? w[6] : w[7]))))));
+        const uint32_t ba = (wa >> (8 * (a & 3))) & 0xffu;
+        const int fbC = (int)(ba & 3) + 2 * (int)((ba >> 2) & 3);
         uint32_t total = 0, nl0 = 0;
         if (have && my_n > a && slack >= 0) total = dec::count_configs(okP, parP, okL1, okL2, par1, par2, &nl0);
         const uint32_t nzm = __ballot_sync(0xffffffffu, total > 0);
@@ -374,7 +366,26 @@ k_expand(LevelArgs A_param)
         if (total > 0) {
             dec::write_lists(S, slot, okP, parP, okL1, okL2, par1, par2, nl0);
 #pragma unroll
-            for (int j = 0; j < NMAX; ++j) if (j >= a && j < jtop) S.colb[j][slot] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+            for (int q = 0; q < NMAX / 4; ++q) S.colw[q][slot] = w[q];
+            // The record's own bound on segments > a (what its parent level charged for them): every child's
+            // bound on those segments is at least this (coverage only grows, budgets only shrink), so
+            // err + pf > slack cuts a configuration before the O(n) bound is evaluated for it.
+            int pf = 0, cov = 0, capsum = 0;
+            const uint32_t cja = __ldg(&P->cj[a]);
+#pragma unroll 1
+            for (int j = my_n - 1; j > a; --j) {
+                const uint32_t b = S.colb(j, slot);
+                const uint32_t cjw = __ldg(&P->cj[j]);
+                const int nP = b & 3, nL = (b >> 2) & 3, bP = (b >> 4) & 3, bL = (b >> 6) & 3;
+                const int cap = min(bP, 2) + 2 * min(bL, 2);
+                const int wn = nP + 2 * nL;
+                cov += wn; capsum += cap;
+                const int fmax = min(6 * (j - a + 1), capsum);
+                const int d = 2 * cov - (int)(cjw & 0xffff);
+                pf += d > 0 ? d : max(0, -d - 2 * fmax);
+                const int f = wn - (int)(cjw >> 16);
+                pf += f > 0 ? f : max(0, -f - (cap + min(capsum, 6)));
+            }
             S.pidx[slot] = pidx; S.score[slot] = hd.x; S.prob[slot] = hd.z; S.ptgs[slot] = hd.w;
             S.slack[slot] = slack; S.lslack[slot] = slack - pf; S.n[slot] = (uint8_t)my_n;
             S.d0[slot] = 2 * covC - (int)(cja & 0xffffu); S.f0[slot] = fbC - (int)(cja >> 16);

@@ -70,6 +70,8 @@ void small_launch(const SmallConfig &cfg, const SmallLaunch &L, cudaStream_t st)
     P.fb_list = nullptr; P.fb_count = L.fb_count; P.active = L.active; P.arena = L.arena; P.stamps = L.stamps;
     P.C = cfg.C; P.tsize = cfg.tsize; P.beam_width = L.beam_width; P.beam_growth = L.beam_growth;
     P.beam_delta = L.beam_delta; P.beam_shift = L.beam_shift;
+    // several contexts of one process may size the kernel differently: (re)state the limit this launch needs
+    cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
     k_solve_small<<<cfg.blocks, cfg.warps_per_block * 32, cfg.smem_bytes, st>>>(P);
 }
 

@@ -179,6 +179,53 @@ def workload_problems(name: str, count: int, rank: int, world: int):
     raise SystemExit(f"unknown workload {name}")
 
 
+def prefix_sharded_record(local: int, rank: int, world: int, dist):
+    """north_star's multi-GPU mode for ONE partition at a time (BASELINE configs 3 and 4): every rank searches the
+    prefixes hashed to it, incumbents and pruning limits are exchanged over NCCL, the shard optima are all-gathered
+    (ambi_bfb_solve with a communicator).  Strong scaling: the same partitions at every N; timed on the host around
+    the collective C-ABI calls, max over ranks."""
+    import torch
+    from ambigram_b200 import capi
+    ctx = capi.Context(device=local, rank=rank, world=world)
+    if world > 1:
+        uid = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(uid[0])
+    out = {}
+    for name, count in (("n30", 8), ("n20j", 16)):
+        probs, _ = workload_problems(name, count, 0, 1)
+        for p in probs[:2]:
+            ctx.solve(p)                                   # warm-up (graph capture, pools)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        per_lh, cands, t_best = [], 0, []
+        t00 = time.perf_counter()
+        for p in probs:
+            t0 = time.perf_counter()
+            s = ctx.solve(p)
+            per_lh.append(time.perf_counter() - t0)
+            cands += int(s.candidates_scored)
+            t_best.append(float(s.seconds_to_best))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t00
+        t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+        ranks = [torch.zeros_like(t) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(ranks, t)
+        else:
+            ranks = [t]
+        prof = ctx.profile()
+        out[name] = {"partitions": len(probs), "ms_total": 1e3 * max(float(r[0]) for r in ranks), "ms_per_lh": 1e3 * max(float(r[0]) for r in ranks) / len(probs),
+                     "per_rank_ms": [round(1e3 * float(r[0]), 3) for r in ranks], "candidates": cands,
+                     "candidates_per_s": cands / max(float(r[0]) for r in ranks), "slowest_lh_ms": 1e3 * max(per_lh),
+                     "time_to_best_ms_median": 1e3 * statistics.median(t_best), "exchange_rounds": prof["exchange_rounds"], "chunked_runs": prof["chunked_runs"]}
+    out["what"] = ("BASELINE config 4 (n=30 / 8 folds, CN noise, seeds 0..7) and config 3 (n=20 / 6 folds with .juncs, seeds 0..15), one "
+                   "partition at a time through ambi_bfb_solve; prefix-sharded x%d over NCCL; strong scaling; host wall clock, max over ranks" % world)
+    ctx.close()
+    return out
+
+
 def run_workload(args):
     import torch
     import torch.distributed as dist
@@ -335,7 +382,12 @@ def main():
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = ctx.launch_count() - launches0
     sols = batch.fetch()
-    t_best = statistics.mean(s.seconds_to_best for s in sols)
+    tb = sorted(s.seconds_to_best for s in sols); tp = sorted(s.seconds for s in sols)
+    pct = lambda v, q: v[min(len(v) - 1, int(q * len(v)))]
+    time_to_best = {"unit": "ms since the search of the batch was enqueued (device %globaltimer, per .lh)",
+                    "best_p50": 1e3 * pct(tb, 0.5), "best_p99": 1e3 * pct(tb, 0.99), "best_max": 1e3 * tb[-1],
+                    "proof_p50": 1e3 * pct(tp, 0.5), "proof_p99": 1e3 * pct(tp, 0.99), "proof_max": 1e3 * tp[-1]}
+    t_best = statistics.mean(tb)
 
     # ---- Stage B on the same batch (first valid topological order per partition) and single-.lh latency
     dags = [capi.construct_dag(p.n, p.start_id, s.element_cn) for p, s in zip(problems, sols)]
@@ -353,9 +405,11 @@ def main():
     for _ in range(3):
         ctx.solve(one)
     t0 = time.perf_counter()
+    single_best = []
     for _ in range(20):
-        ctx.solve(one)
+        single_best.append(ctx.solve(one).seconds_to_best)
     single_ms = (time.perf_counter() - t0) / 20 * 1e3
+    time_to_best["single_lh_best_ms"] = 1e3 * statistics.median(single_best)
     batch.free()
     batch = ctx.upload(problems)
 
@@ -381,6 +435,11 @@ def main():
     e2e_sols = pk.solutions()
     clocks = sampler.stop() if sampler else None
     e2e_cand = sum(s.candidates_scored for s in e2e_sols)
+
+    # ---- north_star's multi-GPU split (one partition at a time, prefix-sharded over NCCL): configs 4 and 3
+    sharded = None
+    if not os.environ.get("AMBI_BENCH_NO_SHARDED"):
+        sharded = prefix_sharded_record(local, rank, world, dist)
 
     if os.environ.get("AMBI_BENCH_DEBUG"):
         print(f"[rank {rank}] dev_ms/step {dev_ms / args.steps:.3f} e2e_ms/step {1e3 * e2e_s / args.steps:.3f} cand/step {cand_per_step}", file=sys.stderr)
@@ -431,7 +490,8 @@ def main():
                         "h2d_bytes_per_step": args.batch * 416 * world, "d2h_bytes_per_step": args.batch * 156 * world},
                 "gpu_launches": launches_all,
                 "candidates_per_step": cand_all, "records_expanded_per_step": nodes_per_step, "problems_per_s": args.batch * world / (ms_per_step * 1e-3),
-                "time_to_best_ms_per_lh": 1e3 * t_best, "single_lh_solve_ms": single_ms, "stage_b": stage_b,
+                "time_to_best_ms_per_lh": 1e3 * t_best, "time_to_best": time_to_best, "single_lh_solve_ms": single_ms, "stage_b": stage_b,
+                "prefix_sharded": sharded,
                 "roofline": roof, "roofline_int32": roof_int, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(problems)
