@@ -39,7 +39,7 @@ class _Problem(C.Structure):
     _fields_ = [("n", C.c_int32), ("start_id", C.c_int32), ("seg_cn2", C.POINTER(C.c_int32)),
                 ("fbi_cn2", C.POINTER(C.c_int32)), ("loop_ub", C.c_int32), ("bias", C.c_int32),
                 ("n_tgs", C.c_int32), ("tgs_pairs", C.POINTER(C.c_int32)), ("flags", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("unit_shift", C.c_uint32)]
 
 
 class _Solution(C.Structure):
@@ -159,8 +159,7 @@ class Problem:
     bias: int = 1
     tgs_pairs: Sequence[int] = ()
     junc_info: bool = False
-    unit: int = 1          # seg_cn2 / fbi_cn2 are 2*unit*copies; only unit 1 is accepted by the library today
-                           # (lh.flatten(unit=...) and the oracle's *_units entry points are the next round's groundwork)
+    unit: int = 1          # seg_cn2 / fbi_cn2 are 2*unit*copies (unit a power of two <= 64 -> ambi_bfb_problem.unit_shift)
 
     def effective_loop_ub(self) -> int:
         return int(self.loop_ub) if self.loop_ub is not None else int(sum(self.seg_cn2) // (2 * self.unit))
@@ -202,8 +201,9 @@ class _Packed:
         self.sol = (_Solution * self.count)()
         self.x = []
         for i, p in enumerate(problems):
-            if getattr(p, "unit", 1) != 1:
-                raise AmbiError(-6, f"problem {i}: the CUDA path takes half-integral copy numbers only (unit = 1)")
+            unit = int(getattr(p, "unit", 1))
+            if unit < 1 or unit > 64 or unit & (unit - 1):
+                raise AmbiError(-6, f"problem {i}: unit must be a power of two <= 64 (copy numbers in units of 1/(2*unit) copies)")
             c2 = np.ascontiguousarray(p.seg_cn2, dtype=np.int32)
             j2 = np.ascontiguousarray(p.fbi_cn2, dtype=np.int32)
             tg = np.ascontiguousarray(p.tgs_pairs if len(p.tgs_pairs) else [0, 0], dtype=np.int32)
@@ -220,6 +220,7 @@ class _Packed:
             q.n_tgs = len(p.tgs_pairs) // 2
             q.tgs_pairs = tg.ctypes.data_as(C.POINTER(C.c_int32))
             q.flags = 1 if p.junc_info else 0
+            q.unit_shift = unit.bit_length() - 1
             x = np.zeros(num_vars(p.n), dtype=np.int32)
             self.x.append(x)
             self.sol[i].element_cn = x.ctypes.data_as(C.POINTER(C.c_int32))

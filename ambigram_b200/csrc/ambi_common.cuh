@@ -51,7 +51,8 @@ struct DevProblem {
     int32_t zero_score;      // score2 of the all-zero assignment = sum(c2)+sum(j2)
     int32_t has_tgs;
     int32_t root_lb;         // admissible bound of the empty prefix (host, same formula as child_bound)
-    int32_t pad[2];
+    int32_t ush;             // copy numbers in units of 1/(2 << ush) copies (ambi_bfb_problem.unit_shift)
+    int32_t pad;
     int32_t c2[AMBI_MAXN];
     int32_t j2[AMBI_MAXN];
     uint32_t cj[AMBI_MAXN];         // c2 | j2<<16 (both < 65536), what k_expand stages in shared memory

@@ -66,6 +66,7 @@ struct ambi_ctx {
 struct ambi_batch {
     int count = 0;
     std::vector<int32_t> n, bias;
+    std::vector<int8_t> ush;
     bool ran = false;
 };
 
@@ -239,7 +240,7 @@ extern "C" int ambi_batch_upload(ambi_ctx *ctx, int32_t count, const ambi_bfb_pr
     DevProblem *stage = ctx->sa.staging(count);
     if (!stage) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
     ambi_batch *b = new ambi_batch();
-    b->count = count; b->n.resize(count); b->bias.resize(count);
+    b->count = count; b->n.resize(count); b->bias.resize(count); b->ush.resize(count);
     std::atomic<int> bad_rc{0}, bad_i{-1};
     std::string bad_why;
     parallel_for(count, [&](int lo, int hi) {
@@ -247,7 +248,7 @@ extern "C" int ambi_batch_upload(ambi_ctx *ctx, int32_t count, const ambi_bfb_pr
             std::string why;
             int rc = to_dev(problems[i], stage[i], why);
             if (rc) { int expect = 0; if (bad_rc.compare_exchange_strong(expect, rc)) { bad_i = i; bad_why = why; } return; }
-            b->n[i] = problems[i].n; b->bias[i] = problems[i].bias;
+            b->n[i] = problems[i].n; b->bias[i] = problems[i].bias; b->ush[i] = (int8_t)problems[i].unit_shift;
         }
     });
     if (bad_rc) { delete b; return fail(ctx, bad_rc, "problem " + std::to_string(bad_i.load()) + ": " + bad_why); }
@@ -282,7 +283,7 @@ static int fetch_into(ambi_ctx *ctx, ambi_batch *b, ambi_bfb_solution *sol, bool
             s.status = F.overflow ? AMBI_ERR_FRONTIER_OVERFLOW : (sc == 0x7fffffff ? AMBI_ERR_CUDA : AMBI_OK);
             if (shard && s.status == AMBI_ERR_CUDA) s.status = AMBI_OK;      // this shard saw no completed assignment
             s.score2 = sc;
-            s.objective2 = sc - 2ll * b->bias[i];
+            s.objective2 = sc - ((2ll * b->bias[i]) << b->ush[i]);
             s.candidates_scored = F.cand[i]; s.nodes_expanded = F.node[i];
             s.incumbent_score2 = F.incumbent[i];
             s.seconds = F.t_proof[i]; s.seconds_to_best = F.t_best[i];
@@ -423,7 +424,7 @@ extern "C" int ambi_bfb_solve(ambi_ctx *ctx, const ambi_bfb_problem *problem, am
     }
     const uint32_t *bq = &all[(size_t)best * 40];
     solution->score2 = (int32_t)bq[0];
-    solution->objective2 = solution->score2 - 2ll * problem->bias;
+    solution->objective2 = solution->score2 - ((2ll * problem->bias) << problem->unit_shift);
     solution->candidates_scored = cands; solution->nodes_expanded = nodes;
     solution->incumbent_score2 = local.incumbent_score2;
     solution->seconds = local.seconds; solution->seconds_to_best = local.seconds_to_best;

@@ -84,8 +84,9 @@ __device__ __forceinline__ void write_lists(SH &S, int slot, uint32_t okP, uint3
 // row, third-generation row `tm` with the record's running count, exact deviation of segment a through the
 // record's d0 = 2 cov_a - 2c_a and f0 = fb_a - 2J_a, and the O(1) prefilter lslack = slack - own bound).
 // Returns slot << 24 | cfg, or 0 when structurally infeasible; *pass = within the limit.
+// `ush`: copy numbers are in units of 1/(2 << ush) copies (0 in the half-copy instantiations: the shifts fold away).
 template <class SH>
-__device__ __forceinline__ uint32_t decode_light(const SH &S, int slot, uint32_t r, uint32_t tm, bool *pass)
+__device__ __forceinline__ uint32_t decode_light(const SH &S, int slot, uint32_t r, uint32_t tm, int ush, bool *pass)
 {
     const uint32_t okP = S.okP[slot], okL1 = S.okL1[slot], par1 = S.par1[slot];
     const uint32_t nl0 = S.nl0[slot];
@@ -144,7 +145,7 @@ __device__ __forceinline__ uint32_t decode_light(const SH &S, int slot, uint32_t
     }
     if (!feas) { *pass = false; return 0u; }
     const int w = (p1 >= 0) + (p2 >= 0) + 2 * nl;
-    const int err = abs(S.d0[slot] + 2 * w) + abs(S.f0[slot] + w);
+    const int err = abs(S.d0[slot] + (w << (ush + 1))) + abs(S.f0[slot] + (w << ush));
     *pass = err <= S.lslack[slot];
     return ((uint32_t)slot << 24) | pack_cfg(p1, p2, l1, l2);
 }

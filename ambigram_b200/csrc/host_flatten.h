@@ -17,7 +17,9 @@ inline int to_dev(const ambi_bfb_problem &p, DevProblem &d, std::string &why)
     if (p.n < 1) { why = "n < 1"; return AMBI_ERR_BAD_ARG; }
     if (p.n > AMBI_MAX_SEGMENTS) { why = "n > AMBI_MAX_SEGMENTS"; return AMBI_ERR_TOO_LARGE; }
     if (!p.seg_cn2 || !p.fbi_cn2) { why = "null copy-number arrays"; return AMBI_ERR_BAD_ARG; }
-    d.n = p.n;
+    if (p.unit_shift > 6) { why = "unit_shift > 6"; return AMBI_ERR_NOT_HALF_INTEGRAL; }
+    const int ush = (int)p.unit_shift;
+    d.n = p.n; d.ush = ush;
     d.loop_ub = p.loop_ub < 0 ? 0 : p.loop_ub;
     d.lmax = d.loop_ub < 2 ? d.loop_ub : 2;
     long long z = 0;
@@ -35,8 +37,8 @@ inline int to_dev(const ambi_bfb_problem &p, DevProblem &d, std::string &why)
         long long lb = 0;
         for (int j = 0; j < p.n; ++j) {
             int fmax = std::min(6 * (j + 1), 6 * (p.n - j));
-            lb += std::max(0, p.seg_cn2[j] - 2 * fmax);
-            lb += std::max(0, p.fbi_cn2[j] - (6 + std::min(6 * (p.n - j), 6)));
+            lb += std::max(0, p.seg_cn2[j] - ((2 * fmax) << ush));
+            lb += std::max(0, p.fbi_cn2[j] - ((6 + std::min(6 * (p.n - j), 6)) << ush));
         }
         d.root_lb = (int32_t)std::min<long long>(lb, z);
     }

@@ -378,7 +378,7 @@ __device__ __noinline__ void expand_level(Fixed &S, const Arr &R, int C, uint32_
             uint32_t entry = 0;
             if (c < T) {
                 const int slot = (int)(s0 + __popc(bm & lt_mask));
-                entry = dec::decode_light(S, slot, c - S.cstart[slot], S.tmask_row, &pass);
+                entry = dec::decode_light(S, slot, c - S.cstart[slot], S.tmask_row, 0, &pass);
             }
             n_infeas += __popc(__ballot_sync(0xffffffffu, c < T && !entry));
             s0 += __popc(bm);

@@ -91,6 +91,7 @@ struct GroupShared {
     uint32_t nl0[GRP];                  // loop multisets whose parents already exist (class 0)
     uint32_t cstart[GRP + 1];           // exclusive prefix of candidate counts
     uint8_t  n[GRP];
+    uint8_t  ush[GRP];                  // copy-number unit of the record's partition (SCALED instantiations only)
     uint32_t cnt[GRP];                  // structurally infeasible configurations per record (not scored)
     const uint32_t *cjp[GRP];           // 2c_j | 2J_j << 16 of the record's partition (DevProblem::cj)
     unsigned long long best[GRP];       // EMIT_BEST: min (tot<<32 | cfg-order key)
@@ -111,10 +112,13 @@ __device__ __forceinline__ uint32_t cfg_code(int n, int p1, int p2, int l1, int 
 // Mirrors oracle/ambi_oracle.c future_bound(): committed coverage / fold-back can only grow; what
 // can still be added is capped by the column budgets and by 6 per remaining row.
 // All lanes walk the same columns (jtop-1 .. a+1) so the shared-memory reads stay conflict free.
-template <int NMAX>
+// SCALED: copy numbers in units of 1/(2U) copies, U = 1 << ush per partition: counts of copies become counts of units
+// where they meet 2c / 2J (the half-copy instantiation is unchanged: ush is the constant 0 there).
+template <int NMAX, bool SCALED>
 __device__ __forceinline__ int child_bound(const GroupShared<NMAX> &S, int slot, int jtop, int a,
                                            int p1, int p2, int l1, int l2, int budget, bool active)
 {
+    const int ush = SCALED ? (int)S.ush[slot] : 0;
     int lb = 0, cov = 0, capsum = 0;
     // ends as bit masks aligned so that column jtop-1 sits in bit 31; the walk shifts them left
     // (pattern ends are distinct columns; a loop column may hold two ends: lm2 = the doubled one)
@@ -145,11 +149,11 @@ __device__ __forceinline__ int child_bound(const GroupShared<NMAX> &S, int slot,
         cov += wn; capsum += cap;
         const int fmax = min(six, capsum);
         six -= 6;
-        const int d = 2 * cov - c2;
-        lb += max(max(d, -d - 2 * fmax), 0);
+        const int d = (cov << (ush + 1)) - c2;
+        lb += max(max(d, -d - (fmax << (ush + 1))), 0);
         const int gmax = cap + min(capsum, 6);
-        const int f = wn - j2;
-        lb += max(max(f, -f - gmax), 0);
+        const int f = (wn << ush) - j2;
+        lb += max(max(f, -f - (gmax << ush)), 0);
         if ((j & 3) == 0 && __ballot_sync(0xffffffffu, active && lb <= budget) == 0) break;
     }
     return lb;
@@ -157,7 +161,7 @@ __device__ __forceinline__ int child_bound(const GroupShared<NMAX> &S, int slot,
 
 // One batch of light-test survivors through the O(n) bound; survivors are queued for the write
 // (EMIT_ALL) or folded into the per-record arg-min (EMIT_BEST).  Returns the new write-queue fill.
-template <int NMAX>
+template <int NMAX, bool SCALED>
 __device__ __noinline__ int heavy_batch(GroupShared<NMAX> &S, const LevelArgs &A, int count, int jtop, int qw)
 {
     const int lane = lane_id();
@@ -172,9 +176,10 @@ __device__ __noinline__ int heavy_batch(GroupShared<NMAX> &S, const LevelArgs &A
     const int slack = S.slack[slot];
     if (act) {
         const int w = (p1 >= 0) + (p2 >= 0) + 2 * ((l1 >= 0) + (l2 >= 0));
-        err = abs(S.d0[slot] + 2 * w) + abs(S.f0[slot] + w);
+        const int ush = SCALED ? (int)S.ush[slot] : 0;
+        err = abs(S.d0[slot] + (w << (ush + 1))) + abs(S.f0[slot] + (w << ush));
     }
-    const int lb = child_bound<NMAX>(S, slot, jtop, a, p1, p2, l1, l2, slack - err, act);
+    const int lb = child_bound<NMAX, SCALED>(S, slot, jtop, a, p1, p2, l1, l2, slack - err, act);
     if (act) { tot = err + lb; keep = tot <= slack; }
     if (A.emit == EMIT_BEST) {
         if (keep) atomicMin(&S.best[slot], ((unsigned long long)(uint32_t)tot << 32) | cfg_code(S.n[slot], p1, p2, l1, l2));
@@ -266,7 +271,7 @@ __device__ __noinline__ void write_batch(GroupShared<NMAX> &S, const LevelArgs &
     }
 }
 
-template <int NMAX>
+template <int NMAX, bool SCALED>
 __global__ void __launch_bounds__(WPB * 32, NMAX <= 16 ? 4 : 3)
 k_expand(LevelArgs A_param)
 {
@@ -371,6 +376,7 @@ k_expand(LevelArgs A_param)
             // bound on those segments is at least this (coverage only grows, budgets only shrink), so
             // err + pf > slack cuts a configuration before the O(n) bound is evaluated for it.
             int pf = 0, cov = 0, capsum = 0;
+            const int ush = SCALED ? P->ush : 0;
             const uint32_t cja = __ldg(&P->cj[a]);
 #pragma unroll 1
             for (int j = my_n - 1; j > a; --j) {
@@ -381,14 +387,15 @@ k_expand(LevelArgs A_param)
                 const int wn = nP + 2 * nL;
                 cov += wn; capsum += cap;
                 const int fmax = min(6 * (j - a + 1), capsum);
-                const int d = 2 * cov - (int)(cjw & 0xffff);
-                pf += d > 0 ? d : max(0, -d - 2 * fmax);
-                const int f = wn - (int)(cjw >> 16);
-                pf += f > 0 ? f : max(0, -f - (cap + min(capsum, 6)));
+                const int d = (cov << (ush + 1)) - (int)(cjw & 0xffff);
+                pf += d > 0 ? d : max(0, -d - (fmax << (ush + 1)));
+                const int f = (wn << ush) - (int)(cjw >> 16);
+                pf += f > 0 ? f : max(0, -f - ((cap + min(capsum, 6)) << ush));
             }
+            S.ush[slot] = (uint8_t)ush;
             S.pidx[slot] = pidx; S.score[slot] = hd.x; S.prob[slot] = hd.z; S.ptgs[slot] = hd.w;
             S.slack[slot] = slack; S.lslack[slot] = slack - pf; S.n[slot] = (uint8_t)my_n;
-            S.d0[slot] = 2 * covC - (int)(cja & 0xffffu); S.f0[slot] = fbC - (int)(cja >> 16);
+            S.d0[slot] = (covC << (ush + 1)) - (int)(cja & 0xffffu); S.f0[slot] = (fbC << ush) - (int)(cja >> 16);
             S.tmask[slot] = P->has_tgs ? P->tgs_mask[a] : 0u;
             S.cjp[slot] = P->cj;
             S.cstart[slot + 1] = incl;
@@ -420,7 +427,7 @@ k_expand(LevelArgs A_param)
             if (qh >= 32 || (cb0 >= T && qh > 0)) {
                 const int cnt = min(qh, 32);
                 n_heavy += cnt; ++n_hcalls;
-                qw = heavy_batch<NMAX>(S, A, cnt, jtop, qw);
+                qw = heavy_batch<NMAX, SCALED>(S, A, cnt, jtop, qw);
                 __syncwarp();
                 qh -= cnt;
                 const uint32_t mv = lane < qh ? S.qh[32 + lane] : 0u;
@@ -437,7 +444,7 @@ k_expand(LevelArgs A_param)
             int own = 0;
             if (c < T) {
                 own = (int)(s0 + __popc(bm & lt_mask));
-                entry = dec::decode_light(S, own, c - S.cstart[own], S.tmask[own], &pass);
+                entry = dec::decode_light(S, own, c - S.cstart[own], S.tmask[own], SCALED ? (int)S.ush[own] : 0, &pass);
             }
             // candidates scored = enumerated minus the (few) structurally infeasible ones, per record
             if (c < T && !entry) atomicAdd(&S.cnt[own], 1u);
@@ -465,7 +472,8 @@ k_expand(LevelArgs A_param)
                           l1 = n - 1 - q1; if (off > 0) l2 = (off - 1 == q1) ? l1 : n - 1 - (off - 1); }
                 const int tot = (int)(bk >> 32);
                 const int w2 = (p1 >= 0) + (p2 >= 0) + 2 * ((l1 >= 0) + (l2 >= 0));
-                const int err = abs(S.d0[lane] + 2 * w2) + abs(S.f0[lane] + w2);
+                const int ush = SCALED ? (int)S.ush[lane] : 0;
+                const int err = abs(S.d0[lane] + (w2 << (ush + 1))) + abs(S.f0[lane] + (w2 << ush));
                 const int pos = __popc(hm & lt_mask);
                 S.qw_cfg[pos] = ((uint32_t)lane << 24) | pack_cfg(p1, p2, l1, l2); S.qw_err[pos] = err; S.qw_tot[pos] = tot;
             }
@@ -755,7 +763,7 @@ __global__ void k_solve_n1(const DevProblem *probs, int count, int32_t *best_sco
     int best = 0x7fffffff, bp = 0, bl = 0;
     for (int pp = 0; pp <= 1; ++pp)
         for (int l = 0; l <= P.loop_ub; ++l) {
-            int e = abs(2 * (pp + 2 * l) - P.c2[0]) + abs(2 * l - P.j2[0]);
+            int e = abs(((pp + 2 * l) << (P.ush + 1)) - P.c2[0]) + abs((l << (P.ush + 1)) - P.j2[0]);
             if (e < best) { best = e; bp = pp; bl = l; }
         }
     best_score[p] = best;
@@ -872,12 +880,14 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     // two instantiations of the expansion kernel: staging for 16 columns (batches whose longest partition has at
     // most 16 segments; 4 blocks per SM) and for 32
     expand_smem_[0] = sizeof(GroupShared<16>) * WPB; expand_smem_[1] = sizeof(GroupShared<32>) * WPB;
-    CK(cudaFuncSetAttribute(k_expand<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[0]));
-    CK(cudaFuncSetAttribute(k_expand<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[1]));
+    CK(cudaFuncSetAttribute(k_expand<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[0]));
+    CK(cudaFuncSetAttribute(k_expand<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[1]));
+    CK(cudaFuncSetAttribute(k_expand<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[0]));
+    CK(cudaFuncSetAttribute(k_expand<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[1]));
     int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand<16>, WPB * 32, expand_smem_[0]));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand<16, true>, WPB * 32, expand_smem_[0]));
     expand_blocks_[0] = sms_ * (per_sm > 0 ? per_sm : 1);
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand<32>, WPB * 32, expand_smem_[1]));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand<32, true>, WPB * 32, expand_smem_[1]));
     expand_blocks_[1] = sms_ * (per_sm > 0 ? per_sm : 1);
     // warp-per-partition kernel for partitions of up to 16 segments (opt-in: AMBI_CFG_SMALL_KERNEL or AMBI_SMALL=1;
     // AMBI_SMALL_C: records per level and warp)
@@ -938,6 +948,10 @@ int StageA::upload(const DevProblem *host_probs, int count)
     for (int i = 0; i < count; ++i) nmax = std::max(nmax, (int)host_probs[i].n);
     if (nmax != nmax_) drop_graphs();
     nmax_ = nmax;
+    bool scaled = false;
+    for (int i = 0; i < count; ++i) scaled = scaled || host_probs[i].ush != 0;
+    if (scaled != scaled_) drop_graphs();
+    scaled_ = scaled;
     uint32_t leaf = 0;
     for (int i = 0; i < count; ++i) if (host_probs[i].n >= 2) leaf |= 1u << (host_probs[i].n - 1);
     if (leaf != leaf_levels_) drop_graphs();
@@ -952,7 +966,7 @@ int StageA::upload(const DevProblem *host_probs, int count)
         n_large_ = 0;
         for (int i = 0; i < count; ++i) {
             const int n = host_probs[i].n;
-            if (small_on_ && n >= 2 && n <= 16) lst.push_back((uint32_t)i);
+            if (small_on_ && n >= 2 && n <= 16 && host_probs[i].ush == 0) lst.push_back((uint32_t)i);
             else if (n >= 2) { act[i] = 1; ++n_large_; }
         }
         n_small_ = (int)lst.size();
@@ -967,8 +981,15 @@ int StageA::upload(const DevProblem *host_probs, int count)
 
 void StageA::launch_expand(const LevelArgs &L)
 {
-    if (nmax_ <= 16) k_expand<16><<<expand_blocks_[0], WPB * 32, expand_smem_[0], stream_>>>(L);
-    else k_expand<32><<<expand_blocks_[1], WPB * 32, expand_smem_[1], stream_>>>(L);
+    // four instantiations: 16 / 32 staged columns x copy numbers in half copies / in finer units (only when some
+    // partition of the batch asks for one: the half-copy kernels carry no scaling arithmetic)
+    if (nmax_ <= 16) {
+        if (scaled_) k_expand<16, true><<<expand_blocks_[0], WPB * 32, expand_smem_[0], stream_>>>(L);
+        else k_expand<16, false><<<expand_blocks_[0], WPB * 32, expand_smem_[0], stream_>>>(L);
+    } else {
+        if (scaled_) k_expand<32, true><<<expand_blocks_[1], WPB * 32, expand_smem_[1], stream_>>>(L);
+        else k_expand<32, false><<<expand_blocks_[1], WPB * 32, expand_smem_[1], stream_>>>(L);
+    }
     ++launches_;
 }
 

@@ -83,7 +83,7 @@ private:
     uint32_t cap_ = 0, cap_base_ = 0, cap_max_ = 0, tsize_ = 0, gen_ = 1;
     size_t buf_bytes_ = 0, pool_bytes_ = 0;
     uint8_t *pool_ = nullptr;
-    bool last_sharded_ = false, chunked_failed_ = false;
+    bool last_sharded_ = false, chunked_failed_ = false, scaled_ = false;
     unsigned long long chunked_runs_ = 0;
     int beam_shift_ = 2;
     int beam_floor_max_ = 16;     // cap of the batch-scaled beam width `16*4096/count` (measured: with the width growing

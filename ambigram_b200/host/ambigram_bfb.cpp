@@ -253,6 +253,7 @@ struct Partition {
     bool trivial = false;
     std::vector<int32_t> c2, j2, tgs, inv_src, inv_tgt;
     int32_t loop_ub = 0;
+    int unit_shift = 0;                 // copy numbers in units of 1/(2 << unit_shift) copies
     std::vector<int32_t> element_cn;
     LhGraph *graph = nullptr;
 };
@@ -294,15 +295,27 @@ static bool flatten(LhGraph &g, const std::vector<std::vector<int>> &components,
             double total = 0;
             for (const Seg &s : g.segs) total += s.cn;
             p.loop_ub = (int32_t)std::floor(total);
+            // The reference's model takes any real copy number (Weight.hpp:11, Graph.cpp:369-405).  The device searches
+            // in integers: copy numbers in units of 1/(2U) copies, U = 2^unit_shift.  Take the coarsest grid the
+            // partition's values lie on; values on no grid up to 1/128 copy (depth-derived decimals) are rounded to it.
+            std::vector<double> cs, js;
             for (int i = p.s_id; i <= p.e_id; ++i) {
                 Seg *s = g.seg(i);
                 if (!s) { why = "missing segment " + std::to_string(i); return false; }
-                double c = 2 * s->cn, jv = 2 * fbi[i];
-                if (std::fabs(c - std::round(c)) > 1e-9 || std::fabs(jv - std::round(jv)) > 1e-9 || c < 0) {
-                    why = "copy numbers are not half-integral (segment " + std::to_string(i) + ")"; return false;
-                }
-                p.c2.push_back((int32_t)std::llround(c)); p.j2.push_back((int32_t)std::llround(jv));
+                if (s->cn < 0) { why = "negative copy number (segment " + std::to_string(i) + ")"; return false; }
+                cs.push_back(s->cn); js.push_back(fbi[i]);
             }
+            int ush = 0;
+            for (; ush < 6; ++ush) {
+                const double u = (double)(2 << ush);
+                bool ok = true;
+                for (size_t k = 0; k < cs.size() && ok; ++k)
+                    ok = std::fabs(u * cs[k] - std::round(u * cs[k])) <= 1e-9 * u && std::fabs(u * js[k] - std::round(u * js[k])) <= 1e-9 * u;
+                if (ok) break;
+            }
+            p.unit_shift = ush;
+            const double u = (double)(2 << ush);
+            for (size_t k = 0; k < cs.size(); ++k) { p.c2.push_back((int32_t)std::llround(u * cs[k])); p.j2.push_back((int32_t)std::llround(u * js[k])); }
             for (const auto &c : valid) { p.tgs.push_back(std::min(c.front(), c.back())); p.tgs.push_back(std::max(c.front(), c.back())); }
             p.element_cn.assign((size_t)len * (len + 1), 0);
         }
@@ -369,6 +382,7 @@ int main(int argc, char **argv)
         probs[i].n = p.e_id - p.s_id + 1; probs[i].start_id = p.s_id; probs[i].seg_cn2 = p.c2.data(); probs[i].fbi_cn2 = p.j2.data();
         probs[i].loop_ub = p.loop_ub; probs[i].bias = p.bias; probs[i].n_tgs = (int32_t)(p.tgs.size() / 2);
         probs[i].tgs_pairs = p.tgs.empty() ? nullptr : p.tgs.data(); probs[i].flags = junc_info ? AMBI_FLAG_JUNC_INFO : 0u;
+        probs[i].unit_shift = (uint32_t)p.unit_shift;
         sols[i].element_cn = p.element_cn.data();
     }
     if (!work.empty() && ambi_bfb_solve_batch(ctx, (int32_t)work.size(), probs.data(), sols.data()) != AMBI_OK) {
@@ -392,7 +406,7 @@ int main(int argc, char **argv)
             Path path;
             if (p.trivial) { for (int i = p.s_id; i <= p.e_id; ++i) path.push_back(i); std::cout << format_path(path) << std::endl; path_len += (int)path.size(); continue; }
             ambi_order_result &r = res[wi];
-            ilp_error += sols[wi].objective2 / 2.0;
+            ilp_error += sols[wi].objective2 / (double)(2 << probs[wi].unit_shift);      // what cbc prints as "objective value"
             ++wi;
             if (print_all && r.found) {
                 // --all: every valid order in the reference's print order (LGM:3672-3695); `path` keeps the first

@@ -50,7 +50,7 @@ enum {
     AMBI_ERR_TOO_LARGE         = -3,  /* n > AMBI_MAX_SEGMENTS                 */
     AMBI_ERR_CUDA              = -4,
     AMBI_ERR_FRONTIER_OVERFLOW = -5,  /* candidate buffers exhausted           */
-    AMBI_ERR_NOT_HALF_INTEGRAL = -6,  /* 2c_i / 2J_i not integral              */
+    AMBI_ERR_NOT_HALF_INTEGRAL = -6,  /* unit_shift out of range (hosts: copy numbers not on the grid) */
     AMBI_ERR_NCCL              = -7
 };
 
@@ -93,7 +93,10 @@ typedef struct {
     int32_t n_tgs;
     const int32_t *tgs_pairs;  /* [2*n_tgs] */
     uint32_t flags;            /* bit0 = junc_info (--junc_info true)           */
-    uint32_t reserved;
+    uint32_t unit_shift;       /* copy numbers in units of 1/(2U) copies, U = 1 << unit_shift (0..6): seg_cn2[i] = 2U*c_i,
+                                  fbi_cn2[i] = 2U*J_i.  0 = half copies.  The reference's model takes any real copy number
+                                  (Weight.hpp:11, Graph.cpp:369-405); a host passes the finest grid its inputs need, or
+                                  rounds to 1/128 copy (unit_shift 6).  score2 / objective2 come back in the same unit. */
 } ambi_bfb_problem;
 
 #define AMBI_FLAG_JUNC_INFO 1u
@@ -105,8 +108,8 @@ typedef struct {
  *   cbc prints as "objective value" (localhap.cpp:199-203).                  */
 typedef struct {
     int32_t *element_cn;       /* [n(n+1)] caller-allocated                     */
-    int64_t score2;            /* 2 * sum(eps)  (integer)                       */
-    int64_t objective2;        /* score2 - 2*bias                               */
+    int64_t score2;            /* 2U * sum(eps)  (integer; U = 1 << unit_shift)  */
+    int64_t objective2;        /* score2 - 2U*bias: divide by 2U for what cbc prints as "objective value" */
     uint64_t candidates_scored;/* row configurations scored on the device      */
     uint64_t nodes_expanded;   /* partial assignments expanded                  */
     int32_t status;

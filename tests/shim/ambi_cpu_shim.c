@@ -30,10 +30,10 @@ int ambi_bfb_solve_batch(ambi_ctx *ctx, int32_t count, const ambi_bfb_problem *p
         int nt = p->n_tgs < 64 ? p->n_tgs : 64;
         for (int t = 0; t < 2 * nt; t++) tg[t] = p->tgs_pairs[t] - p->start_id;     /* the oracle takes 0-based offsets */
         orc_solve_stats st;
-        int rc = orc_solve(p->n, p->seg_cn2, p->fbi_cn2, p->loop_ub, nt, tg, (p->flags & AMBI_FLAG_JUNC_INFO) != 0, 0,
-                           solutions[i].element_cn, &st);
+        int rc = orc_solve_units(p->n, p->seg_cn2, p->fbi_cn2, 1 << p->unit_shift, p->loop_ub, nt, tg, (p->flags & AMBI_FLAG_JUNC_INFO) != 0, 0,
+                                 1, 0, -1, solutions[i].element_cn, &st);
         if (rc) { g_err = "shim: orc_solve failed"; return AMBI_ERR_CUDA; }
-        solutions[i].score2 = st.score2; solutions[i].objective2 = st.score2 - 2 * (int64_t)p->bias;
+        solutions[i].score2 = st.score2; solutions[i].objective2 = st.score2 - ((2 * (int64_t)p->bias) << p->unit_shift);
         solutions[i].candidates_scored = (uint64_t)st.candidates; solutions[i].nodes_expanded = (uint64_t)st.nodes;
         solutions[i].status = AMBI_OK; solutions[i].incumbent_score2 = (int32_t)st.score2;
         solutions[i].seconds = solutions[i].seconds_to_best = 0;

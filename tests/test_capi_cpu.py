@@ -130,11 +130,12 @@ def test_target_cn_is_the_coverage_of_the_assignment():
         assert capi.target_cn(n, x) == want
 
 
-def test_fractional_units_are_refused_by_the_library_binding():
-    """copy numbers in units other than halves exist for the oracle only: the binding must
-    not pass such a problem to the CUDA path as if it were half-integral"""
-    p = capi.Problem(n=3, seg_cn2=[8, 9, 10], fbi_cn2=[0, 4, 0], unit=4)
-    with pytest.raises(capi.AmbiError) as e:
-        capi._Packed([p])
-    assert e.value.status == -6
-    capi._Packed([capi.Problem(n=3, seg_cn2=[8, 9, 10], fbi_cn2=[0, 4, 0])])      # unit 1 marshals fine without a GPU
+def test_units_are_marshalled_as_unit_shift():
+    """copy numbers in units of 1/(2*unit) copies: the binding passes unit = 2^k as ambi_bfb_problem.unit_shift = k and
+    refuses anything that is not a power of two up to 64"""
+    pk = capi._Packed([capi.Problem(n=3, seg_cn2=[8, 9, 10], fbi_cn2=[0, 4, 0], unit=4), capi.Problem(n=3, seg_cn2=[8, 9, 10], fbi_cn2=[0, 4, 0])])
+    assert pk.arr[0].unit_shift == 2 and pk.arr[1].unit_shift == 0
+    for bad in (3, 128, 0):
+        with pytest.raises(capi.AmbiError) as e:
+            capi._Packed([capi.Problem(n=3, seg_cn2=[8, 9, 10], fbi_cn2=[0, 4, 0], unit=bad)])
+        assert e.value.status == -6

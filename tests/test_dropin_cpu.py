@@ -23,7 +23,7 @@ def load(name):
     return json.load(open(os.path.join(ROOT, "tests", "golden", name)))["cases"]
 
 
-CASES = load("cases.json") + load("cases_extra.json")
+CASES = load("cases.json") + load("cases_extra.json") + load("cases_fractional.json")
 MULTI = load("cases_multi.json")
 
 
@@ -56,8 +56,8 @@ def run_dropin(shim, case, d, extra=()):
 
 
 def usable(c):
-    # unit != 1: copy numbers that are not half-integral; k > 16: reference comparator bug
-    return c.get("unit", 1) == 1 and len(c["oracle_x_nz"]) <= 16
+    # k > 16: reference comparator bug.  Copy numbers in eighths (cases_fractional.json) are in.
+    return len(c["oracle_x_nz"]) <= 16
 
 
 @pytest.mark.parametrize("reversed_", [False, True])
@@ -65,19 +65,14 @@ def test_patched_reference_main_prints_the_reference_paths(shim, tmp_path, rever
     key = "ref_inject_paths_rev" if reversed_ else "ref_inject_paths"
     checked = 0
     for c in CASES:
-        if not usable(c) or not c[key] or not all(abs(v - round(v)) < 1e-9 for v in c["seg_cn2"] + c["fbi_cn2"]):
+        if not usable(c) or not c[key]:
             continue
         d = tmp_path / (c["name"] + ("_r" if reversed_ else ""))
         d.mkdir()
-        try:
-            got = run_dropin(shim, c, d, ["--reversed"] if reversed_ else [])
-        except AssertionError as e:
-            if "half-integral" in str(e):
-                continue                  # depth-derived copy numbers: refused by the patch until the unit lands
-            raise
+        got = run_dropin(shim, c, d, ["--reversed"] if reversed_ else [])
         assert got == c[key], c["name"]
         checked += 1
-    assert checked >= 55
+    assert checked >= 80
 
 
 def test_patched_reference_main_print_all(shim, tmp_path):
@@ -88,12 +83,7 @@ def test_patched_reference_main_print_all(shim, tmp_path):
         for rev, key in ((False, "ref_inject_paths_all"), (True, "ref_inject_paths_all_rev")):
             d = tmp_path / (c["name"] + ("_ar" if rev else "_a"))
             d.mkdir()
-            try:
-                got = run_dropin(shim, c, d, ["--all"] + (["--reversed"] if rev else []))
-            except AssertionError as e:
-                if "half-integral" in str(e):
-                    continue
-                raise
+            got = run_dropin(shim, c, d, ["--all"] + (["--reversed"] if rev else []))
             assert got == c[key], c["name"]
             checked += 1
             multi += len(got) > 1

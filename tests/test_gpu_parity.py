@@ -242,6 +242,54 @@ def test_time_to_best_and_time_to_proof_per_partition(any_ctx):
     assert len({round(s.seconds_to_best * 1e9) for s in sols}) > 1        # not one number for the whole batch
 
 
+FRACTIONAL = json.load(open(os.path.join(ROOT, "tests", "golden", "cases_fractional.json")))["cases"]
+
+
+def test_real_valued_copy_numbers_reference_fixtures(ctx):
+    """copy numbers that are not half-integral (multiples of 1/8 copy: unit 4): the reference's LP takes any real
+    right-hand side; fixtures solved by HiGHS through the reference binary (tools/make_golden.py fractional)"""
+    parts = []
+    for c in FRACTIONAL:
+        g = lh.parse_lh(c["lh"])
+        parts.append(lh.flatten(g, [], False, c["unit"])[0])
+    sols = ctx.solve_batch([pt.problem for pt in parts])
+    for c, pt, s in zip(FRACTIONAL, parts, sols):
+        p = pt.problem
+        assert s.status == 0 and s.score2 == c["oracle_score2"], c["name"]
+        assert abs(2 * c["unit"] * (c["ref_highs_objective"] + c["bias"]) - s.score2) < 1e-6, c["name"]
+        assert s.objective2 == s.score2 - 2 * c["unit"] * c["bias"]
+        assert [[int(i), int(v)] for i, v in enumerate(s.element_cn) if v] == c["oracle_x_nz"], c["name"]
+        dag = capi.construct_dag(p.n, p.start_id, s.element_cn)
+        r = ctx.first_valid_order(dag, False)
+        if dag.k <= 16 and c["ref_inject_paths"]:
+            assert r.found and capi.format_path(capi.expand_path(capi.imperfect_fbi(r.bkp, pt.inversions))) == c["ref_inject_paths"][0], c["name"]
+
+
+@pytest.mark.parametrize("unit", [2, 8, 64])
+def test_units_vs_oracle_and_scale_invariance(ctx, unit):
+    """(i) random profiles on the 1/(2*unit) grid against the oracle's *_units search, mixed with half-copy problems
+    in one batch; (ii) a half-copy problem restated in a finer unit has the same assignment and unit x the score"""
+    rng = random.Random(100 + unit)
+    probs = []
+    for s in range(24):
+        n = rng.randint(1, 14)
+        base = lh.problem_from_lh(synth.generate(max(n, 2), 3, 900 + s, 0.5).lh_text()) if n >= 2 else None
+        c2 = [max(0, (2 * unit * v // 2) + rng.randint(-unit, unit)) for v in (base.seg_cn2 if base else [rng.randint(2, 12)])]
+        j2 = [max(0, (2 * unit * v // 2) + rng.randint(0, unit // 2)) if v else 0 for v in (base.fbi_cn2 if base else [rng.randint(0, 6)])]
+        probs.append(Problem(n=len(c2), seg_cn2=c2, fbi_cn2=j2, loop_ub=rng.choice([2, 9]), unit=unit))
+        if base is not None:
+            probs.append(base)
+    sols = ctx.solve_batch(probs)
+    for p, s in zip(probs, sols):
+        check_against_oracle(p, s) if p.unit == 1 else None
+        x, st = orc.solve(p, want_unique=False)
+        assert s.score2 == st.score2 and np.array_equal(s.element_cn, x), (p, s.score2, st.score2)
+    halves = [lh.problem_from_lh(synth.generate(12, 4, 950 + s, 0.5).lh_text()) for s in range(8)]
+    fine = [Problem(n=p.n, seg_cn2=[unit * v for v in p.seg_cn2], fbi_cn2=[unit * v for v in p.fbi_cn2], loop_ub=p.effective_loop_ub(), unit=unit) for p in halves]
+    for a, b in zip(ctx.solve_batch(halves), ctx.solve_batch(fine)):
+        assert b.score2 == unit * a.score2 and np.array_equal(a.element_cn, b.element_cn)
+
+
 def test_bad_arguments(ctx):
     with pytest.raises(capi.AmbiError):
         ctx.solve(Problem(n=33, seg_cn2=[2] * 33, fbi_cn2=[0] * 33))

@@ -22,7 +22,7 @@ def load(name):
     return json.load(open(os.path.join(ROOT, "tests", "golden", name)))["cases"]
 
 
-CASES = load("cases.json") + load("cases_extra.json")
+CASES = load("cases.json") + load("cases_extra.json") + load("cases_fractional.json")
 MULTI = load("cases_multi.json")
 
 
@@ -49,7 +49,7 @@ def test_host_driver_matches_reference_stdout(shim, tmp_path, reversed_):
     key = "ref_inject_paths_rev" if reversed_ else "ref_inject_paths"
     checked = 0
     for c in CASES:
-        if c.get("unit", 1) != 1 or len(c["oracle_x_nz"]) > 16 or not c[key]:
+        if len(c["oracle_x_nz"]) > 16 or not c[key]:
             continue                      # k > 16: reference comparator bug
         d = tmp_path / (c["name"] + ("_r" if reversed_ else ""))
         d.mkdir()
@@ -64,7 +64,7 @@ def test_host_driver_matches_reference_stdout(shim, tmp_path, reversed_):
             args += ["--reversed"]
         assert run_cli(shim, args, str(d)) == c[key], c["name"]
         checked += 1
-    assert checked >= 60
+    assert checked >= 80
 
 
 def test_host_driver_multi_partition_files(shim, tmp_path):
