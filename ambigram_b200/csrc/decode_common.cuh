@@ -146,7 +146,17 @@ __device__ __forceinline__ uint32_t decode_light(const SH &S, int slot, uint32_t
     if (!feas) { *pass = false; return 0u; }
     const int w = (p1 >= 0) + (p2 >= 0) + 2 * nl;
     const int err = abs(S.d0[slot] + (w << (ush + 1))) + abs(S.f0[slot] + (w << ush));
-    *pass = err <= S.lslack[slot];
+    // O(1) prefilter.  lslack = slack - (the record's own bound on segments > a); a child's bound on those segments is
+    // never below the record's.  Sharper: on a segment whose committed coverage already reaches its copy number
+    // (over: 2 cov_j >= 2c_j), every copy this row adds costs exactly 2 more, and likewise for the fold-back count of
+    // a column that already reaches 2J_j (fover) -- both terms of the record's bound are exact there.
+    const uint32_t ov = S.over[slot], fo = S.fover[slot];
+    int extra = 0, fextra = 0;
+    if (p1 >= 0) { extra += __popc(ov & below(p1 + 1)); fextra += (fo >> p1) & 1; }
+    if (p2 >= 0) { extra += __popc(ov & below(p2 + 1)); fextra += (fo >> p2) & 1; }
+    if (l1 >= 0) { extra += 2 * __popc(ov & below(l1 + 1)); fextra += 2 * ((fo >> l1) & 1); }
+    if (l2 >= 0) { extra += 2 * __popc(ov & below(l2 + 1)); fextra += 2 * ((fo >> l2) & 1); }
+    *pass = err + (extra << (ush + 1)) + (fextra << ush) <= S.lslack[slot];
     return ((uint32_t)slot << 24) | pack_cfg(p1, p2, l1, l2);
 }
 

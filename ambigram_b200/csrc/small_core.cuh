@@ -61,6 +61,7 @@ struct Fixed {
     uint32_t okP[32], parP[32], okL1[32], A2m[32], par1[32];
     int32_t  score[32], slack[32], lslack[32], d0[32], f0[32], ptgs[32], frec[32];
     uint32_t nl0[32], cstart[33], rank[32];
+    uint32_t over[32], fover[32];      // columns j > a whose committed coverage / fold-back count already reaches 2c_j / 2J_j
     uint8_t  posP[32][MAXN_SMALL], posE[32][MAXN_SMALL];    // positions of the set bits of okP / E, lowest first
     uint16_t L0[32][L0CAP];                                 // class-0 loop multisets: low | high << 8 (0xff: none)
     uint32_t qh[64], qw_cfg[64];
@@ -189,6 +190,23 @@ __device__ __noinline__ uint32_t phase1(Fixed &S, const Arr &R, int lane)
     // the record's own bound on segments > a: every child's bound on those segments is at least this, so
     // err + pf > slack cuts a configuration before the O(n) bound is evaluated for it
     const int pf = bound_cols(S, s, a, n, 0u, 0u, 0u, n - a, 0, false, false);
+    uint32_t over = 0, fover = 0;
+#ifndef AMBI_NO_OVER
+    {
+        int cov = 0;
+#pragma unroll
+        for (int j = MAXN_SMALL - 1; j >= 1; --j) {
+            if (j < n && j > a) {
+                const uint32_t cb = colbyte(s, j);
+                const int wn = (int)(cb & 3) + 2 * (int)((cb >> 2) & 3);
+                cov += wn;
+                over |= (uint32_t)(2 * cov >= (int)(S.cj[j] & 0xffffu)) << j;
+                fover |= (uint32_t)(wn >= (int)(S.cj[j] >> 16)) << j;
+            }
+        }
+    }
+#endif
+    S.over[lane] = over; S.fover[lane] = fover;
     const uint32_t cja = S.cj[a];
     uint32_t total = 0, nl0 = 0;
     if (have && slack >= 0) total = dec::count_configs(okP, parP, okL1, okL2, par1, par2, &nl0);

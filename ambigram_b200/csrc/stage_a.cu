@@ -84,6 +84,7 @@ struct GroupShared {
     uint32_t okL1[GRP], A2m[GRP];       // column may take one loop end / two loop ends and has two parents
     uint32_t par1[GRP];                 // column already holds >= 1 parent for a loop (row 3)
     uint32_t tmask[GRP];                // third-generation cells of this row
+    uint32_t over[GRP], fover[GRP];     // columns j > a whose committed coverage / fold-back count already reaches 2c_j / 2J_j
     int32_t  score[GRP], slack[GRP], ptgs[GRP], prob[GRP];
     int32_t  d0[GRP], f0[GRP];          // 2 cov_a - 2c_a and fb_a - 2J_a before the row's own entries
     int32_t  lslack[GRP];               // slack minus the record's own bound on segments > a (light-test limit)
@@ -376,6 +377,7 @@ k_expand(LevelArgs A_param)
             // bound on those segments is at least this (coverage only grows, budgets only shrink), so
             // err + pf > slack cuts a configuration before the O(n) bound is evaluated for it.
             int pf = 0, cov = 0, capsum = 0;
+            uint32_t over = 0, fover = 0;
             const int ush = SCALED ? P->ush : 0;
             const uint32_t cja = __ldg(&P->cj[a]);
 #pragma unroll 1
@@ -391,7 +393,9 @@ k_expand(LevelArgs A_param)
                 pf += d > 0 ? d : max(0, -d - (fmax << (ush + 1)));
                 const int f = (wn << ush) - (int)(cjw >> 16);
                 pf += f > 0 ? f : max(0, -f - ((cap + min(capsum, 6)) << ush));
+                over |= (uint32_t)(d >= 0) << j; fover |= (uint32_t)(f >= 0) << j;       // the sharper prefilter of decode_light
             }
+            S.over[slot] = over; S.fover[slot] = fover;
             S.ush[slot] = (uint8_t)ush;
             S.pidx[slot] = pidx; S.score[slot] = hd.x; S.prob[slot] = hd.z; S.ptgs[slot] = hd.w;
             S.slack[slot] = slack; S.lslack[slot] = slack - pf; S.n[slot] = (uint8_t)my_n;

@@ -226,6 +226,32 @@ def prefix_sharded_record(local: int, rank: int, world: int, dist):
     return out
 
 
+def sweep_record(ctx, local: int, rank: int, world: int, dist, count: int = 2000):
+    """BASELINE config 5 (batch of samples with 10..25 segments, folds = ceil(n/3.5)), sample-sharded: a fixed set of
+    `count` samples dealt over the ranks (strong scaling), one ambi_bfb_solve_batch per rank with host buffers"""
+    import torch
+    problems, _ = workload_problems("sweep", count, rank, world)
+    pk = ctx.pack(problems)
+    ctx.solve_packed(pk)                                   # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ctx.solve_packed(pk)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sols = pk.solutions()
+    t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+    c = torch.tensor([float(sum(s.candidates_scored for s in sols)), float(len(problems))], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    secs = float(t[0])
+    return {"samples": int(c[1]), "seconds": secs, "partitions_per_s": float(c[1]) / secs, "candidates_per_s": float(c[0]) / secs,
+            "what": "BASELINE config 5 at %d samples (n ~ U{10..25}, seeds 0..%d), sample-sharded x%d, strong scaling, host buffers, "
+                    "host wall clock, max over ranks" % (count, count - 1, world)}
+
+
 def run_workload(args):
     import torch
     import torch.distributed as dist
@@ -440,6 +466,7 @@ def main():
     sharded = None
     if not os.environ.get("AMBI_BENCH_NO_SHARDED"):
         sharded = prefix_sharded_record(local, rank, world, dist)
+    sweep = None if os.environ.get("AMBI_BENCH_NO_SWEEP") else sweep_record(ctx, local, rank, world, dist)
 
     if os.environ.get("AMBI_BENCH_DEBUG"):
         print(f"[rank {rank}] dev_ms/step {dev_ms / args.steps:.3f} e2e_ms/step {1e3 * e2e_s / args.steps:.3f} cand/step {cand_per_step}", file=sys.stderr)
@@ -491,7 +518,7 @@ def main():
                 "gpu_launches": launches_all,
                 "candidates_per_step": cand_all, "records_expanded_per_step": nodes_per_step, "problems_per_s": args.batch * world / (ms_per_step * 1e-3),
                 "time_to_best_ms_per_lh": 1e3 * t_best, "time_to_best": time_to_best, "single_lh_solve_ms": single_ms, "stage_b": stage_b,
-                "prefix_sharded": sharded,
+                "prefix_sharded": sharded, "sweep": sweep,
                 "roofline": roof, "roofline_int32": roof_int, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(problems)
