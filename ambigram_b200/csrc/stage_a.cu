@@ -31,7 +31,6 @@ namespace ambi {
 constexpr int WPB = 8;              // warps per block in k_expand
 constexpr int GRP = 32;             // frontier records handled together by one warp
 constexpr int BEAM_BINS = 64;
-constexpr int CFG_NONE = 63;        // "no column" in a packed row configuration
 
 enum { EMIT_ALL = 0, EMIT_BEST = 1 };
 
@@ -40,7 +39,9 @@ struct LevelArgs {
     const uint8_t *parents;
     const uint32_t *plist;
     const uint32_t *pcount;
-    uint8_t *children;
+    uint8_t *children;              // key records of the children: header + column state (kstride bytes each)
+    uint2 *links;                   // per child: (parent's index in `parents`, row code) -- the prefix is not copied
+    int kstride;
     uint32_t *ccount;
     uint32_t cap;
     const int32_t *limit;
@@ -228,14 +229,15 @@ __device__ __noinline__ void write_batch(GroupShared<NMAX> &S, const LevelArgs &
         if (A.beam_delta < 0) atomicExch(A.overflow, (uint32_t)a + 1u);
         return;
     }
-    uint8_t *crec = A.children + (size_t)cslot * A.stride;
-    // the 32 column bytes leave one 4-column word at a time (the loop over words stays rolled: the kernel has to fit
-    // the instruction cache)
+    // A child leaves as a KEY record -- header and column state, what the merge and the beam selection look at -- plus
+    // a link word pair (parent, row code).  Four children in five lose the merge: their prefix is never copied;
+    // k_materialise builds full records (key + the parent's rows + the code) for the survivors only.
+    uint8_t *crec = A.children + (size_t)cslot * A.kstride;
     uint32_t *ccol = reinterpret_cast<uint32_t *>(crec + offsetof(NodeHdr, col));
 #pragma unroll 1
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < NMAX / 4; ++q) {
         uint32_t wq = 0;
-        if (q < NMAX / 4 && 4 * q + 3 > a && 4 * q < n) {
+        if (4 * q + 3 > a && 4 * q < n) {
             const uint32_t pw = S.colw[q][slot];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -261,15 +263,7 @@ __device__ __noinline__ void write_batch(GroupShared<NMAX> &S, const LevelArgs &
     const int sc = S.score[slot];
     // completed assignments all share one (empty) state: drop the running third-generation count
     reinterpret_cast<int4 *>(crec)[0] = make_int4(sc + err, sc + tot, S.prob[slot], (n == a + 1) ? 0 : S.ptgs[slot] + hits);
-    const uint4 *src = reinterpret_cast<const uint4 *>(prec + sizeof(NodeHdr));
-    uint4 *dst = reinterpret_cast<uint4 *>(crec + sizeof(NodeHdr));
-    const int nq = (A.nmax + 3) >> 2;
-#pragma unroll 1
-    for (int q = 0; q < nq; ++q) {
-        uint4 v = src[q];
-        if ((a >> 2) == q) { const int r = a & 3; if (r == 0) v.x = code; else if (r == 1) v.y = code; else if (r == 2) v.z = code; else v.w = code; }
-        dst[q] = v;
-    }
+    A.links[cslot] = make_uint2(S.pidx[slot], code);
 }
 
 template <int NMAX, bool SCALED>
@@ -518,6 +512,9 @@ struct DedupArgs {
     const DevProblem *probs;
     int32_t *fmin_cur;          // [prob]
     int nmax;                   // longest partition of the batch
+    const uint2 *links;         // per key record: (parent, row code)
+    const uint8_t *parents;     // full records of the previous level (prefix rows for the tie-break)
+    int pstride;
 };
 
 // beam bins: width 1 from the level's minimum f, everything beyond in the last bin (the cut for the W best
@@ -543,14 +540,20 @@ __device__ __forceinline__ bool same_state(const NodeHdr *x, const NodeHdr *y, b
     return a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
 }
 
-// strict order: lower score, then smaller prefix in search order
-__device__ __forceinline__ bool rec_better(const uint8_t *x, const uint8_t *y, int nrows) {
-    const NodeHdr *hx = reinterpret_cast<const NodeHdr *>(x), *hy = reinterpret_cast<const NodeHdr *>(y);
+// strict order: lower score, then smaller prefix in search order.  A child's prefix is its parent's rows followed by
+// its own row code; the parents are full records of the previous level (read only when the scores tie).
+__device__ __forceinline__ bool rec_better(const DedupArgs &A, uint32_t i, uint32_t o)
+{
+    const NodeHdr *hx = reinterpret_cast<const NodeHdr *>(A.recs + (size_t)i * A.stride);
+    const NodeHdr *hy = reinterpret_cast<const NodeHdr *>(A.recs + (size_t)o * A.stride);
     if (hx->score != hy->score) return hx->score < hy->score;
-    const uint32_t *rx = reinterpret_cast<const uint32_t *>(x + sizeof(NodeHdr));
-    const uint32_t *ry = reinterpret_cast<const uint32_t *>(y + sizeof(NodeHdr));
-    for (int i = 0; i < nrows; ++i) if (rx[i] != ry[i]) return rx[i] < ry[i];
-    return false;
+    const uint2 lx = A.links[i], ly = A.links[o];
+    if (lx.x != ly.x) {
+        const uint32_t *rx = reinterpret_cast<const uint32_t *>(A.parents + (size_t)lx.x * A.pstride + sizeof(NodeHdr));
+        const uint32_t *ry = reinterpret_cast<const uint32_t *>(A.parents + (size_t)ly.x * A.pstride + sizeof(NodeHdr));
+        for (int k = 0; k < A.level; ++k) if (rx[k] != ry[k]) return rx[k] < ry[k];
+    }
+    return lx.y < ly.y;
 }
 
 __global__ void k_dedup(DedupArgs A)
@@ -588,7 +591,7 @@ __global__ void k_dedup(DedupArgs A)
             uint32_t o = (uint32_t)cur;
             uint8_t *orec = A.recs + (size_t)o * A.stride;
             if (same_state(h, reinterpret_cast<const NodeHdr *>(orec), wide)) {
-                if (rec_better(rec, orec, A.level + 1)) {
+                if (rec_better(A, i, o)) {
                     unsigned long long old = atomicCAS(&A.table[slot], cur, mine);
                     if (old == cur) { hdr_kill(reinterpret_cast<NodeHdr *>(orec)); alive = true; break; }
                     continue;
@@ -624,6 +627,9 @@ struct FinalizeArgs {
     const uint32_t *overflow;
     int32_t *seen;              // [prob] best completed score seen so far in any pass ...
     unsigned long long *stamps; // ... and when (%globaltimer) it was first seen: [prob][4], word 1
+    const uint2 *links;         // the key records' (parent, row code)
+    const uint8_t *parents;     // full records of the previous level
+    int pstride;
 };
 
 __global__ void k_finalize(FinalizeArgs A)
@@ -638,7 +644,8 @@ __global__ void k_finalize(FinalizeArgs A)
         if (n == A.level + 1) {
             // all completed assignments of a problem share the empty column state, so the
             // merge above left exactly one alive: the arg-min in (score, search order)
-            const uint32_t *r = reinterpret_cast<const uint32_t *>(rec + sizeof(NodeHdr));
+            const uint2 lk = A.links[i];
+            const uint32_t *r = reinterpret_cast<const uint32_t *>(A.parents + (size_t)lk.x * A.pstride + sizeof(NodeHdr));   // rows 0..n-2; row n-1 = lk.y
             uint32_t *o = A.best_rows + (size_t)h->prob * AMBI_MAXN;
             bool take = true;
             if (A.merge_best) {     // one alive completed record per problem and launch: no race
@@ -646,18 +653,15 @@ __global__ void k_finalize(FinalizeArgs A)
                 if (old < h->score) take = false;
                 else if (old == h->score) {
                     take = false;
-                    for (int k = 0; k < n; ++k) if (r[k] != o[k]) { take = r[k] < o[k]; break; }
+                    for (int k = 0; k < n; ++k) { const uint32_t rk = k < n - 1 ? r[k] : lk.y; if (rk != o[k]) { take = rk < o[k]; break; } }
                 }
             }
             if (take) {
                 if (A.stamps && h->score < A.seen[h->prob]) { A.seen[h->prob] = h->score; A.stamps[(size_t)h->prob * 4 + 1] = globaltimer_ns(); }
                 A.best_score[h->prob] = h->score;
-                for (int k = 0; k < n; ++k) o[k] = r[k];
+                for (int k = 0; k < n; ++k) o[k] = k < n - 1 ? r[k] : lk.y;
                 if (A.limit && h->score < A.limit[h->prob]) A.limit[h->prob] = h->score;
             }
-        } else {
-            if (A.fmin) atomicMin(&A.fmin[h->prob], h->f);
-            else if (A.build_list) { uint32_t s = atomicAdd(A.next_count, 1u); A.next_list[s] = i; }
         }
     }
 }
@@ -715,20 +719,66 @@ __global__ void k_beam_cut(BeamArgs A)
     A.cutq[p] = ((uint32_t)cut << 16) | quota;
 }
 
-__global__ void k_beam_select(BeamArgs A)
+// ---------------------------------------------------------------------------
+// K3d: full records for the survivors of a level (alive after the merge, not completed, and -- in the beam pass --
+// among the W best of their problem): key + the parent's rows + the row code, appended densely to the next
+// frontier.  One warp-wide ballot per 32 key records keeps the appends at one atomic per warp.
+// ---------------------------------------------------------------------------
+struct MatArgs {
+    const DevProblem *probs;
+    const uint8_t *keys; const uint2 *links; const uint32_t *count; uint32_t cap;
+    const uint8_t *parents; int pstride;
+    uint8_t *out; uint32_t *out_count; uint32_t out_cap;
+    int kstride, level, nmax;
+    const uint32_t *overflow;
+    // beam selection (cutq != nullptr): keep below the cut bin, draw a ticket in the cut bin
+    const int32_t *fmin; const uint32_t *cutq; uint32_t *ticket;
+};
+
+__global__ void k_materialise(MatArgs A)
 {
-    uint32_t cnt = min(*A.count, A.cap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const NodeHdr *h = reinterpret_cast<const NodeHdr *>(A.recs + (size_t)i * A.stride);
-        const int prob = h->prob;
-        const DevProblem &P = A.probs[prob];
-        if (hdr_dead(h) || P.n == A.level + 1) continue;
-        const int bin = beam_bin(h->f, A.fmin[prob]);
-        const uint32_t cq = A.cutq[prob];
-        const int cut = (int)(cq >> 16);
-        bool keep = bin < cut;
-        if (bin == cut) keep = atomicAdd(&A.ticket[prob], 1u) < (cq & 0xffffu);
-        if (keep) { uint32_t s = atomicAdd(A.next_count, 1u); A.next_list[s] = i; }
+    if (*A.overflow) return;
+    const uint32_t cnt = min(*A.count, A.cap);
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int nq = (A.nmax + 3) >> 2;
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < cnt; i0 += nthreads) {
+        const uint32_t i = i0 + lane;
+        bool keep = false;
+        const NodeHdr *h = nullptr;
+        if (i < cnt) {
+            h = reinterpret_cast<const NodeHdr *>(A.keys + (size_t)i * A.kstride);
+            keep = !hdr_dead(h) && A.probs[h->prob].n != A.level + 1;
+            if (keep && A.cutq) {
+                const int bin = beam_bin(h->f, A.fmin[h->prob]);
+                const uint32_t cq = A.cutq[h->prob];
+                const int cut = (int)(cq >> 16);
+                keep = bin < cut;
+                if (bin == cut) keep = atomicAdd(&A.ticket[h->prob], 1u) < (cq & 0xffffu);
+            }
+        }
+        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        uint32_t base = 0;
+        if (lane == 0 && km) base = atomicAdd(A.out_count, (uint32_t)__popc(km));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (!keep) continue;
+        const uint32_t o = base + __popc(km & lt_mask);
+        if (o >= A.out_cap) continue;                       // cannot happen: out_cap >= cap
+        uint8_t *dst = A.out + (size_t)o * A.pstride;
+        const uint4 *ksrc = reinterpret_cast<const uint4 *>(h);
+        reinterpret_cast<uint4 *>(dst)[0] = ksrc[0];
+        reinterpret_cast<uint4 *>(dst)[1] = ksrc[1];
+        reinterpret_cast<uint4 *>(dst)[2] = A.kstride > 32 ? ksrc[2] : make_uint4(0, 0, 0, 0);
+        const uint2 lk = A.links[i];
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.parents + (size_t)lk.x * A.pstride + sizeof(NodeHdr));
+        uint4 *rd = reinterpret_cast<uint4 *>(dst + sizeof(NodeHdr));
+        const int a = A.level;
+        for (int q = 0; q < nq; ++q) {
+            uint4 v = src[q];
+            if ((a >> 2) == q) { const int r = a & 3; if (r == 0) v.x = lk.y; else if (r == 1) v.y = lk.y; else if (r == 2) v.z = lk.y; else v.w = lk.y; }
+            rd[q] = v;
+        }
     }
 }
 
@@ -814,7 +864,7 @@ StageA::~StageA() { release(); }
 
 void StageA::release()
 {
-    cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]);
+    cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]); cudaFree(kbuf_); cudaFree(lbuf_); kbuf_ = nullptr; lbuf_ = nullptr;
     cudaFree(table_); cudaFree(counters_); cudaFree(d_funnel_); cudaFree(d_flag_); cudaFree(pool_); pool_ = nullptr; d_funnel_ = nullptr; d_flag_ = nullptr;
     cudaFree(d_arena_); d_arena_ = nullptr; cudaFree(d_stamp0_); d_stamp0_ = nullptr; cudaFreeHost(h_flag_); h_flag_ = nullptr;
     for (int i = 0; i < 2; ++i) if (ev_small_[i]) { cudaEventDestroy(ev_small_[i]); ev_small_[i] = nullptr; }
@@ -867,6 +917,8 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     cap_max_ = (uint32_t)std::min<uint64_t>(2ull * cap_base_, buf_bytes_ / ambi_node_stride(2));
     CK(cudaMalloc(&buf_[0], buf_bytes_));
     CK(cudaMalloc(&buf_[1], buf_bytes_));
+    CK(cudaMalloc(&kbuf_, (size_t)cap_max_ * 48));
+    CK(cudaMalloc(&lbuf_, (size_t)cap_max_ * sizeof(uint2)));
     CK(cudaMalloc(&list_[0], (size_t)cap_max_ * 4));
     CK(cudaMalloc(&list_[1], (size_t)cap_max_ * 4));
     tsize_ = next_pow2((uint64_t)cap_max_ * 2);
@@ -961,6 +1013,7 @@ int StageA::upload(const DevProblem *host_probs, int count)
     if (leaf != leaf_levels_) drop_graphs();
     leaf_levels_ = leaf;
     stride_ = (int)ambi_node_stride(nmax_);
+    kstride_ = nmax_ <= 16 ? 32 : 48;          // key record: header + 16 or 32 column bytes
     cap_ = (uint32_t)std::min<uint64_t>(cap_max_, buf_bytes_ / stride_);
     if ((uint64_t)count > cap_) { snprintf(err_, sizeof err_, "batch of %d partitions exceeds node capacity %u", count, cap_); return -5; }
     CK(cudaMemcpyAsync(d_probs_, host_probs, (size_t)count * sizeof(DevProblem), cudaMemcpyHostToDevice, stream_));
@@ -1008,11 +1061,9 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     uint32_t *c_cur = counters_ + CTR_FRONT + level, *c_nxt = counters_ + CTR_FRONT + level + 1;
     const bool merge = mode != 0;
     LevelArgs L;
-    // level 0 and the beam pass read an index list; otherwise the previous level's children are the frontier
-    const bool listed = level == 0 || mode == 1;
-    L.probs = d_probs_; L.parents = buf_[cur]; L.plist = listed ? list_[cur] : nullptr;
-    L.pcount = listed ? c_cur : counters_ + CTR_CHILD + level - 1;
-    L.children = buf_[cur ^ 1]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
+    // the frontier of a level is a dense array of full records (k_materialise); its children are key records + links
+    L.probs = d_probs_; L.parents = buf_[cur]; L.plist = nullptr; L.pcount = c_cur;
+    L.children = kbuf_; L.links = lbuf_; L.kstride = kstride_; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
     L.cand_count = d_cand_; L.node_count = d_node_; L.funnel = d_funnel_; L.work_counter = c_work; L.overflow = c_over;
     L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = mode == 0 ? EMIT_BEST : EMIT_ALL;
     L.beam_delta = mode == 1 ? beam_delta_ : -1; L.beam_shift = beam_shift_;
@@ -1030,30 +1081,37 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     if (beam) CK(cudaMemsetAsync(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4, stream_));
     if (merge) {
         DedupArgs D;
-        D.recs = buf_[cur ^ 1]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
-        D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = stride_; D.level = level; D.overflow = c_over;
+        D.recs = kbuf_; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
+        D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = kstride_; D.level = level; D.overflow = c_over;
         D.probs = d_probs_; D.fmin_cur = beam ? fmin_cur : nullptr; D.nmax = nmax_;
+        D.links = lbuf_; D.parents = buf_[cur]; D.pstride = stride_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
     }
     FinalizeArgs F;
-    F.probs = d_probs_; F.recs = buf_[cur ^ 1]; F.count = c_child; F.cap = cap_;
-    F.next_list = list_[cur ^ 1]; F.next_count = c_nxt;
+    F.probs = d_probs_; F.recs = kbuf_; F.count = c_child; F.cap = cap_;
+    F.next_list = nullptr; F.next_count = nullptr;
     F.best_score = mode == 2 ? d_best_score_ : d_beam_score_; F.best_rows = mode == 2 ? d_best_rows_ : d_beam_rows_;
-    F.fmin = nullptr; F.stride = stride_; F.level = level;
+    F.fmin = nullptr; F.stride = kstride_; F.level = level;
     F.limit = nullptr; F.merge_best = 0; F.build_list = 0; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
+    F.links = lbuf_; F.parents = buf_[cur]; F.pstride = stride_;
     // this kernel only collects completed assignments: skip the levels where no problem ends
     if ((leaf_levels_ >> level) & 1u) { k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_; }
+    MatArgs M;
+    M.probs = d_probs_; M.keys = kbuf_; M.links = lbuf_; M.count = c_child; M.cap = cap_; M.parents = buf_[cur]; M.pstride = stride_;
+    M.out = buf_[cur ^ 1]; M.out_count = c_nxt; M.out_cap = cap_; M.kstride = kstride_; M.level = level; M.nmax = nmax_; M.overflow = c_over;
+    M.fmin = nullptr; M.cutq = nullptr; M.ticket = nullptr;
     if (beam) {
         BeamArgs B;
-        B.probs = d_probs_; B.recs = buf_[cur ^ 1]; B.count = c_child; B.cap = cap_;
+        B.probs = d_probs_; B.recs = kbuf_; B.count = c_child; B.cap = cap_;
         B.fmin = fmin_cur; B.hist = hist; B.cutq = d_cutq_ + (size_t)level * count_;
-        B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = list_[cur ^ 1];
-        B.next_count = c_nxt; B.nprob = count_; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1)));
-        B.stride = stride_; B.level = level; B.growth = beam_growth_; B.width_div = beam_div_;
+        B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = nullptr;
+        B.next_count = nullptr; B.nprob = count_; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1)));
+        B.stride = kstride_; B.level = level; B.growth = beam_growth_; B.width_div = beam_div_;
         k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
         k_beam_cut<<<(count_ + 127) / 128, 128, 0, stream_>>>(B); ++launches_;
-        k_beam_select<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
+        M.fmin = fmin_cur; M.cutq = B.cutq; M.ticket = B.ticket;          // the selection itself happens while materialising
     }
+    if (level + 1 < nmax_) { k_materialise<<<sms_ * 8, 256, 0, stream_>>>(M); ++launches_; }
     return 0;
 }
 
@@ -1236,17 +1294,6 @@ __global__ void k_iota(uint32_t *list, uint32_t start, uint32_t m, uint32_t *cou
     if (i == 0) *count = m;
 }
 
-__global__ void k_gather(const uint8_t *recs, const uint32_t *list, uint32_t m, uint8_t *dst, int stride)
-{
-    const uint32_t words = (uint32_t)stride / 16;
-    const uint64_t total = (uint64_t)m * words;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)(t / words), w = (uint32_t)(t % words);
-        reinterpret_cast<uint4 *>(dst + (size_t)r * stride)[w] =
-            reinterpret_cast<const uint4 *>(recs + (size_t)list[r] * stride)[w];
-    }
-}
-
 __global__ void k_fold_best_into_limit(int count, int32_t *limit, const int32_t *best_score)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1299,10 +1346,9 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
     std::vector<Seg> stack;
     uint32_t nroots = 0;
     if (start_level >= 1) {
-        // continue from the last level the breadth-first pass completed: its frontier (the children of level
-        // start_level-1, dropped and completed records included -- k_expand skips those) is still intact in
-        // the parent buffer of the level that overflowed; every per-problem result found so far stays valid
-        CK(cudaMemcpyAsync(&nroots, counters_ + CTR_CHILD + start_level - 1, 4, cudaMemcpyDeviceToHost, stream_));
+        // continue from the last level the breadth-first pass completed: its frontier (dense full records) is still
+        // intact in the parent buffer of the level that overflowed; every per-problem result found so far stays valid
+        CK(cudaMemcpyAsync(&nroots, counters_ + CTR_FRONT + start_level, 4, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
         nroots = std::min(nroots, cap_);
         if ((size_t)nroots * stride_ > pool_bytes_) { snprintf(err_, sizeof err_, "chunked pass: frontier pool too small"); return -5; }
@@ -1340,7 +1386,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         k_iota<<<(m + 255) / 256, 256, 0, stream_>>>(list_[0], sg.pos, m, c_par); ++launches_;
         LevelArgs L;
         L.probs = d_probs_; L.parents = pool_ + sg.off; L.plist = list_[0]; L.pcount = c_par;
-        L.children = buf_[0]; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
+        L.children = kbuf_; L.links = lbuf_; L.kstride = kstride_; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
         L.cand_count = d_cand_; L.node_count = d_node_; L.funnel = d_funnel_; L.work_counter = c_work; L.overflow = c_over;
         L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = EMIT_ALL; L.beam_delta = -1; L.beam_shift = 1;
         L.shard_world = sw; L.shard_rank = rank_; L.shard_level = shard_level_eff_; L.gpw = gpw_;
@@ -1359,25 +1405,32 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         sg.pos += m;
         ++chunks; ++since_exchange;
         DedupArgs D;
-        D.recs = buf_[0]; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
-        D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = stride_; D.level = level; D.overflow = c_over;
+        D.recs = kbuf_; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
+        D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = kstride_; D.level = level; D.overflow = c_over;
         D.probs = d_probs_; D.fmin_cur = nullptr; D.nmax = nmax_;
+        D.links = lbuf_; D.parents = pool_ + sg.off; D.pstride = stride_;
         k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
         FinalizeArgs F;
-        F.probs = d_probs_; F.recs = buf_[0]; F.count = c_child; F.cap = cap_;
-        F.next_list = list_[1]; F.next_count = c_next; F.best_score = d_best_score_; F.best_rows = d_best_rows_;
-        F.fmin = nullptr; F.limit = d_limit_; F.stride = stride_; F.level = level; F.merge_best = 1; F.build_list = 1; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
+        F.probs = d_probs_; F.recs = kbuf_; F.count = c_child; F.cap = cap_;
+        F.next_list = nullptr; F.next_count = nullptr; F.best_score = d_best_score_; F.best_rows = d_best_rows_;
+        F.fmin = nullptr; F.limit = d_limit_; F.stride = kstride_; F.level = level; F.merge_best = 1; F.build_list = 0; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
+        F.links = lbuf_; F.parents = pool_ + sg.off; F.pstride = stride_;
         k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_;
+        // the survivors become full records on top of the pool (the next, deeper segment of the stack)
+        const uint64_t room = (pool_bytes_ - pool_top) / (size_t)stride_;
+        MatArgs M;
+        M.probs = d_probs_; M.keys = kbuf_; M.links = lbuf_; M.count = c_child; M.cap = cap_; M.parents = pool_ + sg.off; M.pstride = stride_;
+        M.out = pool_ + pool_top; M.out_count = c_next; M.out_cap = (uint32_t)std::min<uint64_t>(room, 0xffffffffu);
+        M.kstride = kstride_; M.level = level; M.nmax = nmax_; M.overflow = c_over; M.fmin = nullptr; M.cutq = nullptr; M.ticket = nullptr;
+        k_materialise<<<sms_ * 8, 256, 0, stream_>>>(M); ++launches_;
         uint32_t nnext = 0;
         CK(cudaMemcpyAsync(&nnext, c_next, 4, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
         if (nnext) {
-            const size_t need = (size_t)nnext * stride_;
-            if (pool_top + need > pool_bytes_) { snprintf(err_, sizeof err_, "chunked pass: frontier pool exhausted (%zu bytes)", pool_bytes_); return -5; }
-            k_gather<<<sms_ * 8, 256, 0, stream_>>>(buf_[0], list_[1], nnext, pool_ + pool_top, stride_); ++launches_;
+            if (nnext > room) { snprintf(err_, sizeof err_, "chunked pass: frontier pool exhausted (%zu bytes)", pool_bytes_); return -5; }
             stack.push_back({level + 1, pool_top, nnext, 0});
-            pool_top += need;
+            pool_top += (size_t)nnext * stride_;
         }
     }
     chunked_runs_++;

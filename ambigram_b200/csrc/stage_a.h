@@ -94,7 +94,10 @@ private:
     int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
     int stride_ = 0, sms_ = 148;
     uint32_t leaf_levels_ = 0;      // bit a: some problem of the batch has n == a+1
-    uint8_t *buf_[2] = {nullptr, nullptr};
+    uint8_t *buf_[2] = {nullptr, nullptr};      // full records of the current / next frontier
+    uint8_t *kbuf_ = nullptr;                   // key records of a level's children
+    uint2 *lbuf_ = nullptr;                     // their (parent, row code) links
+    int kstride_ = 48;
     uint32_t *list_[2] = {nullptr, nullptr};
     unsigned long long *table_ = nullptr;
     uint32_t *counters_ = nullptr;
