@@ -53,7 +53,7 @@ class _Profile(C.Structure):
                 ("incumbent_pass_ms", C.c_double), ("record_stride", C.c_uint64), ("configs_enumerated", C.c_uint64),
                 ("bounds_evaluated", C.c_uint64), ("children_written", C.c_uint64), ("bound_batches", C.c_uint64), ("exchange_rounds", C.c_uint64),
                 ("chunked_runs", C.c_uint64), ("small_ms", C.c_double), ("small_solved", C.c_uint64), ("global_solved", C.c_uint64),
-                ("small_capacity", C.c_uint64)]
+                ("small_capacity", C.c_uint64), ("stage_b_kernel_ms", C.c_double)]
 
 
 class _Peaks(C.Structure):
@@ -356,7 +356,7 @@ class Context:
                 "configs_enumerated": int(p.configs_enumerated), "bounds_evaluated": int(p.bounds_evaluated),
                 "children_written": int(p.children_written), "bound_batches": int(p.bound_batches), "exchange_rounds": int(p.exchange_rounds),
                 "chunked_runs": int(p.chunked_runs), "small_ms": p.small_ms, "small_solved": int(p.small_solved),
-                "global_solved": int(p.global_solved), "small_capacity": int(p.small_capacity)}
+                "global_solved": int(p.global_solved), "small_capacity": int(p.small_capacity), "stage_b_kernel_ms": p.stage_b_kernel_ms}
 
     def measure_peaks(self) -> dict:
         """on-box INT32 issue rate (alu pipe; alu + fma pipes) and shared-memory bandwidth"""

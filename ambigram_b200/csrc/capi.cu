@@ -177,7 +177,7 @@ extern "C" int ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out)
     out->configs_enumerated = f[0]; out->bounds_evaluated = f[1]; out->children_written = f[2]; out->bound_batches = f[3];
     out->exchange_rounds = ctx->sa.exchange_rounds(); out->chunked_runs = ctx->sa.chunked_runs();
     out->small_ms = ctx->sa.small_ms(); out->small_solved = (uint64_t)ctx->sa.small_solved(); out->global_solved = (uint64_t)ctx->sa.global_solved();
-    out->small_capacity = (uint64_t)ctx->sa.small_capacity();
+    out->small_capacity = (uint64_t)ctx->sa.small_capacity(); out->stage_b_kernel_ms = ctx->sb.kernel_ms();
     return AMBI_OK;
 }
 namespace ambi { int measure_peaks(cudaStream_t st, ambi_peaks *out); }

@@ -27,6 +27,9 @@
 namespace ambi {
 namespace small {
 
+#ifndef AMBI_BEAM_FLOOR
+#define AMBI_BEAM_FLOOR 16           // narrowest beam (k_beam_cut of stage_a.cu uses the same floor)
+#endif
 constexpr int MAXN_SMALL = 16;          // one uint4 of column bytes
 using dec::L0CAP;
 using dec::below;
@@ -573,7 +576,7 @@ __device__ __noinline__ int solve_one(const Params &P, Fixed &S, const Arr &R, u
         t_start = AMBI_GLOBALTIMER();
         S.n = n; S.lmax = D.lmax; S.limit = D.zero_score; S.max_mc = 0;
         S.ctr_cfg = S.ctr_heavy = S.ctr_child = S.ctr_batches = S.ctr_cand = S.ctr_node = 0;
-        S.width = max(16, (int)min(8192.0f, (float)P.beam_width * exp2f(P.beam_growth * (float)max(0, n - 12))));
+        S.width = max(AMBI_BEAM_FLOOR, (int)min(8192.0f, (float)P.beam_width * exp2f(P.beam_growth * (float)max(0, n - 12))));
         S.width = min(S.width, C);
     }
     if (lane < MAXN_SMALL) S.cj[lane] = lane < n ? D.cj[lane] : 0u;

@@ -328,6 +328,7 @@ StageB::~StageB() { release(); }
 void StageB::release()
 {
     cudaFree(d_dags_); cudaFree(d_out_); cudaFree(d_work_); cudaFree(d_all_); cudaFreeHost(h_dags_); cudaFreeHost(h_out_);
+    for (int i = 0; i < 2; ++i) if (ev_[i]) { cudaEventDestroy(ev_[i]); ev_[i] = nullptr; }
     d_dags_ = d_out_ = d_work_ = d_all_ = h_dags_ = h_out_ = nullptr; cap_ = 0; all_bytes_ = 0;
 }
 
@@ -384,12 +385,16 @@ int StageB::run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_o
     CKB(cudaMemcpyAsync(d_dags_, h, (size_t)count * sizeof(DevDag), cudaMemcpyHostToDevice, stream_));
     CKB(cudaMemsetAsync(d_work_, 0, 64, stream_));
     int blocks = (count + 3) / 4; if (blocks > sms_ * 8) blocks = sms_ * 8;
+    if (!ev_[0]) { CKB(cudaEventCreate(&ev_[0])); CKB(cudaEventCreate(&ev_[1])); }
+    CKB(cudaEventRecord(ev_[0], stream_));
     k_first_valid_order<<<blocks, 128, 0, stream_>>>((const DevDag *)d_dags_, (DevOrderOut *)d_out_, count, (uint32_t *)d_work_);
+    CKB(cudaEventRecord(ev_[1], stream_));
     ++launches_;
     CKB(cudaGetLastError());
     DevOrderOut *ho = reinterpret_cast<DevOrderOut *>(h_out_);
     CKB(cudaMemcpyAsync(ho, d_out_, (size_t)count * sizeof(DevOrderOut), cudaMemcpyDeviceToHost, stream_));
     CKB(cudaStreamSynchronize(stream_));
+    { float ms = 0; if (cudaEventElapsedTime(&ms, ev_[0], ev_[1]) == cudaSuccess) kernel_ms_ = ms; }
     for (int i = 0; i < count; ++i) {
         ambi_order_result &r = results[i];
         const DevOrderOut &o = ho[i];

@@ -21,6 +21,7 @@ public:
                 std::vector<std::vector<int32_t>> &bkp_out, unsigned long long *tested, bool *truncated);
     const char *error() const { return err_; }
     unsigned long long launches() const { return launches_; }
+    double kernel_ms() const { return kernel_ms_; }        // device time of the last k_first_valid_order launch
 
 private:
     int ensure(int count);
@@ -31,6 +32,8 @@ private:
     void *d_all_ = nullptr;            // --all scratch: counters | orders | lengths | paths (grow-only)
     size_t all_bytes_ = 0;
     unsigned long long launches_ = 0;
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+    double kernel_ms_ = 0;
     char err_[256];
 };
 

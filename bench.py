@@ -424,8 +424,13 @@ def main():
     for _ in range(5):
         ctx.first_valid_order_packed(dpk)
     stage_b_s = (time.perf_counter() - t0) / 5
+    sb_kernel_s = ctx.profile()["stage_b_kernel_ms"] * 1e-3
+    sb_place = sum(int(r.orders_tested) for r in dpk[3])
+    # algorithmic work of a placement: about k * len integer operations, len = breakpoint-path length
+    sb_ops = sum(int(r.orders_tested) * max(1, d.k) * max(2, int(r.bkp_len)) for d, r in zip(dags, dpk[3]))
     stage_b = {"dags": len(dags), "seconds": stage_b_s, "partitions_per_s": len(dags) / stage_b_s,
-               "placements_per_s": sum(int(r.orders_tested) for r in dpk[3]) / stage_b_s,
+               "placements_per_s": sb_place / stage_b_s, "kernel_ms": 1e3 * sb_kernel_s,
+               "kernel_partitions_per_s": len(dags) / max(sb_kernel_s, 1e-9), "kernel_int_tops": sb_ops / max(sb_kernel_s, 1e-9) / 1e12,
                "found": sum(1 for r in dpk[3] if r.found), "note": "host wall clock around ambi_bfb_first_valid_order_batch (H2D + kernel + D2H)"}
     one = problems[0]
     for _ in range(3):

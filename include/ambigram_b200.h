@@ -242,6 +242,7 @@ typedef struct {
     uint64_t small_solved;       /* partitions it solved in the last run ...                                   */
     uint64_t global_solved;      /* ... and partitions that took the global-memory path (longer, or frontier too wide) */
     uint64_t small_capacity;     /* records per level and warp of the warp-per-partition kernel               */
+    double stage_b_kernel_ms;    /* device time of the last ambi_bfb_first_valid_order[_batch] kernel (Stage B)      */
 } ambi_profile;
 int  ambi_ctx_set_profile(ambi_ctx *ctx, int enable);
 int  ambi_ctx_get_profile(ambi_ctx *ctx, ambi_profile *out);

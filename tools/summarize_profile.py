@@ -30,7 +30,7 @@ def launches(round_, path):
         if len(r) <= mv:
             continue
         k = int(r[idc])
-        launch.setdefault(k, {"name": r[kn].split("(")[0].replace("ambi::", "")})
+        launch.setdefault(k, {"name": r[kn].split("(")[0].replace("void ", "").replace("ambi::", "").split("<")[0]})
         launch[k][r[mn]] = float(r[mv].replace(",", ""))
     L = list(launch.values())
     idx = [i for i, l in enumerate(L) if l["name"] == "k_bump_gen"]
