@@ -77,7 +77,7 @@ EXPORTS = [
     "ambi_abi_version", "ambi_init", "ambi_destroy", "ambi_last_error", "ambi_status_string",
     "ambi_nccl_unique_id", "ambi_comm_init", "ambi_bfb_solve", "ambi_bfb_solve_batch", "ambi_bfb_solve_shard",
     "ambi_bfb_better", "ambi_bfb_construct_dag", "ambi_bfb_first_valid_order", "ambi_bfb_first_valid_order_batch",
-    "ambi_bfb_expand_path", "ambi_bfb_imperfect_fbi", "ambi_bfb_all_valid_orders", "ambi_batch_upload", "ambi_batch_run", "ambi_batch_fetch", "ambi_batch_free",
+    "ambi_bfb_expand_path", "ambi_bfb_imperfect_fbi", "ambi_bfb_all_valid_orders", "ambi_bfb_all_valid_paths", "ambi_batch_upload", "ambi_batch_run", "ambi_batch_fetch", "ambi_batch_free",
     "ambi_ctx_stream", "ambi_ctx_sync", "ambi_ctx_launch_count", "ambi_ctx_set_profile", "ambi_ctx_get_profile",
     "ambi_measure_peaks", "ambi_bfb_target_cn",
 ]
@@ -117,6 +117,9 @@ def load_library(path: Optional[str] = None):
     lib.ambi_bfb_all_valid_orders.argtypes = [vp, C.POINTER(_Dag), C.c_int32, C.c_int32, C.POINTER(C.c_int32),
                                               C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                               C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+    lib.ambi_bfb_all_valid_paths.argtypes = [vp, C.POINTER(_Dag), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32),
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
     lib.ambi_bfb_imperfect_fbi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                            C.c_int32]
     lib.ambi_bfb_expand_path.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.c_int32]
@@ -389,6 +392,23 @@ class Context:
         rows = [[int(v) for v in orders[r * k:(r + 1) * k]] for r in range(n0.value + n1.value)]
         paths = [[int(v) for v in bkp[r * 1024:r * 1024 + blen[r]]] for r in range(n0.value + n1.value)]
         return rows[:n0.value], rows[n0.value:], paths
+
+    def all_valid_paths(self, dag: Dag, inversions: dict, reversed_: bool = False, max_orders: int = 4096, path_stride: int = 4096):
+        """--all with imperfectFBI and the expansion done on the device: -> (number of orders of the initial orientation,
+        of the flipped one, the vertex paths in the reference's print order); `inversions` as for imperfect_fbi"""
+        max_id = max([0] + [int(k) for k in inversions] + [int(v) for st in inversions.values() for v in st])
+        src = np.zeros(max_id + 2, dtype=np.int32); tgt = np.zeros(max_id + 2, dtype=np.int32)
+        for k, (s_, t_) in inversions.items():
+            src[int(k)], tgt[int(k)] = int(s_), int(t_)
+        paths = np.zeros(max_orders * path_stride, dtype=np.int32)
+        plen = np.zeros(max_orders, dtype=np.int32)
+        n0, n1, tested = C.c_int32(0), C.c_int32(0), C.c_uint64(0)
+        I = C.POINTER(C.c_int32)
+        self._check(self.lib.ambi_bfb_all_valid_paths(self.handle, C.byref(dag.raw), int(reversed_), src.ctypes.data_as(I), tgt.ctypes.data_as(I),
+                                                      max_id, max_orders, None, paths.ctypes.data_as(I), path_stride, plen.ctypes.data_as(I),
+                                                      C.byref(n0), C.byref(n1), C.byref(tested)))
+        out = [[int(v) for v in paths[r * path_stride:r * path_stride + plen[r]]] for r in range(n0.value + n1.value)]
+        return n0.value, n1.value, out
 
     @staticmethod
     def pack_dags(dags: Sequence[Dag], reversed_: Sequence[bool]):

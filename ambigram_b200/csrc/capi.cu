@@ -9,6 +9,7 @@
 #include "stage_a.h"
 #include "stage_b.h"
 #include "host_flatten.h"
+#include "path_surgery.h"
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -502,21 +503,24 @@ extern "C" int ambi_bfb_first_valid_order(ambi_ctx *ctx, const ambi_dag *dag, in
 // getBFB visits the orders of the initial orientation lexicographically and prints each valid one; if
 // the lexicographically LAST topological order fails there, it flips the orientation and goes through
 // all orders again (LGM:3691-3695), printing the valid ones of the flipped orientation as well.
-extern "C" int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, int32_t max_orders,
-                                         int32_t *orders_out, int32_t *bkp_out, int32_t bkp_stride, int32_t *bkp_len_out,
-                                         int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested)
+// shared body of ambi_bfb_all_valid_orders / ambi_bfb_all_valid_paths
+static int all_valid_impl(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, int32_t max_orders,
+                          int32_t *orders_out, int32_t *bkp_out, int32_t bkp_stride, int32_t *bkp_len_out,
+                          const int32_t *inv_src, const int32_t *inv_tgt, int32_t max_id,
+                          int32_t *path_out, int32_t path_stride, int32_t *path_len_out,
+                          int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested)
 {
-    if (!ctx || !dag || !orders_out || !n_initial || !n_flipped || max_orders <= 0) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_all_valid_orders: bad argument");
     cudaSetDevice(ctx->cfg.device);
     *n_initial = *n_flipped = 0;
     unsigned long long tested = 0;
     const int k = dag->k;
     if (k <= 0) { if (n_tested) *n_tested = 0; return AMBI_OK; }
-    std::vector<std::vector<int32_t>> first, second, bfirst, bsecond;
+    const bool surgery = path_out != nullptr;
+    std::vector<std::vector<int32_t>> first, second, bfirst, bsecond, pfirst, psecond;
     bool trunc = false;
     const int fwd0 = reversed ? 0 : 1;
-    int rc = ctx->sb.run_all(*dag, fwd0, max_orders, first, bfirst, &tested, &trunc);
     auto sb_status = [](int r) { return r == -2 ? AMBI_ERR_BAD_ARG : (r == -3 ? AMBI_ERR_TOO_LARGE : AMBI_ERR_CUDA); };
+    int rc = ctx->sb.run_all(*dag, fwd0, max_orders, first, bfirst, &tested, &trunc, inv_src, inv_tgt, max_id, path_stride, surgery ? &pfirst : nullptr);
     if (rc) return fail(ctx, sb_status(rc), ctx->sb.error());
     if (trunc) return fail(ctx, AMBI_ERR_TOO_LARGE, "more valid orders than max_orders");
     // lexicographically last topological order: always take the highest free index
@@ -535,7 +539,8 @@ extern "C" int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int
     const bool have_orders = (int)last.size() == k;
     const bool last_valid = have_orders && std::binary_search(first.begin(), first.end(), last);
     if (have_orders && !last_valid) {
-        rc = ctx->sb.run_all(*dag, 1 - fwd0, max_orders - (int32_t)first.size() > 0 ? max_orders - (int32_t)first.size() : 1, second, bsecond, &tested, &trunc);
+        rc = ctx->sb.run_all(*dag, 1 - fwd0, max_orders - (int32_t)first.size() > 0 ? max_orders - (int32_t)first.size() : 1, second, bsecond, &tested, &trunc,
+                             inv_src, inv_tgt, max_id, path_stride, surgery ? &psecond : nullptr);
         if (rc) return fail(ctx, sb_status(rc), ctx->sb.error());
         if (trunc) return fail(ctx, AMBI_ERR_TOO_LARGE, "more valid orders than max_orders");
     }
@@ -543,18 +548,44 @@ extern "C" int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int
     size_t o = 0, row = 0;
     for (auto *lst : {&first, &second}) {
         const auto &bl = lst == &first ? bfirst : bsecond;
+        const auto &pl = lst == &first ? pfirst : psecond;
         for (size_t i = 0; i < lst->size(); ++i, ++row) {
-            for (int32_t x : (*lst)[i]) orders_out[o++] = x;
+            if (orders_out) for (int32_t x : (*lst)[i]) orders_out[o++] = x;
             if (bkp_out && bkp_len_out && bkp_stride > 0) {
                 const int len = (int)std::min<size_t>(bl[i].size(), (size_t)bkp_stride);
                 bkp_len_out[row] = len;
                 for (int t = 0; t < len; ++t) bkp_out[row * (size_t)bkp_stride + t] = bl[i][t];
+            }
+            if (surgery) {
+                path_len_out[row] = (int32_t)pl[i].size();
+                for (size_t t = 0; t < pl[i].size(); ++t) path_out[row * (size_t)path_stride + t] = pl[i][t];
             }
         }
     }
     *n_initial = (int32_t)first.size(); *n_flipped = (int32_t)second.size();
     if (n_tested) *n_tested = tested;
     return AMBI_OK;
+}
+
+extern "C" int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, int32_t max_orders,
+                                         int32_t *orders_out, int32_t *bkp_out, int32_t bkp_stride, int32_t *bkp_len_out,
+                                         int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested)
+{
+    if (!ctx || !dag || !orders_out || !n_initial || !n_flipped || max_orders <= 0) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_all_valid_orders: bad argument");
+    return all_valid_impl(ctx, dag, reversed, max_orders, orders_out, bkp_out, bkp_stride, bkp_len_out, nullptr, nullptr, 0, nullptr, 0, nullptr,
+                          n_initial, n_flipped, n_tested);
+}
+
+// --all with the post-search path surgery on the device: every path getBFB would print, as
+// signed vertex ids, after imperfectFBI (LGM:3431-3512) and the expansion of the breakpoint pairs (LGM:3661-3670).
+extern "C" int ambi_bfb_all_valid_paths(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, const int32_t *inv_src, const int32_t *inv_tgt,
+                                        int32_t max_id, int32_t max_orders, int32_t *orders_out, int32_t *path_out, int32_t path_stride,
+                                        int32_t *path_len_out, int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested)
+{
+    if (!ctx || !dag || !inv_src || !inv_tgt || max_id < 0 || !path_out || !path_len_out || path_stride <= 0 || !n_initial || !n_flipped || max_orders <= 0)
+        return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_bfb_all_valid_paths: bad argument");
+    return all_valid_impl(ctx, dag, reversed, max_orders, orders_out, nullptr, 0, nullptr, inv_src, inv_tgt, max_id, path_out, path_stride, path_len_out,
+                          n_initial, n_flipped, n_tested);
 }
 
 extern "C" int ambi_bfb_target_cn(int32_t n, const int32_t *x, int32_t *target)
@@ -572,14 +603,7 @@ extern "C" int ambi_bfb_target_cn(int32_t n, const int32_t *x, int32_t *target)
 
 extern "C" int ambi_bfb_expand_path(const int32_t *bkp, int32_t bkp_len, int32_t *path_out, int32_t cap)
 {
-    // LGM:3661-3670: each pair (first,last) of a monotone run expands to every id in between
-    int len = 0;
-    for (int j = 1; j < bkp_len; j += 2) {
-        int u = bkp[j - 1], v = bkp[j];
-        if (u > 0) { for (int k = u; k <= v; ++k) { if (len < cap) path_out[len] = k; ++len; } }
-        else { for (int k = -u; k >= -v; --k) { if (len < cap) path_out[len] = -k; ++len; } }
-    }
-    return len;
+    return ambi::expand_path(bkp, bkp_len, path_out, cap);      // LGM:3661-3670 (path_surgery.h)
 }
 
 // imperfectFBI (LGM:3431-3512), host side of Seam B: rewrite fold vertices whose fold-back junction
@@ -588,46 +612,6 @@ extern "C" int ambi_bfb_expand_path(const int32_t *bkp, int32_t bkp_len, int32_t
 extern "C" int ambi_bfb_imperfect_fbi(int32_t *bkp, int32_t len, const int32_t *inv_src, const int32_t *inv_tgt, int32_t max_id)
 {
     if (!bkp || len < 0 || (len & 1) || !inv_src || !inv_tgt) return AMBI_ERR_BAD_ARG;
-    auto has = [&](int id) { return id >= 1 && id <= max_id && inv_src[id] != 0; };
-    auto mag = [](int v) { return v < 0 ? -v : v; };
-    int pos = 0;
-    while (pos < len) {
-        int r = len;                                   // first q >= pos+3 holding the complement of bkp[pos]
-        for (int q = pos + 3; q < len; ++q) if (bkp[q] == -bkp[pos]) { r = q; break; }
-        const int l = r - 1;
-        if (r == len || bkp[l] != -bkp[pos + 1]) {     // not the outer pair of a palindrome (LGM:3442-3472)
-            int id = mag(bkp[pos + 1]);
-            if (has(id)) {
-                const int lo = std::min(inv_src[id], inv_tgt[id]), hi = std::max(inv_src[id], inv_tgt[id]);
-                bkp[pos + 1] = bkp[pos + 1] > 0 ? lo : -hi;
-            }
-            if (pos > 0) {
-                id = mag(bkp[pos]);
-                if (has(id) && mag(bkp[pos - 1]) == id) {
-                    const int other = inv_src[id] == id ? inv_tgt[id] : inv_src[id];
-                    bkp[pos] = bkp[pos] > 0 ? other : -other;
-                }
-            }
-            if (bkp[pos] > 0 && mag(bkp[pos]) > mag(bkp[pos + 1])) bkp[pos + 1] = bkp[pos];
-            if (bkp[pos] < 0 && mag(bkp[pos]) < mag(bkp[pos + 1])) bkp[pos + 1] = bkp[pos];
-            pos += 2;
-        } else {                                       // palindrome: walk outwards from its centre (LGM:3473-3509)
-            int p1 = pos + (l - pos) / 2, p2 = p1 + 1;
-            while (p1 >= pos - 1 && p1 > 0) {
-                const int id = mag(bkp[p1]);
-                if (has(id)) {
-                    const int lo = std::min(inv_src[id], inv_tgt[id]), hi = std::max(inv_src[id], inv_tgt[id]);
-                    if (bkp[p1] > 0) { bkp[p1] = lo; bkp[p1 + 1] = -hi; }
-                    else { bkp[p1] = -hi; bkp[p1 + 1] = lo; }
-                    if (p2 != p1 + 1) {
-                        if (p1 > pos - 1) bkp[p2] = -bkp[p1];
-                        bkp[p2 - 1] = -bkp[p1 + 1];
-                    }
-                }
-                p1 -= 2; p2 += 2;
-            }
-            pos = r + 1;
-        }
-    }
+    ambi::imperfect_fbi(bkp, len, inv_src, inv_tgt, max_id);     // one implementation for host and device (path_surgery.h)
     return AMBI_OK;
 }

@@ -15,6 +15,7 @@
 // The winner is the solution with the smallest t (shared-memory atomicMin),
 // which is the lexicographically first valid order.
 #include "stage_b.h"
+#include "path_surgery.h"
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -320,6 +321,22 @@ k_all_valid_orders(const DevDag *dag, int forward, int32_t *orders, int8_t *bkps
     if (tested) atomicAdd(n_tested, tested);
 }
 
+// --all post-processing on the device (getBFB after an order has assembled, LGM:3656-3670): one thread per valid order
+// turns its breakpoint path (relative int8 ids) into absolute signed ids, applies imperfectFBI and expands the pairs
+// to the vertex path the reference prints.
+__global__ void k_path_surgery(const int8_t *bkps, const int32_t *bkp_lens, uint32_t n_orders, int base,
+                               const int16_t *inv_src, const int16_t *inv_tgt, int max_id,
+                               int16_t *scratch /*[n][MAXPATH]*/, int16_t *paths /*[n][stride]*/, int32_t *path_lens, int stride)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_orders) return;
+    const int len = bkp_lens[i];
+    int16_t *b = scratch + (size_t)i * MAXPATH;
+    for (int t = 0; t < len; ++t) { const int v = bkps[(size_t)i * MAXPATH + t]; b[t] = (int16_t)(v > 0 ? v - 1 + base : -(-v - 1 + base)); }
+    imperfect_fbi(b, len, inv_src, inv_tgt, max_id);
+    path_lens[i] = expand_path(b, len, paths + (size_t)i * stride, stride);
+}
+
 #define CKB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
     snprintf(err_, sizeof err_, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return -4; } } while (0)
 
@@ -409,7 +426,9 @@ int StageB::run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_o
 
 // every valid order of one orientation, sorted lexicographically (the reference's print order)
 int StageB::run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::vector<std::vector<int32_t>> &out,
-                    std::vector<std::vector<int32_t>> &bkp_out, unsigned long long *tested, bool *truncated)
+                    std::vector<std::vector<int32_t>> &bkp_out, unsigned long long *tested, bool *truncated,
+                    const int32_t *inv_src, const int32_t *inv_tgt, int32_t max_id, int32_t path_stride,
+                    std::vector<std::vector<int32_t>> *paths_out)
 {
     out.clear(); bkp_out.clear(); *truncated = false;
     if (dag.k <= 0) return 0;
@@ -418,7 +437,10 @@ int StageB::run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::v
     DevDag h;
     if (int rc = to_devdag(dag, 0, h, 0)) return rc;
     // grow-only scratch kept in the object (no per-call cudaMalloc, nothing to leak on the error paths)
-    const size_t need = (size_t)max_orders * ((size_t)dag.k * sizeof(int32_t) + MAXPATH + sizeof(int32_t)) + 64;
+    const bool surgery = paths_out != nullptr && inv_src && inv_tgt && path_stride > 0;
+    if (paths_out) paths_out->clear();
+    const size_t need = (size_t)max_orders * ((size_t)dag.k * sizeof(int32_t) + MAXPATH + sizeof(int32_t)) + 64 +
+                        (surgery ? (size_t)max_orders * ((size_t)MAXPATH * 2 + (size_t)path_stride * 2 + 4) + (size_t)(max_id + 2) * 4 + 64 : 0);
     if (need > all_bytes_) {
         cudaFree(d_all_); d_all_ = nullptr; all_bytes_ = 0;
         CKB(cudaMalloc(&d_all_, need));
@@ -442,6 +464,28 @@ int StageB::run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::v
     *truncated = cnt[0] > (uint32_t)max_orders;
     std::vector<int32_t> flat((size_t)n * dag.k), lens(n);
     std::vector<int8_t> paths((size_t)n * MAXPATH);
+    std::vector<int16_t> hp; std::vector<int32_t> hpl;
+    if (n && surgery) {
+        // imperfectFBI + expansion of every valid order on the device
+        uint8_t *q = reinterpret_cast<uint8_t *>(d_bkps) + (size_t)max_orders * MAXPATH;
+        q = reinterpret_cast<uint8_t *>(((uintptr_t)q + 15) & ~(uintptr_t)15);
+        int16_t *d_inv_s = reinterpret_cast<int16_t *>(q); int16_t *d_inv_t = d_inv_s + (max_id + 2);
+        q += (size_t)(max_id + 2) * 4; q = reinterpret_cast<uint8_t *>(((uintptr_t)q + 15) & ~(uintptr_t)15);
+        int16_t *d_scratch = reinterpret_cast<int16_t *>(q); q += (size_t)max_orders * MAXPATH * 2;
+        int16_t *d_paths = reinterpret_cast<int16_t *>(q); q += (size_t)max_orders * path_stride * 2;
+        int32_t *d_plens = reinterpret_cast<int32_t *>(q);
+        std::vector<int16_t> hs((size_t)max_id + 2, 0), ht((size_t)max_id + 2, 0);
+        for (int i = 0; i <= max_id; ++i) { hs[i] = (int16_t)inv_src[i]; ht[i] = (int16_t)inv_tgt[i]; }
+        CKB(cudaMemcpyAsync(d_inv_s, hs.data(), hs.size() * 2, cudaMemcpyHostToDevice, stream_));
+        CKB(cudaMemcpyAsync(d_inv_t, ht.data(), ht.size() * 2, cudaMemcpyHostToDevice, stream_));
+        k_path_surgery<<<(n + 127) / 128, 128, 0, stream_>>>(d_bkps, d_lens, n, h.base, d_inv_s, d_inv_t, max_id, d_scratch, d_paths, d_plens, path_stride);
+        ++launches_;
+        CKB(cudaGetLastError());
+        hp.resize((size_t)n * path_stride); hpl.resize(n);
+        CKB(cudaMemcpyAsync(hp.data(), d_paths, hp.size() * 2, cudaMemcpyDeviceToHost, stream_));
+        CKB(cudaMemcpyAsync(hpl.data(), d_plens, hpl.size() * 4, cudaMemcpyDeviceToHost, stream_));
+        CKB(cudaStreamSynchronize(stream_));               // hs / ht go out of scope
+    }
     if (n) {
         CKB(cudaMemcpyAsync(flat.data(), d_orders, flat.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
         CKB(cudaMemcpyAsync(lens.data(), d_lens, lens.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
@@ -455,8 +499,13 @@ int StageB::run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::v
         return std::lexicographical_compare(flat.begin() + (size_t)x * dag.k, flat.begin() + (size_t)(x + 1) * dag.k,
                                             flat.begin() + (size_t)y * dag.k, flat.begin() + (size_t)(y + 1) * dag.k); });
     out.resize(n); bkp_out.resize(n);
+    if (surgery) paths_out->resize(n);
     for (uint32_t q = 0; q < n; ++q) {
         const uint32_t i = perm[q];
+        if (surgery) {
+            if (hpl[i] > path_stride) { snprintf(err_, sizeof err_, "expanded path of %d vertices exceeds path_stride %d", hpl[i], path_stride); return -3; }
+            (*paths_out)[q].assign(hp.begin() + (size_t)i * path_stride, hp.begin() + (size_t)i * path_stride + hpl[i]);
+        }
         out[q].assign(flat.begin() + (size_t)i * dag.k, flat.begin() + (size_t)(i + 1) * dag.k);
         bkp_out[q].resize(lens[i]);
         for (int t = 0; t < lens[i]; ++t) { int v = paths[(size_t)i * MAXPATH + t]; bkp_out[q][t] = v > 0 ? v - 1 + h.base : -(-v - 1 + h.base); }

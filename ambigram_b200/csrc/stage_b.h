@@ -18,7 +18,9 @@ public:
     // first valid topological order for each DAG (orientation per reversed[i], flipped if none)
     int run(int count, const ambi_dag *dags, const int32_t *reversed, ambi_order_result *results);
     int run_all(const ambi_dag &dag, int forward, int32_t max_orders, std::vector<std::vector<int32_t>> &out,
-                std::vector<std::vector<int32_t>> &bkp_out, unsigned long long *tested, bool *truncated);
+                std::vector<std::vector<int32_t>> &bkp_out, unsigned long long *tested, bool *truncated,
+                const int32_t *inv_src = nullptr, const int32_t *inv_tgt = nullptr, int32_t max_id = 0, int32_t path_stride = 0,
+                std::vector<std::vector<int32_t>> *paths_out = nullptr);
     const char *error() const { return err_; }
     unsigned long long launches() const { return launches_; }
     double kernel_ms() const { return kernel_ms_; }        // device time of the last k_first_valid_order launch

@@ -410,17 +410,16 @@ int main(int argc, char **argv)
             ++wi;
             if (print_all && r.found) {
                 // --all: every valid order in the reference's print order (LGM:3672-3695); `path` keeps the first
-                const int kmax = 4096;
-                std::vector<int32_t> ords((size_t)kmax * std::max(dags[wi - 1].k, 1)), bk((size_t)kmax * 1024), bl(kmax);
+                // (enumeration, imperfectFBI and expansion all on the device: ambi_bfb_all_valid_paths)
+                const int kmax = 4096, pstride = 8192;
+                std::vector<int32_t> pv((size_t)kmax * pstride), pl(kmax);
                 int32_t n0 = 0, n1 = 0;
-                if (ambi_bfb_all_valid_orders(ctx, &dags[wi - 1], reversed ? 1 : 0, kmax, ords.data(), bk.data(), 1024, bl.data(), &n0, &n1, nullptr) != AMBI_OK) {
-                    std::cerr << "ambi_bfb_all_valid_orders: " << ambi_last_error(ctx) << std::endl; return 1;
+                if (ambi_bfb_all_valid_paths(ctx, &dags[wi - 1], reversed ? 1 : 0, p.inv_src.data(), p.inv_tgt.data(), (int32_t)p.inv_src.size() - 2,
+                                             kmax, nullptr, pv.data(), pstride, pl.data(), &n0, &n1, nullptr) != AMBI_OK) {
+                    std::cerr << "ambi_bfb_all_valid_paths: " << ambi_last_error(ctx) << std::endl; return 1;
                 }
                 for (int q = 0; q < n0 + n1; ++q) {
-                    ambi_bfb_imperfect_fbi(&bk[(size_t)q * 1024], bl[q], p.inv_src.data(), p.inv_tgt.data(), (int32_t)p.inv_src.size() - 2);
-                    std::vector<int32_t> buf(1 << 16);
-                    int len = ambi_bfb_expand_path(&bk[(size_t)q * 1024], bl[q], buf.data(), (int32_t)buf.size());
-                    Path one(buf.begin(), buf.begin() + std::min<int>(len, (int)buf.size()));
+                    Path one(pv.begin() + (size_t)q * pstride, pv.begin() + (size_t)q * pstride + pl[q]);
                     if (q == 0) path = one;
                     std::cout << format_path(one) << std::endl;
                 }

@@ -200,6 +200,16 @@ int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int32_t revers
                               int32_t *orders_out, int32_t *bkp_out, int32_t bkp_stride, int32_t *bkp_len_out,
                               int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested);
 
+/* --all with the post-search path surgery done on the device: row r of path_out
+ * (path_stride entries per row) holds the path_len_out[r] signed vertex ids (+id '+', -id '-') the reference prints
+ * for the r-th valid order -- breakpoint path, imperfectFBI (LGM:3431-3512; inv_src/inv_tgt as for
+ * ambi_bfb_imperfect_fbi), expansion of the pairs (LGM:3661-3670) -- in the print order of
+ * ambi_bfb_all_valid_orders.  orders_out may be NULL.  AMBI_ERR_TOO_LARGE if a path has more than path_stride vertices. */
+int ambi_bfb_all_valid_paths(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, const int32_t *inv_src,
+                             const int32_t *inv_tgt, int32_t max_id, int32_t max_orders, int32_t *orders_out,
+                             int32_t *path_out, int32_t path_stride, int32_t *path_len_out,
+                             int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested);
+
 /* imperfectFBI (LGM:3431-3512), host bookkeeping for the winning order only: fold
  * vertices whose junction joins two different segments are rewritten in place.
  * inv_src/inv_tgt[id] = endpoints of inversions[id] (0 = none), id <= max_id.  */

@@ -111,3 +111,28 @@ int ambi_bfb_all_valid_orders(ambi_ctx *ctx, const ambi_dag *dag, int32_t revers
     *n_initial = (int32_t)n1; *n_flipped = (int32_t)n2;
     return AMBI_OK;
 }
+
+/* --all with the path surgery: orders from above, then imperfectFBI and expansion per order with the oracle */
+int ambi_bfb_all_valid_paths(ambi_ctx *ctx, const ambi_dag *dag, int32_t reversed, const int32_t *inv_src, const int32_t *inv_tgt,
+                             int32_t max_id, int32_t max_orders, int32_t *orders_out, int32_t *path_out, int32_t path_stride,
+                             int32_t *path_len_out, int32_t *n_initial, int32_t *n_flipped, uint64_t *n_tested)
+{
+    const int k = dag->k > 0 ? dag->k : 1;
+    int32_t *ords = orders_out ? orders_out : (int32_t *)malloc(sizeof(int32_t) * (size_t)max_orders * k);
+    int rc = ambi_bfb_all_valid_orders(ctx, dag, reversed, max_orders, ords, NULL, 0, NULL, n_initial, n_flipped, n_tested);
+    if (rc == AMBI_OK) {
+        orc_dag d;
+        memset(&d, 0, sizeof d);
+        d.k = dag->k;
+        for (int v = 0; v < d.k; v++) { d.kind[v] = dag->kind[v]; d.a[v] = dag->a[v]; d.b[v] = dag->b[v]; d.cn[v] = dag->cn[v]; d.adj[v] = dag->adj[v]; }
+        for (int r = 0; r < *n_initial + *n_flipped; r++) {
+            int32_t bkp[4096]; int32_t bl = 0;
+            const int fwd = (r < *n_initial) ? (reversed ? 0 : 1) : (reversed ? 1 : 0);
+            orc_assemble_order(&d, ords + (size_t)r * d.k, fwd, bkp, &bl);
+            orc_imperfect_fbi(bkp, bl, inv_src, inv_tgt, max_id);
+            path_len_out[r] = orc_expand_path(bkp, bl, path_out + (size_t)r * path_stride, path_stride);
+        }
+    }
+    if (!orders_out) free(ords);
+    return rc;
+}

@@ -359,6 +359,30 @@ def test_all_valid_orders_matches_reference_print_all(ctx):
     assert seen_multi >= 10
 
 
+def test_all_valid_paths_device_surgery_matches_reference_print_all(ctx):
+    """--all with imperfectFBI and the expansion on the device (ambi_bfb_all_valid_paths): the vertex paths the reference
+    prints, incl. the imperfect fold-back fixtures, against its stdout and against the host-side surgery"""
+    checked = imperfect = 0
+    for c in CASES:
+        if "ref_inject_paths_all" not in c or c["name"].startswith("indel_"):
+            continue
+        part = partition_of(c)
+        p = part.problem
+        x = np.zeros(p.n * (p.n + 1), dtype=np.int32)
+        for i, v in c["oracle_x_nz"]:
+            x[i] = v
+        dag = capi.construct_dag(p.n, p.start_id, x)
+        for rev, key in ((False, "ref_inject_paths_all"), (True, "ref_inject_paths_all_rev")):
+            n0, n1, paths = ctx.all_valid_paths(dag, part.inversions, rev)
+            assert [capi.format_path(v) for v in paths] == c[key], c["name"]
+            first, second, bk = ctx.all_valid_orders(dag, rev)
+            assert (n0, n1) == (len(first), len(second))
+            assert paths == [capi.expand_path(capi.imperfect_fbi(b, part.inversions)) for b in bk]
+            checked += 1
+        imperfect += c["name"].startswith("imperfect_")
+    assert checked >= 80 and imperfect >= 10
+
+
 def test_measured_peaks_are_plausible(ctx):
     """on-box roofline denominators: integer issue rate and shared-memory bandwidth"""
     pk = ctx.measure_peaks()

@@ -91,3 +91,25 @@ def test_host_driver_batch_list(shim, tmp_path):
         want += c["ref_inject_paths"]
     (tmp_path / "list.txt").write_text("\n".join(names) + "\n")
     assert run_cli(shim, ["--op", "bfb", "--in_list", "list.txt"], str(tmp_path)) == want
+
+
+def test_host_driver_print_all(shim, tmp_path):
+    """--all: every valid order's path in the reference's print order (the driver asks the library for the finished
+    vertex paths: ambi_bfb_all_valid_paths)"""
+    checked = 0
+    for c in CASES:
+        if "ref_inject_paths_all" not in c or c["name"].startswith("indel_") or len(c["oracle_x_nz"]) > 16:
+            continue
+        for rev, key in ((False, "ref_inject_paths_all"), (True, "ref_inject_paths_all_rev")):
+            d = tmp_path / (c["name"] + ("_ar" if rev else "_a"))
+            d.mkdir()
+            (d / "in.lh").write_text(c["lh"])
+            args = ["--op", "bfb", "--in_lh", "in.lh", "--all"] + (["--reversed"] if rev else [])
+            if c["juncs"]:
+                (d / "in.juncs").write_text(c["juncs"])
+                args += ["--juncdb", "in.juncs"]
+            if c["junc_info"]:
+                args += ["--junc_info", "true"]
+            assert run_cli(shim, args, str(d)) == c[key], c["name"]
+            checked += 1
+    assert checked >= 40
