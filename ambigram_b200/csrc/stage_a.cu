@@ -266,15 +266,11 @@ __device__ __noinline__ void write_batch(GroupShared<NMAX> &S, const LevelArgs &
     A.links[cslot] = make_uint2(S.pidx[slot], code);
 }
 
+// Body of the expansion kernel: `A` lives in shared memory (the stage functions take it by reference), `s_raw` is the
+// block's dynamic shared memory (one GroupShared per warp).  Called by k_expand and by the fused program kernel.
 template <int NMAX, bool SCALED>
-__global__ void __launch_bounds__(WPB * 32, NMAX <= 16 ? 4 : 3)
-k_expand(LevelArgs A_param)
+__device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
 {
-    extern __shared__ __align__(16) uint8_t s_raw[];
-    __shared__ LevelArgs s_args;            // the stage functions take the arguments by reference
-    if (threadIdx.x == 0) s_args = A_param;
-    __syncthreads();
-    const LevelArgs &A = s_args;
     if (*A.overflow) return;                // an earlier level of this pass did not fit (block-uniform)
     GroupShared<NMAX> &S = reinterpret_cast<GroupShared<NMAX> *>(s_raw)[threadIdx.x >> 5];
     const int lane = lane_id();
@@ -489,6 +485,17 @@ k_expand(LevelArgs A_param)
     }
 }
 
+template <int NMAX, bool SCALED>
+__global__ void __launch_bounds__(WPB * 32, NMAX <= 16 ? 4 : 3)
+k_expand(LevelArgs A_param)
+{
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ LevelArgs s_args;
+    if (threadIdx.x == 0) s_args = A_param;
+    __syncthreads();
+    expand_body<NMAX, SCALED>(s_args, s_raw);
+}
+
 // ---------------------------------------------------------------------------
 // K3a: merge records that reached the same column state.
 // A dropped record is flagged in its own header (bit 31 of the tgs word), so no
@@ -556,7 +563,7 @@ __device__ __forceinline__ bool rec_better(const DedupArgs &A, uint32_t i, uint3
     return lx.y < ly.y;
 }
 
-__global__ void k_dedup(DedupArgs A)
+__device__ __forceinline__ void dedup_body(const DedupArgs &A)
 {
     if (*A.overflow) return;
     uint32_t cnt = min(*A.count, A.cap);
@@ -632,7 +639,7 @@ struct FinalizeArgs {
     int pstride;
 };
 
-__global__ void k_finalize(FinalizeArgs A)
+__device__ __forceinline__ void finalize_body(const FinalizeArgs &A)
 {
     if (*A.overflow) return;
     uint32_t cnt = min(*A.count, A.cap);
@@ -689,7 +696,7 @@ struct BeamArgs {
     int level;
 };
 
-__global__ void k_beam_hist(BeamArgs A)
+__device__ __forceinline__ void beam_hist_body(const BeamArgs &A)
 {
     uint32_t cnt = min(*A.count, A.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
@@ -702,10 +709,9 @@ __global__ void k_beam_hist(BeamArgs A)
 
 // per problem: the bin in which the cumulative count reaches the beam width, and how many records of that bin
 // still fit (every record in a lower bin is kept, records of the cut bin draw tickets)
-__global__ void k_beam_cut(BeamArgs A)
+__device__ __forceinline__ void beam_cut_body(const BeamArgs &A)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.nprob) return;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < A.nprob; p += gridDim.x * blockDim.x) {
     const uint32_t width = max(16u, (uint32_t)max((float)A.width_floor, min(8192.0f, (float)A.width * exp2f(A.growth * (float)max(0, A.probs[p].n - 12)))) / (uint32_t)A.width_div);
     const uint32_t *hs = A.hist + (size_t)p * BEAM_BINS;
     uint32_t below = 0;
@@ -717,6 +723,7 @@ __global__ void k_beam_cut(BeamArgs A)
         below += c;
     }
     A.cutq[p] = ((uint32_t)cut << 16) | quota;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -735,7 +742,7 @@ struct MatArgs {
     const int32_t *fmin; const uint32_t *cutq; uint32_t *ticket;
 };
 
-__global__ void k_materialise(MatArgs A)
+__device__ __forceinline__ void materialise_body(const MatArgs &A)
 {
     if (*A.overflow) return;
     const uint32_t cnt = min(*A.count, A.cap);
@@ -782,29 +789,40 @@ __global__ void k_materialise(MatArgs A)
     }
 }
 
+__global__ void k_dedup(DedupArgs A) { dedup_body(A); }
+__global__ void k_finalize(FinalizeArgs A) { finalize_body(A); }
+__global__ void k_beam_hist(BeamArgs A) { beam_hist_body(A); }
+__global__ void k_beam_cut(BeamArgs A) { beam_cut_body(A); }
+__global__ void k_materialise(MatArgs A) { materialise_body(A); }
+
 // ---------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------
 // `active`: partitions this (global-memory) path still has to solve; the others were solved by the
 // warp-per-partition kernel (stage_small.cu) and keep their results
-__global__ void k_init_roots(const DevProblem *probs, int count, uint8_t *recs, int stride, int nmax,
-                             uint32_t *list, uint32_t *lcount, int32_t *limit, int32_t *best_score, int first,
-                             const uint8_t *active)
+struct InitRootsArgs {
+    const DevProblem *probs; int count; uint8_t *recs; int stride, nmax;
+    uint32_t *list, *lcount; int32_t *limit, *best_score; int first; const uint8_t *active;
+};
+
+__device__ __forceinline__ void init_roots_body(const InitRootsArgs &A)
 {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= count || !active[p]) return;
-    const DevProblem &P = probs[p];
-    if (first) { limit[p] = P.zero_score; best_score[p] = 0x7fffffff; }
-    if (P.n < 2) return;                  // n == 1 handled by k_solve_n1
-    uint32_t s = atomicAdd(lcount, 1u);
-    uint8_t *rec = recs + (size_t)s * stride;
-    NodeHdr *h = reinterpret_cast<NodeHdr *>(rec);
-    for (int b = 0; b < AMBI_MAXN; ++b) h->col[b] = b < P.n ? (uint8_t)((AMBI_BUD_INF << 4) | (AMBI_BUD_INF << 6)) : 0;
-    h->score = 0; h->f = P.root_lb; h->prob = p; h->tgs = 0;
-    uint32_t *r = reinterpret_cast<uint32_t *>(rec + sizeof(NodeHdr));
-    for (int k = 0; k < nmax; ++k) r[k] = 0;
-    list[s] = s;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < A.count; p += gridDim.x * blockDim.x) {
+        if (!A.active[p]) continue;
+        const DevProblem &P = A.probs[p];
+        if (A.first) { A.limit[p] = P.zero_score; A.best_score[p] = 0x7fffffff; }
+        if (P.n < 2) continue;                // n == 1 handled by k_solve_n1
+        uint32_t s = atomicAdd(A.lcount, 1u);
+        uint8_t *rec = A.recs + (size_t)s * A.stride;
+        NodeHdr *h = reinterpret_cast<NodeHdr *>(rec);
+        for (int b = 0; b < AMBI_MAXN; ++b) h->col[b] = b < P.n ? (uint8_t)((AMBI_BUD_INF << 4) | (AMBI_BUD_INF << 6)) : 0;
+        h->score = 0; h->f = P.root_lb; h->prob = p; h->tgs = 0;
+        uint32_t *r = reinterpret_cast<uint32_t *>(rec + sizeof(NodeHdr));
+        for (int k = 0; k < A.nmax; ++k) r[k] = 0;
+        A.list[s] = s;
+    }
 }
+__global__ void k_init_roots(InitRootsArgs A) { init_roots_body(A); }
 
 // Single-segment partitions: no a<b rows exist; P[s,s] in {0,1}, L[s,s] in [0,loop_ub]
 // (LGM:4708-4724); the pattern coefficient of the fold-back row is 0 (LGM:4464-4476).
@@ -837,15 +855,89 @@ __global__ void k_prepare(const DevProblem *probs, int count, int32_t *best_scor
     stamps[(size_t)p * 4] = 0; stamps[(size_t)p * 4 + 1] = 0; stamps[(size_t)p * 4 + 2] = 0; stamps[(size_t)p * 4 + 3] = 0;
 }
 
-__global__ void k_set_limit(const DevProblem *probs, int count, int32_t *limit, const int32_t *best_score,
-                            int32_t *incumbent, const uint8_t *active, int32_t *seen, unsigned long long *stamps)
+struct SetLimitArgs {
+    const DevProblem *probs; int count; int32_t *limit; const int32_t *best_score; int32_t *incumbent;
+    const uint8_t *active; int32_t *seen; unsigned long long *stamps;
+};
+
+__device__ __forceinline__ void set_limit_body(const SetLimitArgs &A)
 {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= count || !active[p]) return;
-    if (best_score[p] < seen[p]) { seen[p] = best_score[p]; stamps[(size_t)p * 4 + 1] = globaltimer_ns(); }   // incumbent of the pass that just ended
-    int z = limit[p], b = best_score[p];       // limit starts at the all-zero score (k_init_roots)
-    int l = b < z ? b : z;
-    limit[p] = l; incumbent[p] = l;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < A.count; p += gridDim.x * blockDim.x) {
+        if (!A.active[p]) continue;
+        if (A.best_score[p] < A.seen[p]) { A.seen[p] = A.best_score[p]; A.stamps[(size_t)p * 4 + 1] = globaltimer_ns(); }   // incumbent of the pass that just ended
+        int z = A.limit[p], b = A.best_score[p];       // limit starts at the all-zero score (k_init_roots)
+        int l = b < z ? b : z;
+        A.limit[p] = l; A.incumbent[p] = l;
+    }
+}
+__global__ void k_set_limit(SetLimitArgs A) { set_limit_body(A); }
+
+// ---------------------------------------------------------------------------
+// The launch sequence of a search as a PROGRAM: a list of operations (one per kernel launch or clear) that is
+// either played as individual launches -- plain, or captured into the CUDA graph that large batches replay --
+// or interpreted by ONE cooperative kernel with a grid-wide barrier between operations (k_program).  A search
+// of a single partition is some 200 dependent operations on frontiers of a few hundred records: launch latency,
+// not work, is what it costs, and the barrier of a small resident grid is several times cheaper than a launch.
+// ---------------------------------------------------------------------------
+enum { OP_MEMSET32 = 0, OP_INIT_ROOTS, OP_EXPAND, OP_DEDUP, OP_FINALIZE, OP_BEAM_HIST, OP_BEAM_CUT, OP_MATERIALISE, OP_SET_LIMIT, OP_BUMP_GEN };
+
+struct MemsetArgs { uint32_t *ptr; unsigned long long words; uint32_t value; };
+
+struct Op {                     // plain data: it is copied to the device and into shared memory word by word
+    int kind;
+    int sync_after;             // the next operation depends on this one (grid barrier / stream order)
+    union {
+        MemsetArgs ms; InitRootsArgs ir; LevelArgs ex; DedupArgs dd; FinalizeArgs fz; BeamArgs bm; MatArgs mt; SetLimitArgs sl; uint32_t *gen;
+    } u;
+};
+
+__global__ void k_memset32(MemsetArgs A)
+{
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.words; i += (unsigned long long)gridDim.x * blockDim.x) A.ptr[i] = A.value;
+}
+
+}  // namespace ambi
+#include <cooperative_groups.h>
+namespace ambi {
+
+// Interpreter: every block walks the same program; an operation is a grid-stride body, followed by a grid barrier.
+// Before an expansion whose frontier has outgrown what this small grid should chew on, the kernel stops and reports
+// the operation it stopped at: the host plays the rest as ordinary full-width launches (same buffers, same counters).
+template <int NMAX, bool SCALED>
+__global__ void __launch_bounds__(WPB * 32, NMAX <= 16 ? 4 : 3)
+k_program(const Op *ops, int first, int n_ops, uint32_t big_frontier, uint32_t *stopped_at)
+{
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __shared__ Op s_op;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int i = first; i < n_ops; ++i) {
+        __syncthreads();
+        if (threadIdx.x < sizeof(Op) / 4) reinterpret_cast<uint32_t *>(&s_op)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&ops[i])[threadIdx.x];
+        __syncthreads();
+        const Op &op = s_op;
+        switch (op.kind) {
+        case OP_MEMSET32:
+            for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < op.u.ms.words; k += (unsigned long long)gridDim.x * blockDim.x) op.u.ms.ptr[k] = op.u.ms.value;
+            break;
+        case OP_INIT_ROOTS: init_roots_body(op.u.ir); break;
+        case OP_EXPAND:
+            if (*op.u.ex.pcount > big_frontier) {               // the same value in every thread: written before the last barrier
+                if (blockIdx.x == 0 && threadIdx.x == 0) *stopped_at = (uint32_t)i;
+                return;
+            }
+            expand_body<NMAX, SCALED>(op.u.ex, s_raw);
+            break;
+        case OP_DEDUP: dedup_body(op.u.dd); break;
+        case OP_FINALIZE: finalize_body(op.u.fz); break;
+        case OP_BEAM_HIST: beam_hist_body(op.u.bm); break;
+        case OP_BEAM_CUT: beam_cut_body(op.u.bm); break;
+        case OP_MATERIALISE: materialise_body(op.u.mt); break;
+        case OP_SET_LIMIT: set_limit_body(op.u.sl); break;
+        case OP_BUMP_GEN: if (blockIdx.x == 0 && threadIdx.x == 0) *op.u.gen += 128u; break;
+        }
+        if (op.sync_after) grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *stopped_at = (uint32_t)n_ops;
 }
 
 // ---------------------------------------------------------------------------
@@ -857,7 +949,7 @@ __global__ void k_set_limit(const DevProblem *probs, int count, int32_t *limit, 
 static uint32_t next_pow2(uint64_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
 // device counters: one set per level so that a whole pass needs a single clear
-enum { CTR_OVERFLOW = 0, CTR_GEN = 1, CTR_SMALL_WORK = 2, CTR_SMALL_FB = 3, CTR_WORK = 8, CTR_CHILD = 8 + 40, CTR_FRONT = 8 + 80, CTR_TOTAL = 8 + 128 };
+enum { CTR_OVERFLOW = 0, CTR_GEN = 1, CTR_SMALL_WORK = 2, CTR_SMALL_FB = 3, CTR_STOP = 4, CTR_WORK = 8, CTR_CHILD = 8 + 40, CTR_FRONT = 8 + 80, CTR_TOTAL = 8 + 128 };
 
 StageA::StageA() { err_[0] = 0; }
 StageA::~StageA() { release(); }
@@ -866,6 +958,7 @@ void StageA::release()
 {
     cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]); cudaFree(kbuf_); cudaFree(lbuf_); kbuf_ = nullptr; lbuf_ = nullptr;
     cudaFree(table_); cudaFree(counters_); cudaFree(d_funnel_); cudaFree(d_flag_); cudaFree(pool_); pool_ = nullptr; d_funnel_ = nullptr; d_flag_ = nullptr;
+    cudaFree(d_prog_); d_prog_ = nullptr; d_prog_cap_ = 0; prog_valid_ = false;
     cudaFree(d_arena_); d_arena_ = nullptr; cudaFree(d_stamp0_); d_stamp0_ = nullptr; cudaFreeHost(h_flag_); h_flag_ = nullptr;
     for (int i = 0; i < 2; ++i) if (ev_small_[i]) { cudaEventDestroy(ev_small_[i]); ev_small_[i] = nullptr; }
     buf_[0] = buf_[1] = nullptr; list_[0] = list_[1] = nullptr; table_ = nullptr;
@@ -945,6 +1038,27 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     expand_blocks_[0] = sms_ * (per_sm > 0 ? per_sm : 1);
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_expand<32, true>, WPB * 32, expand_smem_[1]));
     expand_blocks_[1] = sms_ * (per_sm > 0 ? per_sm : 1);
+    // the fused program kernel (small batches): a small resident grid -- its barrier is what a step costs
+    CK(cudaFuncSetAttribute(k_program<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[0]));
+    CK(cudaFuncSetAttribute(k_program<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[0]));
+    CK(cudaFuncSetAttribute(k_program<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[1]));
+    CK(cudaFuncSetAttribute(k_program<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_[1]));
+    {
+        int coop = 0, dev2 = 0; CK(cudaGetDevice(&dev2));
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev2));
+        fused_on_ = coop != 0;
+        int bps = 2;
+        if (const char *e = getenv("AMBI_FUSED_BPS")) bps = std::max(1, atoi(e));
+        if (const char *e = getenv("AMBI_FUSED_MAX")) fused_max_count_ = atoi(e);
+        if (const char *e = getenv("AMBI_FUSED_BIG")) fused_big_ = (uint32_t)atoll(e);
+        for (int i = 0; i < 2; ++i) {
+            int p2 = 1;
+            if (i == 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, k_program<16, true>, WPB * 32, expand_smem_[0]));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, k_program<32, true>, WPB * 32, expand_smem_[1]));
+            if (p2 < 1) fused_on_ = false;
+            fused_blocks_[i] = sms_ * std::max(1, std::min(bps, p2));
+        }
+    }
     // warp-per-partition kernel for partitions of up to 16 segments (opt-in: AMBI_CFG_SMALL_KERNEL or AMBI_SMALL=1;
     // AMBI_SMALL_C: records per level and warp)
     small_on_ = use_small || getenv("AMBI_SMALL") != nullptr;
@@ -985,6 +1099,7 @@ int StageA::ensure_problem_arrays(int count)
 
 void StageA::drop_graphs()
 {
+    prog_valid_ = false;
     if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
     if (graph_exec2_) { cudaGraphExecDestroy(graph_exec2_); graph_exec2_ = nullptr; }
 }
@@ -1036,6 +1151,61 @@ int StageA::upload(const DevProblem *host_probs, int count)
     return 0;
 }
 
+// ---- operations: recorded into a program (rec_ set) or launched at once -------------------------------------
+int StageA::op(const Op &o)
+{
+    if (rec_) { rec_->push_back(o); return 0; }
+    return launch_op(o);
+}
+
+int StageA::launch_op(const Op &o)
+{
+    const int tpb = 128, pblocks = (count_ + tpb - 1) / tpb;
+    switch (o.kind) {
+    case OP_MEMSET32: CK(cudaMemsetAsync(o.u.ms.ptr, (int)(o.u.ms.value & 0xffu), (size_t)o.u.ms.words * 4, stream_)); return 0;   // 0 or 0x7f7f7f7f
+    case OP_INIT_ROOTS: k_init_roots<<<pblocks, tpb, 0, stream_>>>(o.u.ir); break;
+    case OP_EXPAND: launch_expand(o.u.ex); return 0;
+    case OP_DEDUP: k_dedup<<<sms_ * 8, 256, 0, stream_>>>(o.u.dd); break;
+    case OP_FINALIZE: k_finalize<<<sms_ * 8, 256, 0, stream_>>>(o.u.fz); break;
+    case OP_BEAM_HIST: k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(o.u.bm); break;
+    case OP_BEAM_CUT: k_beam_cut<<<pblocks, tpb, 0, stream_>>>(o.u.bm); break;
+    case OP_MATERIALISE: k_materialise<<<sms_ * 8, 256, 0, stream_>>>(o.u.mt); break;
+    case OP_SET_LIMIT: k_set_limit<<<pblocks, tpb, 0, stream_>>>(o.u.sl); break;
+    case OP_BUMP_GEN: k_bump_gen<<<1, 1, 0, stream_>>>(o.u.gen); break;
+    }
+    ++launches_;
+    return 0;
+}
+
+int StageA::op_memset(void *ptr, int byte, size_t bytes)
+{
+    Op o; memset(&o, 0, sizeof o);
+    o.kind = OP_MEMSET32; o.sync_after = 1;
+    o.u.ms.ptr = static_cast<uint32_t *>(ptr); o.u.ms.words = bytes / 4; o.u.ms.value = 0x01010101u * (uint32_t)(byte & 0xff);
+    return op(o);
+}
+
+// The whole search as one cooperative kernel (k_program) for small batches; what it leaves (a frontier too wide for
+// its small grid) is played as ordinary launches.  [first, last) index the recorded program.
+int StageA::run_fused(int first, int last)
+{
+    const int idx = nmax_ <= 16 ? 0 : 1;
+    const Op *d_ops = d_prog_;
+    uint32_t *d_stop = counters_ + CTR_STOP;
+    uint32_t big = fused_big_;
+    void *args[] = {(void *)&d_ops, (void *)&first, (void *)&last, (void *)&big, (void *)&d_stop};
+    const void *fn = nmax_ <= 16 ? (scaled_ ? (const void *)k_program<16, true> : (const void *)k_program<16, false>)
+                                 : (scaled_ ? (const void *)k_program<32, true> : (const void *)k_program<32, false>);
+    CK(cudaLaunchCooperativeKernel(fn, dim3(fused_blocks_[idx]), dim3(WPB * 32), args, expand_smem_[idx], stream_));
+    ++launches_;
+    CK(cudaMemcpyAsync(h_flag_ + 1, d_stop, 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    const int stopped = (int)h_flag_[1];
+    fused_stops_ += stopped < last;
+    for (int i = stopped; i < last; ++i) if (int rc = launch_op(prog_[i])) return rc;
+    return 0;
+}
+
 void StageA::launch_expand(const LevelArgs &L)
 {
     // four instantiations: 16 / 32 staged columns x copy numbers in half copies / in finer units (only when some
@@ -1073,19 +1243,19 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
         if (prof_used_ + 2 > prof_ev_.size()) { cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); prof_ev_.push_back(e0); prof_ev_.push_back(e1); }
         CK(cudaEventRecord(prof_ev_[prof_used_], stream_));
     }
-    launch_expand(L);
+    { Op o; memset(&o, 0, sizeof o); o.kind = OP_EXPAND; o.sync_after = 1; o.u.ex = L; if (int rc = op(o)) return rc; }
     if (prof) { CK(cudaEventRecord(prof_ev_[prof_used_ + 1], stream_)); prof_used_ += 2; }
     const bool beam = mode == 1;
     int32_t *fmin_cur = d_fmin_ + (size_t)level * count_;
     uint32_t *hist = d_hist_;
-    if (beam) CK(cudaMemsetAsync(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4, stream_));
+    if (beam) { if (int rc = op_memset(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4)) return rc; }
     if (merge) {
         DedupArgs D;
         D.recs = kbuf_; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = kstride_; D.level = level; D.overflow = c_over;
         D.probs = d_probs_; D.fmin_cur = beam ? fmin_cur : nullptr; D.nmax = nmax_;
         D.links = lbuf_; D.parents = buf_[cur]; D.pstride = stride_;
-        k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
+        { Op o; memset(&o, 0, sizeof o); o.kind = OP_DEDUP; o.sync_after = 1; o.u.dd = D; if (int rc = op(o)) return rc; }
     }
     FinalizeArgs F;
     F.probs = d_probs_; F.recs = kbuf_; F.count = c_child; F.cap = cap_;
@@ -1095,7 +1265,8 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     F.limit = nullptr; F.merge_best = 0; F.build_list = 0; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
     F.links = lbuf_; F.parents = buf_[cur]; F.pstride = stride_;
     // this kernel only collects completed assignments: skip the levels where no problem ends
-    if ((leaf_levels_ >> level) & 1u) { k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_; }
+    // (it reads what the merge left and writes per-problem results only: no barrier needed before the next operation)
+    if ((leaf_levels_ >> level) & 1u) { Op o; memset(&o, 0, sizeof o); o.kind = OP_FINALIZE; o.sync_after = 0; o.u.fz = F; if (int rc = op(o)) return rc; }
     MatArgs M;
     M.probs = d_probs_; M.keys = kbuf_; M.links = lbuf_; M.count = c_child; M.cap = cap_; M.parents = buf_[cur]; M.pstride = stride_;
     M.out = buf_[cur ^ 1]; M.out_count = c_nxt; M.out_cap = cap_; M.kstride = kstride_; M.level = level; M.nmax = nmax_; M.overflow = c_over;
@@ -1107,11 +1278,12 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
         B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = nullptr;
         B.next_count = nullptr; B.nprob = count_; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1)));
         B.stride = kstride_; B.level = level; B.growth = beam_growth_; B.width_div = beam_div_;
-        k_beam_hist<<<sms_ * 8, 256, 0, stream_>>>(B); ++launches_;
-        k_beam_cut<<<(count_ + 127) / 128, 128, 0, stream_>>>(B); ++launches_;
+        { Op o; memset(&o, 0, sizeof o); o.kind = OP_BEAM_HIST; o.sync_after = 1; o.u.bm = B; if (int rc = op(o)) return rc; }
+        { Op o; memset(&o, 0, sizeof o); o.kind = OP_BEAM_CUT; o.sync_after = 1; o.u.bm = B; if (int rc = op(o)) return rc; }
         M.fmin = fmin_cur; M.cutq = B.cutq; M.ticket = B.ticket;          // the selection itself happens while materialising
     }
-    if (level + 1 < nmax_) { k_materialise<<<sms_ * 8, 256, 0, stream_>>>(M); ++launches_; }
+    if (level + 1 < nmax_) { Op o; memset(&o, 0, sizeof o); o.kind = OP_MATERIALISE; o.sync_after = 1; o.u.mt = M; if (int rc = op(o)) return rc; }
+    else if (rec_ && !rec_->empty()) rec_->back().sync_after = 1;      // the pass ends here
     return 0;
 }
 
@@ -1119,13 +1291,18 @@ int StageA::run_pass(int mode, int shard_world, bool first)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
     // everything but the overflow flag
-    CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
+    (void)blocks;
+    if (int rc = op_memset(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t))) return rc;
     if (mode == 1) {
-        CK(cudaMemsetAsync(d_fmin_, 0x7f, (size_t)count_ * 4 * nmax_, stream_));
-        CK(cudaMemsetAsync(d_ticket_, 0, (size_t)count_ * 4 * nmax_, stream_));
+        if (int rc = op_memset(d_fmin_, 0x7f, (size_t)count_ * 4 * nmax_)) return rc;
+        if (int rc = op_memset(d_ticket_, 0, (size_t)count_ * 4 * nmax_)) return rc;
     }
-    k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, buf_[0], stride_, nmax_, list_[0],
-                                              counters_ + CTR_FRONT, d_limit_, d_best_score_, first ? 1 : 0, d_active_); ++launches_;
+    {
+        Op o; memset(&o, 0, sizeof o); o.kind = OP_INIT_ROOTS; o.sync_after = 1;
+        o.u.ir.probs = d_probs_; o.u.ir.count = count_; o.u.ir.recs = buf_[0]; o.u.ir.stride = stride_; o.u.ir.nmax = nmax_; o.u.ir.list = list_[0];
+        o.u.ir.lcount = counters_ + CTR_FRONT; o.u.ir.limit = d_limit_; o.u.ir.best_score = d_best_score_; o.u.ir.first = first ? 1 : 0; o.u.ir.active = d_active_;
+        if (int rc = op(o)) return rc;
+    }
     int cur = 0;
     for (int a = 0; a < nmax_; ++a) { if (int rc = run_level(a, cur, mode, shard_world)) return rc; cur ^= 1; }
     return 0;
@@ -1138,16 +1315,19 @@ int StageA::run_pass(int mode, int shard_world, bool first)
 int StageA::enqueue_incumbent(bool coop)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
-    CK(cudaMemsetAsync(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t), stream_));
-    k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
-    CK(cudaMemsetAsync(d_beam_score_, 0x7f, (size_t)count_ * 4, stream_));
+    (void)blocks;
+    if (int rc = op_memset(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t))) return rc;
+    { Op o; memset(&o, 0, sizeof o); o.kind = OP_BUMP_GEN; o.sync_after = 1; o.u.gen = counters_ + CTR_GEN; if (int rc = op(o)) return rc; }
+    if (int rc = op_memset(d_beam_score_, 0x7f, (size_t)count_ * 4)) return rc;
     shard_level_eff_ = -1;
     // ---- pass 0: greedy dive -> first incumbent (limit starts at the all-zero score)
     if (int rc = run_pass(0, 1, true)) return rc;
-    k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_, d_active_, d_seen_, d_stamps_); ++launches_;
+    { Op o; memset(&o, 0, sizeof o); o.kind = OP_SET_LIMIT; o.sync_after = 1; o.u.sl.probs = d_probs_; o.u.sl.count = count_; o.u.sl.limit = d_limit_;
+      o.u.sl.best_score = d_beam_score_; o.u.sl.incumbent = d_incumbent_; o.u.sl.active = d_active_; o.u.sl.seen = d_seen_; o.u.sl.stamps = d_stamps_;
+      if (int rc = op(o)) return rc; }
     // ---- pass 1: beam of width W inside that limit -> tighter incumbent
     if (beam_ > 1) {
-        CK(cudaMemsetAsync(d_beam_score_, 0x7f, (size_t)count_ * 4, stream_));
+        if (int rc = op_memset(d_beam_score_, 0x7f, (size_t)count_ * 4)) return rc;
         beam_div_ = 1;
         if (coop) {
             int sl = shard_level_ > 0 ? shard_level_ : 2;
@@ -1164,7 +1344,10 @@ int StageA::enqueue_incumbent(bool coop)
 int StageA::enqueue_exact(bool sharded)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
-    if (beam_ > 1) { k_set_limit<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, d_limit_, d_beam_score_, d_incumbent_, d_active_, d_seen_, d_stamps_); ++launches_; }
+    (void)blocks;
+    if (beam_ > 1) { Op o; memset(&o, 0, sizeof o); o.kind = OP_SET_LIMIT; o.sync_after = 1; o.u.sl.probs = d_probs_; o.u.sl.count = count_; o.u.sl.limit = d_limit_;
+      o.u.sl.best_score = d_beam_score_; o.u.sl.incumbent = d_incumbent_; o.u.sl.active = d_active_; o.u.sl.seen = d_seen_; o.u.sl.stamps = d_stamps_;
+      if (int rc = op(o)) return rc; }
     if (!capturing_) CK(cudaEventRecord(ev_[1], stream_));
     int sw = sharded ? world_ : 1;
     shard_level_eff_ = -1;
@@ -1249,6 +1432,36 @@ int StageA::run(bool sharded)
     if (use_graph && graph_exec_ && graph_mode_ != mode) {
         cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr;
         if (graph_exec2_) { cudaGraphExecDestroy(graph_exec2_); graph_exec2_ = nullptr; }
+    }
+    // small batches: the whole launch sequence as one cooperative kernel (latency, not work, is what they cost)
+    const bool fused = fused_on_ && !profile_ && global_count_ <= fused_max_count_ && getenv("AMBI_NO_FUSED") == nullptr;
+    if (fused) {
+        if (!prog_valid_ || prog_mode_ != mode) {
+            prog_.clear();
+            rec_ = &prog_; capturing_ = true;
+            int rc = enqueue_incumbent(coop);
+            prog_split_ = (int)prog_.size();
+            if (!rc) rc = enqueue_exact(sharded);
+            rec_ = nullptr; capturing_ = false;
+            if (rc) return rc;
+            if (prog_.size() > d_prog_cap_) {
+                cudaFree(d_prog_); d_prog_ = nullptr; d_prog_cap_ = 0;
+                CK(cudaMalloc(&d_prog_, prog_.size() * sizeof(Op)));
+                d_prog_cap_ = prog_.size();
+            }
+            CK(cudaMemcpyAsync(d_prog_, prog_.data(), prog_.size() * sizeof(Op), cudaMemcpyHostToDevice, stream_));
+            CK(cudaStreamSynchronize(stream_));
+            prog_valid_ = true; prog_mode_ = mode;
+        }
+        if (!coop) { if (int rc = run_fused(0, (int)prog_.size())) return rc; }
+        else {
+            if (int rc = run_fused(0, prog_split_)) return rc;
+            if (allreduce_(allreduce_user_, d_beam_score_, count_, 0)) { snprintf(err_, sizeof err_, "incumbent all-reduce(min) failed"); return -4; }
+            if (int rc = run_fused(prog_split_, (int)prog_.size())) return rc;
+        }
+        used_graph_ = true;                 // (no per-pass events in this mode either)
+        CK(cudaEventRecord(ev_[2], stream_));
+        return 0;
     }
     if (!coop) {
         if (!use_graph) {
@@ -1358,8 +1571,11 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
     } else {
         // roots -> pool
         CK(cudaMemsetAsync(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t), stream_));
-        k_init_roots<<<blocks, tpb, 0, stream_>>>(d_probs_, count_, pool_, stride_, nmax_, list_[0],
-                                                  counters_ + CTR_FRONT, d_limit_, d_best_score_, 0, d_active_); ++launches_;
+        {
+            InitRootsArgs ir; ir.probs = d_probs_; ir.count = count_; ir.recs = pool_; ir.stride = stride_; ir.nmax = nmax_; ir.list = list_[0];
+            ir.lcount = counters_ + CTR_FRONT; ir.limit = d_limit_; ir.best_score = d_best_score_; ir.first = 0; ir.active = d_active_;
+            k_init_roots<<<blocks, tpb, 0, stream_>>>(ir); ++launches_;
+        }
         CK(cudaMemcpyAsync(&nroots, counters_ + CTR_FRONT, 4, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
         if (nroots > 0) stack.push_back({0, 0, nroots, 0});

@@ -7,6 +7,7 @@
 namespace ambi {
 
 struct LevelArgs;
+struct Op;
 
 struct HostResult {
     int64_t score2;
@@ -49,6 +50,7 @@ public:
     int global_solved() const { return global_count_; }
     double small_ms() const { return prof_small_ms_; }
     int small_capacity() const { return small_cfg_.C; }
+    unsigned long long fused_stops() const { return fused_stops_; }
     // per-kernel timing (CUDA events around every k_expand launch; adds launch gaps, so only
     // enabled for the bench's roofline pass)
     void set_profile(bool on) { profile_ = on; }
@@ -70,6 +72,10 @@ private:
     void free_problem_arrays();
     int run_level(int level, int cur, int mode, int shard_world);
     void launch_expand(const LevelArgs &L);
+    int op(const Op &o);
+    int launch_op(const Op &o);
+    int op_memset(void *ptr, int byte, size_t bytes);
+    int run_fused(int first, int last);
     int run_pass(int mode, int shard_world, bool first);
     int enqueue_incumbent(bool coop);
     int enqueue_exact(bool sharded);
@@ -140,6 +146,16 @@ private:
     double prof_small_ms_ = 0;
     cudaEvent_t ev_small_[2] = {nullptr, nullptr};
     int prepare();
+    // the launch sequence as a program (stage_a.cu "The launch sequence of a search as a PROGRAM")
+    std::vector<Op> *rec_ = nullptr;
+    std::vector<Op> prog_;
+    Op *d_prog_ = nullptr;
+    size_t d_prog_cap_ = 0;
+    int prog_split_ = 0, prog_mode_ = -1;
+    bool prog_valid_ = false, fused_on_ = false;
+    int fused_max_count_ = 64, fused_blocks_[2] = {148, 148};
+    uint32_t fused_big_ = 32768;
+    unsigned long long fused_stops_ = 0;
     unsigned long long exchange_rounds_ = 0;
     char err_[256];
 };
