@@ -1057,6 +1057,7 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
             else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, k_program<32, true>, WPB * 32, expand_smem_[1]));
             if (p2 < 1) fused_on_ = false;
             fused_blocks_[i] = sms_ * std::max(1, std::min(bps, p2));
+            if (const char *e = getenv("AMBI_FUSED_BLOCKS")) fused_blocks_[i] = std::max(1, std::min(atoi(e), sms_ * p2));
         }
     }
     // warp-per-partition kernel for partitions of up to 16 segments (opt-in: AMBI_CFG_SMALL_KERNEL or AMBI_SMALL=1;
@@ -1177,10 +1178,10 @@ int StageA::launch_op(const Op &o)
     return 0;
 }
 
-int StageA::op_memset(void *ptr, int byte, size_t bytes)
+int StageA::op_memset(void *ptr, int byte, size_t bytes, bool sync_after)
 {
     Op o; memset(&o, 0, sizeof o);
-    o.kind = OP_MEMSET32; o.sync_after = 1;
+    o.kind = OP_MEMSET32; o.sync_after = sync_after ? 1 : 0;
     o.u.ms.ptr = static_cast<uint32_t *>(ptr); o.u.ms.words = bytes / 4; o.u.ms.value = 0x01010101u * (uint32_t)(byte & 0xff);
     return op(o);
 }
@@ -1248,7 +1249,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     const bool beam = mode == 1;
     int32_t *fmin_cur = d_fmin_ + (size_t)level * count_;
     uint32_t *hist = d_hist_;
-    if (beam) { if (int rc = op_memset(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4)) return rc; }
+    if (beam) { if (int rc = op_memset(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4, false)) return rc; }     // used after the merge's barrier
     if (merge) {
         DedupArgs D;
         D.recs = kbuf_; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
@@ -1292,11 +1293,11 @@ int StageA::run_pass(int mode, int shard_world, bool first)
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
     // everything but the overflow flag
     (void)blocks;
-    if (int rc = op_memset(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t))) return rc;
-    if (mode == 1) {
-        if (int rc = op_memset(d_fmin_, 0x7f, (size_t)count_ * 4 * nmax_)) return rc;
-        if (int rc = op_memset(d_ticket_, 0, (size_t)count_ * 4 * nmax_)) return rc;
+    if (mode == 1) {        // (independent clears share the barrier of the last one)
+        if (int rc = op_memset(d_fmin_, 0x7f, (size_t)count_ * 4 * nmax_, false)) return rc;
+        if (int rc = op_memset(d_ticket_, 0, (size_t)count_ * 4 * nmax_, false)) return rc;
     }
+    if (int rc = op_memset(counters_ + CTR_WORK, 0, (CTR_TOTAL - CTR_WORK) * sizeof(uint32_t))) return rc;
     {
         Op o; memset(&o, 0, sizeof o); o.kind = OP_INIT_ROOTS; o.sync_after = 1;
         o.u.ir.probs = d_probs_; o.u.ir.count = count_; o.u.ir.recs = buf_[0]; o.u.ir.stride = stride_; o.u.ir.nmax = nmax_; o.u.ir.list = list_[0];
@@ -1316,9 +1317,9 @@ int StageA::enqueue_incumbent(bool coop)
 {
     const int tpb = 128, blocks = (count_ + tpb - 1) / tpb;
     (void)blocks;
-    if (int rc = op_memset(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t))) return rc;
-    { Op o; memset(&o, 0, sizeof o); o.kind = OP_BUMP_GEN; o.sync_after = 1; o.u.gen = counters_ + CTR_GEN; if (int rc = op(o)) return rc; }
-    if (int rc = op_memset(d_beam_score_, 0x7f, (size_t)count_ * 4)) return rc;
+    if (int rc = op_memset(counters_ + CTR_OVERFLOW, 0, sizeof(uint32_t), false)) return rc;
+    { Op o; memset(&o, 0, sizeof o); o.kind = OP_BUMP_GEN; o.sync_after = 0; o.u.gen = counters_ + CTR_GEN; if (int rc = op(o)) return rc; }
+    if (int rc = op_memset(d_beam_score_, 0x7f, (size_t)count_ * 4, false)) return rc;      // (run_pass ends its clears with a barrier)
     shard_level_eff_ = -1;
     // ---- pass 0: greedy dive -> first incumbent (limit starts at the all-zero score)
     if (int rc = run_pass(0, 1, true)) return rc;
@@ -1327,7 +1328,7 @@ int StageA::enqueue_incumbent(bool coop)
       if (int rc = op(o)) return rc; }
     // ---- pass 1: beam of width W inside that limit -> tighter incumbent
     if (beam_ > 1) {
-        if (int rc = op_memset(d_beam_score_, 0x7f, (size_t)count_ * 4)) return rc;
+        if (int rc = op_memset(d_beam_score_, 0x7f, (size_t)count_ * 4, false)) return rc;
         beam_div_ = 1;
         if (coop) {
             int sl = shard_level_ > 0 ? shard_level_ : 2;

@@ -74,7 +74,7 @@ private:
     void launch_expand(const LevelArgs &L);
     int op(const Op &o);
     int launch_op(const Op &o);
-    int op_memset(void *ptr, int byte, size_t bytes);
+    int op_memset(void *ptr, int byte, size_t bytes, bool sync_after = true);
     int run_fused(int first, int last);
     int run_pass(int mode, int shard_world, bool first);
     int enqueue_incumbent(bool coop);
@@ -153,7 +153,7 @@ private:
     size_t d_prog_cap_ = 0;
     int prog_split_ = 0, prog_mode_ = -1;
     bool prog_valid_ = false, fused_on_ = false;
-    int fused_max_count_ = 64, fused_blocks_[2] = {148, 148};
+    int fused_max_count_ = 0, fused_blocks_[2] = {148, 148};      // 0: off (measured no faster than graph replay; AMBI_FUSED_MAX=64 turns it on)
     uint32_t fused_big_ = 32768;
     unsigned long long fused_stops_ = 0;
     unsigned long long exchange_rounds_ = 0;

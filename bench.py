@@ -44,11 +44,12 @@ def host_threads() -> int:
 
 def profiled_traffic():
     """dram bytes per k_expand launch from the committed ncu capture of this round (profiles/)"""
-    p = os.path.join(ROOT, "profiles", "r01_launches_summary.json")
-    try:
-        return float(json.load(open(p))["k_expand"]["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r02_launches_summary.json", "r01_launches_summary.json"):
+        try:
+            return float(json.load(open(os.path.join(ROOT, "profiles", name)))["k_expand"]["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def measured_peaks():

@@ -290,6 +290,25 @@ def test_units_vs_oracle_and_scale_invariance(ctx, unit):
         assert b.score2 == unit * a.score2 and np.array_equal(a.element_cn, b.element_cn)
 
 
+def test_program_in_one_cooperative_kernel_gives_the_same_answers(monkeypatch):
+    """AMBI_FUSED_MAX: batches of up to that many partitions run their whole launch sequence inside one cooperative
+    kernel (k_program), stopping where a frontier outgrows its small grid; same answers as launch by launch"""
+    probs = [lh.problem_from_lh(synth.generate(n, f, 70 + s, 0.5).lh_text()) for (n, f) in [(6, 3), (12, 4), (16, 5), (20, 6)] for s in range(3)]
+    monkeypatch.setenv("AMBI_FUSED_MAX", "64")
+    monkeypatch.setenv("AMBI_FUSED_BIG", "2048")
+    with capi.Context(device=0) as c:
+        fused = [c.solve(p) for p in probs] + c.solve_batch(probs)
+    monkeypatch.delenv("AMBI_FUSED_MAX")
+    with capi.Context(device=0, node_capacity=4096) as c:
+        monkeypatch.setenv("AMBI_FUSED_MAX", "64")
+    for p, s in zip(probs + probs, fused):
+        check_against_oracle(p, s)
+    monkeypatch.setenv("AMBI_FUSED_MAX", "64")
+    with capi.Context(device=0, node_capacity=4096) as c:          # overflow inside the cooperative kernel -> chunked pass
+        for p in probs[-3:]:
+            check_against_oracle(p, c.solve(p))
+
+
 def test_bad_arguments(ctx):
     with pytest.raises(capi.AmbiError):
         ctx.solve(Problem(n=33, seg_cn2=[2] * 33, fbi_cn2=[0] * 33))
