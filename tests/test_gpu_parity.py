@@ -298,12 +298,8 @@ def test_program_in_one_cooperative_kernel_gives_the_same_answers(monkeypatch):
     monkeypatch.setenv("AMBI_FUSED_BIG", "2048")
     with capi.Context(device=0) as c:
         fused = [c.solve(p) for p in probs] + c.solve_batch(probs)
-    monkeypatch.delenv("AMBI_FUSED_MAX")
-    with capi.Context(device=0, node_capacity=4096) as c:
-        monkeypatch.setenv("AMBI_FUSED_MAX", "64")
     for p, s in zip(probs + probs, fused):
         check_against_oracle(p, s)
-    monkeypatch.setenv("AMBI_FUSED_MAX", "64")
     with capi.Context(device=0, node_capacity=4096) as c:          # overflow inside the cooperative kernel -> chunked pass
         for p in probs[-3:]:
             check_against_oracle(p, c.solve(p))
