@@ -23,19 +23,19 @@ namespace ambi {
 namespace dec {
 
 constexpr int L0CAP = 16;               // class-0 loop multisets listed per record (more: decoded the slow way)
-constexpr int CFGN = 63;                // "no column" in a packed configuration
+constexpr uint32_t ENTRY_VALID = 0x80000000u;    // queue entry: ENTRY_VALID | slot << 24 | packed configuration
 
 __device__ __forceinline__ uint32_t below(int b) { return (1u << b) - 1u; }
 __device__ __forceinline__ int nth_bit_slow(uint32_t m, int k) { for (; k > 0; --k) m &= m - 1; return __ffs((int)m) - 1; }
-// packed row configuration: p1 | p2<<6 | l1<<12 | l2<<18 (columns, CFGN = absent; p1<p2, l1<=l2)
+// packed row configuration: four 6-bit fields holding column + 1 (0 = absent; p1<p2, l1<=l2), so that a field decodes
+// with one subtraction
 __device__ __forceinline__ uint32_t pack_cfg(int p1, int p2, int l1, int l2)
 {
-    return (uint32_t)(p1 & 63) | ((uint32_t)(p2 & 63) << 6) | ((uint32_t)(l1 & 63) << 12) | ((uint32_t)(l2 & 63) << 18);
+    return (uint32_t)(p1 + 1) | ((uint32_t)(p2 + 1) << 6) | ((uint32_t)(l1 + 1) << 12) | ((uint32_t)(l2 + 1) << 18);
 }
 __device__ __forceinline__ void unpack_cfg(uint32_t c, int &p1, int &p2, int &l1, int &l2)
 {
-    p1 = c & 63; p2 = (c >> 6) & 63; l1 = (c >> 12) & 63; l2 = (c >> 18) & 63;
-    p1 = p1 == CFGN ? -1 : p1; p2 = p2 == CFGN ? -1 : p2; l1 = l1 == CFGN ? -1 : l1; l2 = l2 == CFGN ? -1 : l2;
+    p1 = (int)(c & 63u) - 1; p2 = (int)((c >> 6) & 63u) - 1; l1 = (int)((c >> 12) & 63u) - 1; l2 = (int)((c >> 18) & 63u) - 1;
 }
 
 // Phase 1, lane = record: number of configurations of a record with these masks (nl0 = class-0 loop multisets).
@@ -83,7 +83,7 @@ __device__ __forceinline__ void write_lists(SH &S, int slot, uint32_t okP, uint3
 // Lane = candidate: decode configuration number r of record `slot` and run the light test (rows 2/4/5 inside the
 // row, third-generation row `tm` with the record's running count, exact deviation of segment a through the
 // record's d0 = 2 cov_a - 2c_a and f0 = fb_a - 2J_a, and the O(1) prefilter lslack = slack - own bound).
-// Returns slot << 24 | cfg, or 0 when structurally infeasible; *pass = within the limit.
+// Returns ENTRY_VALID | slot << 24 | cfg, or 0 when structurally infeasible; *pass = within the limit.
 // `ush`: copy numbers are in units of 1/(2 << ush) copies (0 in the half-copy instantiations: the shifts fold away).
 template <class SH>
 __device__ __forceinline__ uint32_t decode_light(const SH &S, int slot, uint32_t r, uint32_t tm, int ush, bool *pass)
@@ -150,14 +150,25 @@ __device__ __forceinline__ uint32_t decode_light(const SH &S, int slot, uint32_t
     // never below the record's.  Sharper: on a segment whose committed coverage already reaches its copy number
     // (over: 2 cov_j >= 2c_j), every copy this row adds costs exactly 2 more, and likewise for the fold-back count of
     // a column that already reaches 2J_j (fover) -- both terms of the record's bound are exact there.
-    const uint32_t ov = S.over[slot], fo = S.fover[slot];
-    int extra = 0, fextra = 0;
-    if (p1 >= 0) { extra += __popc(ov & below(p1 + 1)); fextra += (fo >> p1) & 1; }
-    if (p2 >= 0) { extra += __popc(ov & below(p2 + 1)); fextra += (fo >> p2) & 1; }
-    if (l1 >= 0) { extra += 2 * __popc(ov & below(l1 + 1)); fextra += 2 * ((fo >> l1) & 1); }
-    if (l2 >= 0) { extra += 2 * __popc(ov & below(l2 + 1)); fextra += 2 * ((fo >> l2) & 1); }
-    *pass = err + (extra << (ush + 1)) + (fextra << ush) <= S.lslack[slot];
-    return ((uint32_t)slot << 24) | pack_cfg(p1, p2, l1, l2);
+    // (fill_ovt() below tabulates the two masks per record.)
+    // ovt[slot][1 + e] = 2 * (such segments in (a, e]) + (column e is such a fold-back column), ovt[slot][0] = 0 for an
+    // absent end (-1): four table reads on the load/store pipe instead of four population counts on the alu pipe
+    const uint8_t *t = S.ovt[slot];
+    const int extra = (int)t[1 + p1] + (int)t[1 + p2] + 2 * ((int)t[1 + l1] + (int)t[1 + l2]);
+    *pass = err + (extra << ush) <= S.lslack[slot];
+    return ENTRY_VALID | ((uint32_t)slot << 24) | pack_cfg(p1, p2, l1, l2);
+}
+
+// Phase 1, lane = record: the prefilter table of decode_light from the record's masks `over` (segments j > a whose
+// committed coverage already reaches 2c_j) and `fover` (columns whose fold-back count already reaches 2J_j).
+template <class SH>
+__device__ __forceinline__ void fill_ovt(SH &S, int slot, uint32_t over, uint32_t fover, int n)
+{
+    uint8_t *t = S.ovt[slot];
+    t[0] = 0;
+    int run = 0;
+#pragma unroll 1
+    for (int e = 0; e < n; ++e) { run += (int)((over >> e) & 1u); t[1 + e] = (uint8_t)(2 * run + (int)((fover >> e) & 1u)); }
 }
 
 // Owner of candidate cb0 + lane by a run-length walk over the records' candidate ranges: s0 = record that owns

@@ -64,7 +64,7 @@ struct Fixed {
     uint32_t okP[32], parP[32], okL1[32], A2m[32], par1[32];
     int32_t  score[32], slack[32], lslack[32], d0[32], f0[32], ptgs[32], frec[32];
     uint32_t nl0[32], cstart[33], rank[32];
-    uint32_t over[32], fover[32];      // columns j > a whose committed coverage / fold-back count already reaches 2c_j / 2J_j
+    uint8_t  ovt[32][MAXN_SMALL + 4];   // prefilter table of decode_light (decode_common.cuh fill_ovt)
     uint8_t  posP[32][MAXN_SMALL], posE[32][MAXN_SMALL];    // positions of the set bits of okP / E, lowest first
     uint16_t L0[32][L0CAP];                                 // class-0 loop multisets: low | high << 8 (0xff: none)
     uint32_t qh[64], qw_cfg[64];
@@ -209,7 +209,7 @@ __device__ __noinline__ uint32_t phase1(Fixed &S, const Arr &R, int lane)
         }
     }
 #endif
-    S.over[lane] = over; S.fover[lane] = fover;
+    dec::fill_ovt(S, lane, over, fover, n);
     const uint32_t cja = S.cj[a];
     uint32_t total = 0, nl0 = 0;
     if (have && slack >= 0) total = dec::count_configs(okP, parP, okL1, okL2, par1, par2, &nl0);
@@ -236,7 +236,7 @@ __device__ __noinline__ int heavy_batch(Fixed &S, const Arr &R, int count, int q
     const int a = S.a, n = S.n;
     const bool act = lane < count;
     const uint32_t e = act ? S.qh[lane] : 0u;
-    const int slot = e >> 24;
+    const int slot = (e >> 24) & 31;
     const uint32_t cfg = e & 0xffffffu;
     int p1, p2, l1, l2; unpack_cfg(cfg, p1, p2, l1, l2);
     const uint4 s = R.st[min(S.g0 + slot, S.m - 1)];
@@ -295,7 +295,7 @@ __device__ __noinline__ void merge_batch(Fixed &S, const Arr &R, int count, int 
     const int a = S.a, n = S.n;
     const bool act = lane < count;
     uint32_t cfg = 0; int err = 0, tot = 0, slot = 0;
-    if (act) { const uint32_t e = S.qw_cfg[lane]; slot = e >> 24; cfg = e & 0xffffffu; err = S.qw_err[lane]; tot = S.qw_tot[lane]; }
+    if (act) { const uint32_t e = S.qw_cfg[lane]; slot = (e >> 24) & 31; cfg = e & 0xffffffu; err = S.qw_err[lane]; tot = S.qw_tot[lane]; }
     int p1, p2, l1, l2; unpack_cfg(cfg, p1, p2, l1, l2);
     const int pidx = min(S.g0 + slot, S.m - 1);
     const uint4 ps = R.st[pidx];

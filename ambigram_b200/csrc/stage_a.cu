@@ -85,7 +85,7 @@ struct GroupShared {
     uint32_t okL1[GRP], A2m[GRP];       // column may take one loop end / two loop ends and has two parents
     uint32_t par1[GRP];                 // column already holds >= 1 parent for a loop (row 3)
     uint32_t tmask[GRP];                // third-generation cells of this row
-    uint32_t over[GRP], fover[GRP];     // columns j > a whose committed coverage / fold-back count already reaches 2c_j / 2J_j
+    uint8_t  ovt[GRP][NMAX + 4];        // prefilter table of decode_light (decode_common.cuh fill_ovt)
     int32_t  score[GRP], slack[GRP], ptgs[GRP], prob[GRP];
     int32_t  d0[GRP], f0[GRP];          // 2 cov_a - 2c_a and fb_a - 2J_a before the row's own entries
     int32_t  lslack[GRP];               // slack minus the record's own bound on segments > a (light-test limit)
@@ -171,7 +171,7 @@ __device__ __noinline__ int heavy_batch(GroupShared<NMAX> &S, const LevelArgs &A
     const int a = A.level;
     const bool act = lane < count;
     const uint32_t e = act ? S.qh[lane] : 0u;
-    const int slot = e >> 24;
+    const int slot = (e >> 24) & 31;
     const uint32_t cfg = e & 0xffffffu;
     int p1, p2, l1, l2; unpack_cfg(cfg, p1, p2, l1, l2);
     int err = 0, tot = 0; bool keep = false;
@@ -201,7 +201,7 @@ __device__ __noinline__ void write_batch(GroupShared<NMAX> &S, const LevelArgs &
     const int a = A.level;
     const bool act = lane < count;
     uint32_t cfg = 0; int err = 0, tot = 0, slot = 0;
-    if (act) { const uint32_t e = S.qw_cfg[lane]; slot = e >> 24; cfg = e & 0xffffffu; err = S.qw_err[lane]; tot = S.qw_tot[lane]; }
+    if (act) { const uint32_t e = S.qw_cfg[lane]; slot = (e >> 24) & 31; cfg = e & 0xffffffu; err = S.qw_err[lane]; tot = S.qw_tot[lane]; }
     int p1, p2, l1, l2; unpack_cfg(cfg, p1, p2, l1, l2);
     const int n = S.n[slot];
     bool wr = act;
@@ -385,7 +385,7 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
                 pf += f > 0 ? f : max(0, -f - ((cap + min(capsum, 6)) << ush));
                 over |= (uint32_t)(d >= 0) << j; fover |= (uint32_t)(f >= 0) << j;       // the sharper prefilter of decode_light
             }
-            S.over[slot] = over; S.fover[slot] = fover;
+            dec::fill_ovt(S, slot, over, fover, my_n);
             S.ush[slot] = (uint8_t)ush;
             S.pidx[slot] = pidx; S.score[slot] = hd.x; S.prob[slot] = hd.z; S.ptgs[slot] = hd.w;
             S.slack[slot] = slack; S.lslack[slot] = slack - pf; S.n[slot] = (uint8_t)my_n;
