@@ -99,3 +99,21 @@ def test_patched_reference_main_multi_partition_files(shim, tmp_path):
         for g, ref, uniq in zip(got, c["ref_highs_paths"], c["oracle_unique"]):
             if uniq:
                 assert g == ref, c["name"]
+
+
+TRX = load("cases_trx.json")
+
+
+def test_patched_reference_main_translocation_modes(shim, tmp_path):
+    """PROP I1 / I2 / C1 / C2: host-only graph rewrites of the reference around the same search
+    (insertBeforeBFB, concatBeforeBFB, virusBFB, translocationBFB stay the reference's code).  Synthetic inputs after
+    the README's four examples; every path line -- per chromosome and the stitched `||` path -- equal to the unmodified
+    reference's.  (HiGHS played cbc there: a tie in Stage A could legitimately print another path; none of the twelve
+    inputs has one.)"""
+    modes = set()
+    for c in TRX:
+        d = tmp_path / c["name"]
+        d.mkdir()
+        assert run_dropin(shim, c, d) == c["ref_highs_paths"], c["name"]
+        modes.add(c["name"].split("_")[1])
+    assert modes == {"I1", "I2", "C1", "C2"} and len(TRX) >= 12

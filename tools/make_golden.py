@@ -431,7 +431,65 @@ def extra_large(which):
     print("wrote", out, len(doc["cases"]), "cases")
 
 
+def extra_trx():
+    """translocation modes (PROP I1 / I2 / C1 / C2, LGM:4052-4395, 3839-3939, localhap.cpp:71-88, 295-316): host-only graph
+    rewrites around the same search.  The four inputs of the reference's README are not available offline, so these are
+    synthetic multi-chromosome profiles built after them; recorded: every path line the unmodified reference prints
+    (HiGHS standing in for cbc) -> tests/golden/cases_trx.json.  The tests run the reference's own main() with the two
+    seams patched in (oracle/_ref/Ambigram_dropin) on the same inputs."""
+    hdr = "SAMPLE trx\nAVG_CHR_SEG_DP 30\nAVG_WHOLE_HOST_DP 30\nAVG_JUNC_DP 30\nPURITY 1\nAVG_TUMOR_PLOIDY 2\nPLOIDY 2m1\n"
+
+    def seg(i, ch, cn):
+        return f"SEG H:{i}:{ch}:{1000 * i}:{1000 * i + 999} {15.0 * cn} {float(cn)}"
+
+    def junc(a, da, b, db, cn=1):
+        return f"JUNC H:{a}:{da} H:{b}:{db} {15.0 * cn} {float(cn)} U B"
+
+    def lh_text(virus_start, sources, sinks, segs, juncs, prop):
+        return (hdr + f"VIRUS_START {virus_start}\nSOURCE {','.join(map(str, sources))}\nSINK {','.join(map(str, sinks))}\n" +
+                "\n".join([seg(*x) for x in segs] + [junc(*x) for x in juncs]) + f"\nPROP {prop}\n")
+
+    inputs = []
+    for k, (c2, c3, c6) in enumerate([(3, 3, 4), (3, 3, 2), (5, 3, 4)]):            # C2: concatenation after BFB
+        inputs.append((f"trx_C2_{k}", lh_text(8, [1, 5], [4, 7],
+                       [(1, "chr2", 1), (2, "chr2", c2), (3, "chr2", c3), (4, "chr2", 2), (5, "chr6", 1), (6, "chr6", c6), (7, "chr6", c6)],
+                       [(4, "+", 4, "-"), (2, "-", 2, "+"), (7, "+", 7, "-", c6 // 2), (6, "-", 6, "+"), (3, "+", 6, "+")], "C2:chr2:chr6 M:chr2")))
+    for k, (c3, c4) in enumerate([(4, 3), (4, 2), (3, 3)]):                         # I2: insertion after BFB
+        inputs.append((f"trx_I2_{k}", lh_text(10, [1, 5, 8], [4, 7, 9],
+                       [(1, "chr2", 1), (2, "chr2", 3), (3, "chr2", c3), (4, "chr2", c4), (5, "chr6", 1), (6, "chr6", 2), (7, "chr6", 2), (8, "chr13", 1), (9, "chr13", 1)],
+                       [(4, "+", 4, "-"), (2, "-", 2, "+"), (4, "+", 4, "-"), (3, "-", 3, "+"), (7, "+", 7, "-"), (3, "+", 5, "+"), (6, "-", 8, "+"), (9, "+", 4, "-")],
+                       "I2:chr2:chr6:chr13 M:chr2 S:3")))
+    for k, (c2, c4, cv) in enumerate([(4, 2, 4), (4, 2, 2), (3, 2, 3)]):            # I1: insertion before BFB
+        inputs.append((f"trx_I1_{k}", lh_text(5, [1, 5], [4, 6],
+                       [(1, "chr8", 1), (2, "chr8", c2), (3, "chr8", c2), (4, "chr8", c4), (5, "virus", 0), (6, "virus", cv)],
+                       [(4, "+", 4, "-"), (2, "-", 2, "+"), (3, "+", 6, "+", 2), (6, "+", 4, "+", 2)], "I1:chr8:virus:chr8 M:chr8")))
+    for k, (c2, c4, cv) in enumerate([(3, 2, 2), (3, 2, 1), (5, 2, 2)]):            # C1: concatenation before BFB
+        inputs.append((f"trx_C1_{k}", lh_text(7, [1, 5], [4, 6],
+                       [(1, "chr1", 1), (2, "chr1", c2), (3, "chr1", c2), (4, "chr1", c4), (5, "chrV", cv), (6, "chrV", cv)],
+                       [(4, "+", 4, "-"), (2, "-", 2, "+"), (6, "+", 2, "+", 2)], "C1:chr1:chrV")))
+    trx_re = re.compile(r"^\d+[+-](\|{0,2}\d+[+-])*$")
+    cases = []
+    for name, text in inputs:
+        with tempfile.TemporaryDirectory() as d:
+            open(os.path.join(d, "in.lh"), "w").write(text)
+            env = dict(os.environ, PATH=BIN + ":" + os.environ["PATH"])
+            try:
+                r = subprocess.run([REF, "--op", "bfb", "--in_lh", "in.lh", "--lp_prefix", "p"], cwd=d, env=env, capture_output=True, text=True, timeout=300)
+            except subprocess.TimeoutExpired:
+                print(name, "reference timed out"); continue
+            lines = [ln.strip() for ln in r.stdout.splitlines() if trx_re.match(ln.strip())]
+            marks = [ln.strip() for ln in r.stdout.splitlines() if ln.startswith(("BFB with translocation", "TRX-BFB mode"))]
+            print(name, r.returncode, lines, marks, flush=True)
+            if r.returncode == 0 and lines:
+                cases.append({"name": name, "lh": text, "ref_rc": r.returncode, "ref_highs_paths": lines, "ref_marks": marks})
+    out = os.path.join(ROOT, "tests", "golden", "cases_trx.json")
+    json.dump({"generator": "tools/make_golden.py trx", "cases": cases}, open(out, "w"), indent=0)
+    print("wrote", out, len(cases), "cases")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "trx":
+        return extra_trx()
     if len(sys.argv) > 1 and sys.argv[1] == "large":
         return extra_large(sys.argv[2:])
     if len(sys.argv) > 1 and sys.argv[1] == "fractional":
