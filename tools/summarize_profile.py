@@ -83,7 +83,7 @@ def full(round_, rep):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     md = [f"# {round_}: `ncu --set full --clock-control none --import-source on -k regex:k_expand` (exact-pass levels of one step)\n",
-          "Command: `" + os.environ.get("AMBI_PROFILE_CMD", "AMBI_NO_GRAPH=1 ncu --set full --clock-control none --import-source on -k regex:k_expand -s 26 -c 2 python scratch/prof_target.py 32768") + "`;",
+          "Command: `" + os.environ.get("AMBI_PROFILE_CMD", "AMBI_NO_GRAPH=1 ncu --set full --clock-control none --import-source on -k regex:k_expand -s 26 -c 2 python tools/prof_target.py 32768") + "`;",
           "the same command exited 0 without ncu directly before.  Numbers under a profiler are not bench values.\n"]
     stall = [k for k in hdr if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")]
     for r in rows[2:]:
