@@ -621,16 +621,12 @@ struct FinalizeArgs {
     const uint8_t *recs;
     const uint32_t *count;
     uint32_t cap;
-    uint32_t *next_list;
-    uint32_t *next_count;
     int32_t *best_score;        // [prob]
     uint32_t *best_rows;        // [prob][AMBI_MAXN]
-    int32_t *fmin;              // beam: per-problem min f of this level (or nullptr)
     int32_t *limit;             // chunked mode: tighten the pruning limit as completed assignments arrive
     int stride;
     int level;
     int merge_best;             // chunked mode: keep the better of (stored best, this chunk's best)
-    int build_list;             // append the surviving open records to next_list (else expand reads the buffer itself)
     const uint32_t *overflow;
     int32_t *seen;              // [prob] best completed score seen so far in any pass ...
     unsigned long long *stamps; // ... and when (%globaltimer) it was first seen: [prob][4], word 1
@@ -685,8 +681,6 @@ struct BeamArgs {
     uint32_t *hist;             // [prob][BEAM_BINS]
     uint32_t *cutq;             // [prob] cut bin << 16 | records still to take from it
     uint32_t *ticket;           // [prob]
-    uint32_t *next_list;
-    uint32_t *next_count;
     int nprob;
     int width_floor;            // batch-scaled width (a fixed budget of beam records per batch)
     int width;                  // per-problem beam width of a 12-segment partition ...
@@ -1013,7 +1007,6 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     CK(cudaMalloc(&kbuf_, (size_t)cap_max_ * 48));
     CK(cudaMalloc(&lbuf_, (size_t)cap_max_ * sizeof(uint2)));
     CK(cudaMalloc(&list_[0], (size_t)cap_max_ * 4));
-    CK(cudaMalloc(&list_[1], (size_t)cap_max_ * 4));
     tsize_ = next_pow2((uint64_t)cap_max_ * 2);
     CK(cudaMalloc(&table_, (size_t)tsize_ * 8));
     CK(cudaMemsetAsync(table_, 0, (size_t)tsize_ * 8, stream_));
@@ -1260,10 +1253,9 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     }
     FinalizeArgs F;
     F.probs = d_probs_; F.recs = kbuf_; F.count = c_child; F.cap = cap_;
-    F.next_list = nullptr; F.next_count = nullptr;
     F.best_score = mode == 2 ? d_best_score_ : d_beam_score_; F.best_rows = mode == 2 ? d_best_rows_ : d_beam_rows_;
-    F.fmin = nullptr; F.stride = kstride_; F.level = level;
-    F.limit = nullptr; F.merge_best = 0; F.build_list = 0; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
+    F.stride = kstride_; F.level = level;
+    F.limit = nullptr; F.merge_best = 0; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
     F.links = lbuf_; F.parents = buf_[cur]; F.pstride = stride_;
     // this kernel only collects completed assignments: skip the levels where no problem ends
     // (it reads what the merge left and writes per-problem results only: no barrier needed before the next operation)
@@ -1276,8 +1268,8 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
         BeamArgs B;
         B.probs = d_probs_; B.recs = kbuf_; B.count = c_child; B.cap = cap_;
         B.fmin = fmin_cur; B.hist = hist; B.cutq = d_cutq_ + (size_t)level * count_;
-        B.ticket = d_ticket_ + (size_t)level * count_; B.next_list = nullptr;
-        B.next_count = nullptr; B.nprob = count_; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1)));
+        B.ticket = d_ticket_ + (size_t)level * count_;
+        B.nprob = count_; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1)));
         B.stride = kstride_; B.level = level; B.growth = beam_growth_; B.width_div = beam_div_;
         { Op o; memset(&o, 0, sizeof o); o.kind = OP_BEAM_HIST; o.sync_after = 1; o.u.bm = B; if (int rc = op(o)) return rc; }
         { Op o; memset(&o, 0, sizeof o); o.kind = OP_BEAM_CUT; o.sync_after = 1; o.u.bm = B; if (int rc = op(o)) return rc; }
@@ -1630,8 +1622,8 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
         FinalizeArgs F;
         F.probs = d_probs_; F.recs = kbuf_; F.count = c_child; F.cap = cap_;
-        F.next_list = nullptr; F.next_count = nullptr; F.best_score = d_best_score_; F.best_rows = d_best_rows_;
-        F.fmin = nullptr; F.limit = d_limit_; F.stride = kstride_; F.level = level; F.merge_best = 1; F.build_list = 0; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
+        F.best_score = d_best_score_; F.best_rows = d_best_rows_;
+        F.limit = d_limit_; F.stride = kstride_; F.level = level; F.merge_best = 1; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
         F.links = lbuf_; F.parents = pool_ + sg.off; F.pstride = stride_;
         k_finalize<<<sms_ * 8, 256, 0, stream_>>>(F); ++launches_;
         // the survivors become full records on top of the pool (the next, deeper segment of the stack)
