@@ -56,10 +56,6 @@ struct ambi_ctx {
     ambi_config cfg;
     cudaStream_t stream = nullptr;
     StageA sa;
-    StageA sa2;                        // second Stage-A engine (own stream, own buffers), created on first use: large batches
-    cudaStream_t stream2 = nullptr;    //   that come with host buffers are solved in two halves so that flattening and result
-    bool sa2_ready = false;            //   mapping of one half overlap the search of the other (ambi_bfb_solve_batch)
-    unsigned long long sa2_counted = 0;
     StageB sb;
     ncclComm_t comm = nullptr;
     uint32_t *d_gather = nullptr;      // world * 40 words
@@ -153,9 +149,8 @@ extern "C" void ambi_destroy(ambi_ctx *ctx)
     cudaSetDevice(ctx->cfg.device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     cudaFree(ctx->d_gather);
-    ctx->sa.release(); ctx->sa2.release(); ctx->sb.release();
+    ctx->sa.release(); ctx->sb.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
 
@@ -239,11 +234,12 @@ extern "C" int ambi_bfb_better(int32_t n, int64_t sa, const int32_t *xa, int64_t
 }
 
 // ---- device-resident batch -------------------------------------------------
-// flatten `count` problems into the engine's pinned staging and start their upload (no synchronisation)
-static int upload_to(ambi_ctx *ctx, StageA &sa, int32_t count, const ambi_bfb_problem *problems, ambi_batch **out)
+extern "C" int ambi_batch_upload(ambi_ctx *ctx, int32_t count, const ambi_bfb_problem *problems, ambi_batch **out)
 {
-    DevProblem *stage = sa.staging(count);
-    if (!stage) return fail(ctx, AMBI_ERR_CUDA, sa.error());
+    if (!ctx || !out || count <= 0 || !problems) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_batch_upload: bad argument");
+    cudaSetDevice(ctx->cfg.device);
+    DevProblem *stage = ctx->sa.staging(count);
+    if (!stage) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
     ambi_batch *b = new ambi_batch();
     b->count = count; b->n.resize(count); b->bias.resize(count); b->ush.resize(count);
     std::atomic<int> bad_rc{0}, bad_i{-1};
@@ -257,18 +253,10 @@ static int upload_to(ambi_ctx *ctx, StageA &sa, int32_t count, const ambi_bfb_pr
         }
     });
     if (bad_rc) { delete b; return fail(ctx, bad_rc, "problem " + std::to_string(bad_i.load()) + ": " + bad_why); }
-    if (int urc = sa.upload(stage, count)) { delete b; return fail(ctx, urc == -5 ? AMBI_ERR_FRONTIER_OVERFLOW : AMBI_ERR_CUDA, sa.error()); }
-    *out = b;
-    return AMBI_OK;
-}
-
-extern "C" int ambi_batch_upload(ambi_ctx *ctx, int32_t count, const ambi_bfb_problem *problems, ambi_batch **out)
-{
-    if (!ctx || !out || count <= 0 || !problems) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_batch_upload: bad argument");
-    cudaSetDevice(ctx->cfg.device);
-    if (int rc = upload_to(ctx, ctx->sa, count, problems, out)) return rc;
+    if (int urc = ctx->sa.upload(stage, count)) { delete b; return fail(ctx, urc == -5 ? AMBI_ERR_FRONTIER_OVERFLOW : AMBI_ERR_CUDA, ctx->sa.error()); }
     cudaStreamSynchronize(ctx->stream);
-    ctx->resident = *out;
+    ctx->resident = b;
+    *out = b;
     return AMBI_OK;
 }
 
@@ -281,11 +269,11 @@ extern "C" int ambi_batch_run(ambi_ctx *ctx, ambi_batch *b)
     return AMBI_OK;
 }
 
-static int fetch_from(ambi_ctx *ctx, StageA &sa, ambi_batch *b, ambi_bfb_solution *sol, bool shard)
+static int fetch_into(ambi_ctx *ctx, ambi_batch *b, ambi_bfb_solution *sol, bool shard)
 {
     StageA::Fetched F;
-    int rc = sa.fetch_raw(&F);
-    if (rc) return fail(ctx, AMBI_ERR_CUDA, sa.error());
+    int rc = ctx->sa.fetch_raw(&F);
+    if (rc) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
     std::atomic<int> worst{AMBI_OK};
     parallel_for(b->count, [&](int lo, int hi) {
         int w = AMBI_OK;
@@ -309,34 +297,9 @@ static int fetch_from(ambi_ctx *ctx, StageA &sa, ambi_batch *b, ambi_bfb_solutio
         int cur = worst.load();
         while (w < cur && !worst.compare_exchange_weak(cur, w)) {}
     });
-    if (worst == AMBI_ERR_FRONTIER_OVERFLOW) return fail(ctx, worst, sa.error());
+    if (worst == AMBI_ERR_FRONTIER_OVERFLOW) return fail(ctx, worst, ctx->sa.error());
     if (worst) return fail(ctx, worst, "search returned no assignment");
     return AMBI_OK;
-}
-
-static int fetch_into(ambi_ctx *ctx, ambi_batch *b, ambi_bfb_solution *sol, bool shard) { return fetch_from(ctx, ctx->sa, b, sol, shard); }
-
-// Two halves of a large batch on two engines: while the first half is searched the host flattens the second, and
-// while the second is searched the host maps the first half's results back to element_cn.
-static int solve_two_halves(ambi_ctx *ctx, int32_t count, const ambi_bfb_problem *problems, ambi_bfb_solution *solutions)
-{
-    if (!ctx->sa2_ready) {
-        if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) return fail(ctx, AMBI_ERR_CUDA, "second stream");
-        if (ctx->sa2.init(ctx->stream2, ctx->cfg.node_capacity, ctx->cfg.beam_width, ctx->cfg.rank, ctx->cfg.world, ctx->cfg.shard_level,
-                          (ctx->cfg.flags & AMBI_CFG_SMALL_KERNEL) != 0)) return fail(ctx, AMBI_ERR_CUDA, ctx->sa2.error());
-        ctx->sa2_ready = true;
-    }
-    const int32_t half = count / 2;
-    ambi_batch *b1 = nullptr, *b2 = nullptr;
-    int rc = upload_to(ctx, ctx->sa, half, problems, &b1);
-    if (!rc && ctx->sa.run(false)) rc = fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
-    int rc2 = rc ? rc : upload_to(ctx, ctx->sa2, count - half, problems + half, &b2);
-    if (!rc2 && ctx->sa2.run(false)) rc2 = fail(ctx, AMBI_ERR_CUDA, ctx->sa2.error());
-    if (!rc) rc = fetch_from(ctx, ctx->sa, b1, solutions, false);
-    if (!rc2 && b2) rc2 = fetch_from(ctx, ctx->sa2, b2, solutions + half, false);
-    ctx->extra_launches += ctx->sa2.launches() - ctx->sa2_counted; ctx->sa2_counted = ctx->sa2.launches();
-    delete b1; delete b2;
-    return rc ? rc : rc2;
 }
 
 extern "C" int ambi_batch_fetch(ambi_ctx *ctx, ambi_batch *b, ambi_bfb_solution *solutions)
@@ -368,15 +331,6 @@ extern "C" int ambi_bfb_solve_batch(ambi_ctx *ctx, int32_t count, const ambi_bfb
     while (lo < count) {
         int32_t hi = lo; double w = 0;
         while (hi < count && (hi == lo || w + frontier_estimate(problems[hi].n) <= budget)) { w += frontier_estimate(problems[hi].n); ++hi; }
-        static const bool pipeline = getenv("AMBI_NO_PIPELINE") == nullptr;
-        if (pipeline && hi - lo >= 16384 && ctx->cfg.world <= 1) {
-            cudaSetDevice(ctx->cfg.device);
-            int rc = solve_two_halves(ctx, hi - lo, problems + lo, solutions + lo);
-            if (rc && rc != AMBI_ERR_FRONTIER_OVERFLOW) return rc;
-            if (rc) worst = rc;
-            lo = hi;
-            continue;
-        }
         ambi_batch *b = nullptr;
         static const bool timing = getenv("AMBI_TIMING") != nullptr;
         auto t0 = std::chrono::steady_clock::now();

@@ -305,23 +305,6 @@ def test_program_in_one_cooperative_kernel_gives_the_same_answers(monkeypatch):
             check_against_oracle(p, c.solve(p))
 
 
-def test_large_host_batch_in_two_pipelined_halves(ctx):
-    """ambi_bfb_solve_batch on 16384+ partitions with host buffers runs two halves on two engines (flattening and
-    result mapping of one half overlap the search of the other): same answers as the halves solved one by one"""
-    rng = random.Random(77)
-    probs = []
-    for _ in range(16500):
-        n = rng.randint(2, 6)
-        probs.append(Problem(n=n, seg_cn2=[rng.choice([2, 4, 6, 8, 12]) for _ in range(n)], fbi_cn2=[rng.choice([0, 0, 2, 4]) for _ in range(n)],
-                             loop_ub=rng.choice([2, 9])))
-    whole = ctx.solve_batch(probs)
-    parts = ctx.solve_batch(probs[:8000]) + ctx.solve_batch(probs[8000:])
-    for a, b in zip(whole, parts):
-        assert a.status == 0 and a.score2 == b.score2 and np.array_equal(a.element_cn, b.element_cn) and a.candidates_scored == b.candidates_scored
-    for i in rng.sample(range(len(probs)), 150):
-        check_against_oracle(probs[i], whole[i])
-
-
 def test_bad_arguments(ctx):
     with pytest.raises(capi.AmbiError):
         ctx.solve(Problem(n=33, seg_cn2=[2] * 33, fbi_cn2=[0] * 33))
