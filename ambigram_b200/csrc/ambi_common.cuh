@@ -66,7 +66,7 @@ struct NodeHdr {             // the four header words and columns 0..15 share th
     int32_t score;           // exact deviation (x2) of segments < level          partitions of <= 16 segments
     int32_t f;               // score + admissible bound on the rest             are merged, selected and staged
     int32_t prob;            //                                                  from that one sector
-    int32_t tgs;             // running count of the third-generation row (bit 31: dropped by the merge)
+    int32_t tgs;             // running count of the third-generation row
     uint8_t col[AMBI_MAXN];
 };                           // 48 bytes, followed by uint32 rows[nmax]
 

@@ -31,6 +31,10 @@ namespace ambi {
 constexpr int WPB = 8;              // warps per block in k_expand
 constexpr int GRP = 32;             // frontier records handled together by one warp
 constexpr int BEAM_BINS = 64;
+#ifndef AMBI_CHUNK
+#define AMBI_CHUNK 4
+#endif
+constexpr uint32_t CHUNK = AMBI_CHUNK;        // consecutive configurations of a record stepped through by one lane (k_expand phase 2)
 
 enum { EMIT_ALL = 0, EMIT_BEST = 1 };
 
@@ -41,6 +45,7 @@ struct LevelArgs {
     const uint32_t *pcount;
     uint8_t *children;              // key records of the children: header + column state (kstride bytes each)
     uint2 *links;                   // per child: (parent's index in `parents`, row code) -- the prefix is not copied
+    uint8_t *dead;                  // per child: 0 open, 2 completed assignment (set here), 1 once the merge dropped it -- the key records stay read-only
     int kstride;
     uint32_t *ccount;
     uint32_t cap;
@@ -79,26 +84,29 @@ template <int NMAX>
 struct GroupShared {
     uint32_t colw[NMAX / 4][GRP];       // column bytes nP | nL<<2 | bP<<4 | bL<<6 of the record in the slot, 4 columns per word
     __device__ __forceinline__ uint32_t colb(int j, int slot) const { return reinterpret_cast<const uint8_t *>(&colw[j >> 2][slot])[j & 3]; }
-    uint8_t  posP[GRP][NMAX], posE[GRP][NMAX];   // decode lists (decode_common.cuh)
-    uint16_t L0[GRP][dec::L0CAP];
+    uint8_t  posP[GRP][NMAX];           // enumeration lists (decode_common.cuh, "Incremental enumeration")
+    uint16_t LE[GRP][dec::L0CAP + NMAX];
     uint32_t okP[GRP], parP[GRP];       // column may take a pattern end / has a pattern parent (row 1)
     uint32_t okL1[GRP], A2m[GRP];       // column may take one loop end / two loop ends and has two parents
-    uint32_t par1[GRP];                 // column already holds >= 1 parent for a loop (row 3)
+    uint32_t A1m[GRP];                  // column may take one loop end and already holds a parent for it (row 3)
     uint32_t tmask[GRP];                // third-generation cells of this row
     uint8_t  ovt[GRP][NMAX + 4];        // prefilter table of decode_light (decode_common.cuh fill_ovt)
-    int32_t  score[GRP], slack[GRP], ptgs[GRP], prob[GRP];
+    int32_t  score[GRP], slack[GRP], prob[GRP];
     int32_t  d0[GRP], f0[GRP];          // 2 cov_a - 2c_a and fb_a - 2J_a before the row's own entries
     int32_t  lslack[GRP];               // slack minus the record's own bound on segments > a (light-test limit)
     uint32_t pidx[GRP];
-    uint32_t nl0[GRP];                  // loop multisets whose parents already exist (class 0)
-    uint32_t cstart[GRP + 1];           // exclusive prefix of candidate counts
+    uint16_t nl0[GRP];                  // loop multisets whose parents already exist (class 0)
+    uint16_t ncfg[GRP];                 // configurations of the record
+    uint32_t cstart[GRP + 1];           // exclusive prefix of the records' chunk counts (work items of phase 2)
     uint8_t  n[GRP];
+    uint8_t  ptgs[GRP];                 // running third-generation count (at most 5)
     uint8_t  ush[GRP];                  // copy-number unit of the record's partition (SCALED instantiations only)
     uint32_t cnt[GRP];                  // structurally infeasible configurations per record (not scored)
-    const uint32_t *cjp[GRP];           // 2c_j | 2J_j << 16 of the record's partition (DevProblem::cj)
-    unsigned long long best[GRP];       // EMIT_BEST: min (tot<<32 | cfg-order key)
     uint32_t qh[64];                    // light-test survivors awaiting the bound: slot<<24 | cfg
-    uint32_t qw_cfg[64]; int32_t qw_err[64]; int32_t qw_tot[64];   // children awaiting the write
+    uint32_t qw_cfg[64]; int32_t qw_err[64];       // children awaiting the write ...
+    alignas(8) int32_t qw_tot[64];                 // ... (EMIT_BEST never queues children: the same bytes hold best[])
+    // EMIT_BEST: per record min (tot << 32 | cfg-order key)
+    __device__ __forceinline__ unsigned long long *best() { return reinterpret_cast<unsigned long long *>(qw_tot); }
 };
 
 using dec::pack_cfg;
@@ -117,7 +125,7 @@ __device__ __forceinline__ uint32_t cfg_code(int n, int p1, int p2, int l1, int 
 // SCALED: copy numbers in units of 1/(2U) copies, U = 1 << ush per partition: counts of copies become counts of units
 // where they meet 2c / 2J (the half-copy instantiation is unchanged: ush is the constant 0 there).
 template <int NMAX, bool SCALED>
-__device__ __forceinline__ int child_bound(const GroupShared<NMAX> &S, int slot, int jtop, int a,
+__device__ __forceinline__ int child_bound(const GroupShared<NMAX> &S, const DevProblem *probs, int slot, int jtop, int a,
                                            int p1, int p2, int l1, int l2, int budget, bool active)
 {
     const int ush = SCALED ? (int)S.ush[slot] : 0;
@@ -131,7 +139,7 @@ __device__ __forceinline__ int child_bound(const GroupShared<NMAX> &S, int slot,
     // ends at or below the current column (the walk goes right to left, every end is < jtop)
     int rp_le = __popc(pm), rl_le = __popc(lm1) + __popc(lm2);
     int six = 6 * (jtop - 1 - a);                                // 6 * (j - a)
-    const uint32_t *cjp = S.cjp[slot];
+    const uint32_t *cjp = probs[S.prob[slot]].cj;           // 2c_j | 2J_j << 16 of the record's partition, through the read-only cache
     const int nrec = S.n[slot];
 #pragma unroll 2
     for (int j = jtop - 1; j > a; --j) {
@@ -181,10 +189,10 @@ __device__ __noinline__ int heavy_batch(GroupShared<NMAX> &S, const LevelArgs &A
         const int ush = SCALED ? (int)S.ush[slot] : 0;
         err = abs(S.d0[slot] + (w << (ush + 1))) + abs(S.f0[slot] + (w << ush));
     }
-    const int lb = child_bound<NMAX, SCALED>(S, slot, jtop, a, p1, p2, l1, l2, slack - err, act);
+    const int lb = child_bound<NMAX, SCALED>(S, A.probs, slot, jtop, a, p1, p2, l1, l2, slack - err, act);
     if (act) { tot = err + lb; keep = tot <= slack; }
     if (A.emit == EMIT_BEST) {
-        if (keep) atomicMin(&S.best[slot], ((unsigned long long)(uint32_t)tot << 32) | cfg_code(S.n[slot], p1, p2, l1, l2));
+        if (keep) atomicMin(&S.best()[slot], ((unsigned long long)(uint32_t)tot << 32) | cfg_code(S.n[slot], p1, p2, l1, l2));
         return qw;
     }
     const uint32_t km = __ballot_sync(0xffffffffu, keep);
@@ -262,8 +270,9 @@ __device__ __noinline__ void write_batch(GroupShared<NMAX> &S, const LevelArgs &
                    (l1 >= 0 && ((tm >> l1) & 1)) + (l2 >= 0 && ((tm >> l2) & 1));
     const int sc = S.score[slot];
     // completed assignments all share one (empty) state: drop the running third-generation count
-    reinterpret_cast<int4 *>(crec)[0] = make_int4(sc + err, sc + tot, S.prob[slot], (n == a + 1) ? 0 : S.ptgs[slot] + hits);
+    reinterpret_cast<int4 *>(crec)[0] = make_int4(sc + err, sc + tot, S.prob[slot], (n == a + 1) ? 0 : (int)S.ptgs[slot] + hits);
     A.links[cslot] = make_uint2(S.pidx[slot], code);
+    A.dead[cslot] = (n == a + 1) ? 2 : 0;
 }
 
 // Body of the expansion kernel: `A` lives in shared memory (the stage functions take it by reference), `s_raw` is the
@@ -297,8 +306,7 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
         int4 hd = make_int4(0, 0, 0, 0);
         uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (have) {
-            // no list: the frontier is the previous level's child buffer itself, minus the records the
-            // merge dropped (their header is flagged) and the completed assignments (n == level)
+            // no list: the frontier is the dense array of the previous level's survivors (k_materialise)
             pidx = A.plist ? A.plist[base + lane] : base + lane;
             const uint8_t *prec = A.parents + (size_t)pidx * A.stride;
             hd = reinterpret_cast<const int4 *>(prec)[0];                   // score, f, prob, tgs
@@ -308,11 +316,9 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
                 const uint4 c1 = reinterpret_cast<const uint4 *>(prec + offsetof(NodeHdr, col))[1];
                 w[4] = c1.x; w[5] = c1.y; w[6] = c1.z; w[7] = c1.w;
             }
-            const bool dropped = (uint32_t)hd.w & 0x80000000u;
-            hd.w &= 0x7fffffff;
             P = &A.probs[hd.z];
             my_n = P->n; lmax = P->lmax;
-            slack = dropped ? -1 : A.limit[hd.z] - hd.x;
+            slack = A.limit[hd.z] - hd.x;
             // heuristic band (the beam only feeds the incumbent): a child may exceed its parent's f by
             // beam_delta, or by half of what is left up to the current limit if that is more
             if (A.beam_delta >= 0) slack = min(slack, hd.y - hd.x + max(A.beam_delta, (A.limit[hd.z] - hd.y) >> A.beam_shift));
@@ -346,21 +352,14 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
                             ((a >> 2) == 4 ? w[4] : ((a >> 2) == 5 ? w[5] : ((a >> 2) == 6 ? w[6] : w[7]))))));
         const uint32_t ba = (wa >> (8 * (a & 3))) & 0xffu;
         const int fbC = (int)(ba & 3) + 2 * (int)((ba >> 2) & 3);
-        uint32_t total = 0, nl0 = 0;
-        if (have && my_n > a && slack >= 0) total = dec::count_configs(okP, parP, okL1, okL2, par1, par2, &nl0);
-        const uint32_t nzm = __ballot_sync(0xffffffffu, total > 0);
+        // every open record within the limit has at least the empty configuration: it takes a staging slot
+        const bool staged = have && my_n > a && slack >= 0;
+        const uint32_t nzm = __ballot_sync(0xffffffffu, staged);
         const int ns = __popc(nzm);                       // staged records
         const int slot = __popc(nzm & lt_mask);
-        // exclusive prefix of candidate counts over the staged records
-        uint32_t incl = total;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
-        int jtop = total > 0 ? my_n : 0;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) jtop = max(jtop, __shfl_xor_sync(0xffffffffu, jtop, o));
-        if (total > 0) {
-            dec::write_lists(S, slot, okP, parP, okL1, okL2, par1, par2, nl0);
+        const int jtop = (int)__reduce_max_sync(0xffffffffu, staged ? (unsigned)my_n : 0u);
+        uint32_t total = 0;
+        if (staged) {
 #pragma unroll
             for (int q = 0; q < NMAX / 4; ++q) S.colw[q][slot] = w[q];
             // The record's own bound on segments > a (what its parent level charged for them): every child's
@@ -383,29 +382,69 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
                 pf += d > 0 ? d : max(0, -d - (fmax << (ush + 1)));
                 const int f = (wn << ush) - (int)(cjw >> 16);
                 pf += f > 0 ? f : max(0, -f - ((cap + min(capsum, 6)) << ush));
-                over |= (uint32_t)(d >= 0) << j; fover |= (uint32_t)(f >= 0) << j;       // the sharper prefilter of decode_light
+                over |= (uint32_t)(d >= 0) << j; fover |= (uint32_t)(f >= 0) << j;       // the sharper prefilter of the light test
             }
             dec::fill_ovt(S, slot, over, fover, my_n);
+            const int lslack = slack - pf;
+            const int d0 = (covC << (ush + 1)) - (int)(cja & 0xffffu), f0 = (fbC << ush) - (int)(cja >> 16);
+            // Columns the prefilter would refuse in every configuration are taken out of the masks before anything is
+            // counted or listed: an end at column c charges ovt[c] (a loop end twice that), and the exact deviation of
+            // segment a is at least its minimum over the weights w the end can come with -- the configurations that
+            // disappear are exactly ones the light test would drop one by one.  They still count as candidates.
+            uint32_t nl0 = 0;
+            const uint32_t total_all = dec::count_configs_call(okP, parP, okL1, okL2, par1, par2, &nl0);
+            total = total_all;
+            if (lslack < 0) total = 0;                    // the record's own bound is already beyond the limit
+            else {
+                int e[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) e[k] = abs(d0 + (k << (ush + 1))) + abs(f0 + (k << ush));
+                const int m4 = min(e[4], min(e[5], e[6])), m2 = min(min(e[2], e[3]), m4), m1 = min(e[1], m2);
+                const uint32_t rP = dec::allowed_cols(over, fover, (lslack - m1) >> ush);
+                const uint32_t rL1 = dec::allowed_cols(over, fover, (lslack - m2) >> (ush + 1));
+                const uint32_t rL2 = dec::allowed_cols(over, fover, (lslack - m4) >> (ush + 2));
+                if ((okP & ~rP) | (okL1 & ~rL1) | (okL2 & ~rL2)) {
+                    okP &= rP; okL1 &= rL1; okL2 &= rL2;
+                    total = dec::count_configs_call(okP, parP, okL1, okL2, par1, par2, &nl0);
+                }
+                dec::write_lists2(S, slot, okP, parP, okL1, okL2, par1, par2, nl0);
+            }
+            atomicAdd(&A.cand_count[hd.z], (unsigned long long)total_all);
             S.ush[slot] = (uint8_t)ush;
-            S.pidx[slot] = pidx; S.score[slot] = hd.x; S.prob[slot] = hd.z; S.ptgs[slot] = hd.w;
-            S.slack[slot] = slack; S.lslack[slot] = slack - pf; S.n[slot] = (uint8_t)my_n;
-            S.d0[slot] = (covC << (ush + 1)) - (int)(cja & 0xffffu); S.f0[slot] = (fbC << ush) - (int)(cja >> 16);
+            S.pidx[slot] = pidx; S.score[slot] = hd.x; S.prob[slot] = hd.z; S.ptgs[slot] = (uint8_t)hd.w;
+            S.slack[slot] = slack; S.lslack[slot] = lslack; S.n[slot] = (uint8_t)my_n;
+            S.d0[slot] = d0; S.f0[slot] = f0;
             S.tmask[slot] = P->has_tgs ? P->tgs_mask[a] : 0u;
-            S.cjp[slot] = P->cj;
-            S.cstart[slot + 1] = incl;
+            S.ncfg[slot] = (uint16_t)total;
         }
-        if (lane >= ns) S.cstart[lane + 1] = T;           // beyond the last staged record
+        // phase 2 works in chunks of CHUNK consecutive configurations of a record (a record left without any still owns
+        // one, empty, chunk): exclusive prefix of the chunk counts over the staged records
+        uint32_t incl = staged ? max(1u, (total + CHUNK - 1) / CHUNK) : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const uint32_t TI = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t T = __reduce_add_sync(0xffffffffu, total);
+        if (staged) S.cstart[slot + 1] = incl;
+        if (lane >= ns) S.cstart[lane + 1] = TI;          // beyond the last staged record
         if (lane == 0) S.cstart[0] = 0;
-        S.best[lane] = ~0ull; S.cnt[lane] = 0;
+        if (A.emit == EMIT_BEST) S.best()[lane] = ~0ull;
+        S.cnt[lane] = 0;
         __syncwarp();
 
-        // ---- phase 2: lane = candidate (flattened over the group's records); three stages fed
-        //      through two shared-memory queues so that each stage runs with full lanes
+        // ---- phase 2: lane = a chunk of consecutive configurations of one record (flattened over the group's
+        //      records), stepped through by a cursor; three stages fed through two shared-memory queues so that
+        //      each stage runs with full lanes
         int qh = 0, qw = 0;                 // queue fills (warp-uniform)
-        uint32_t cb0 = 0, s0 = 0;           // s0: staged record that owns candidate cb0
+        uint32_t ib0 = 0, s0 = 0;           // s0: staged record that owns chunk ib0
+        int st = 0, rsteps = 0;             // step within the current round of chunks / its length (warp-uniform)
+        int own = 0, left = 0;              // this lane's record and configurations in its chunk
+        uint32_t my_nl0 = 1;
+        dec::Cursor cur;
+        cur.m_rem = 0; cur.li = 0; cur.width = 1; cur.hi = -1; cur.pi = 0; cur.kP = 0; cur.pcode = 0; cur.pw = 0;
         uint32_t n_heavy = 0, n_write = 0, n_hcalls = 0;  // funnel statistics (warp-uniform)
         for (;;) {
-            if (qw >= 32 || (cb0 >= T && qh == 0 && qw > 0)) {
+            const bool enum_done = st >= rsteps && ib0 >= TI;
+            if (qw >= 32 || (enum_done && qh == 0 && qw > 0)) {
                 const int cnt = min(qw, 32);
                 n_write += cnt;
                 write_batch<NMAX>(S, A, cnt);
@@ -418,9 +457,10 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
                 __syncwarp();
                 continue;
             }
-            if (qh >= 32 || (cb0 >= T && qh > 0)) {
+            if (qh >= 32 || (enum_done && qh > 0)) {
                 const int cnt = min(qh, 32);
                 n_heavy += cnt; ++n_hcalls;
+                __syncwarp();               // the queue entries of the last steps
                 qw = heavy_batch<NMAX, SCALED>(S, A, cnt, jtop, qw);
                 __syncwarp();
                 qh -= cnt;
@@ -430,29 +470,39 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
                 __syncwarp();
                 continue;
             }
-            if (cb0 >= T) break;
-            const uint32_t bm = dec::owner_mask(S, s0, cb0, lane);
-            const uint32_t c = cb0 + lane;
+            if (enum_done) break;
+            if (st >= rsteps) {             // next round: 32 chunks, one per lane
+                const uint32_t bm = dec::owner_mask(S, s0, ib0, lane);
+                const uint32_t it = ib0 + lane;
+                left = 0;
+                if (it < TI) {
+                    own = (int)(s0 + __popc(bm & lt_mask));
+                    const uint32_t r0 = (it - S.cstart[own]) * CHUNK;
+                    left = min((int)CHUNK, (int)S.ncfg[own] - (int)r0);
+                    if (left > 0) { my_nl0 = S.nl0[own]; dec::cursor_start(S, own, r0, cur); }
+                }
+                s0 += __popc(bm);
+                ib0 += 32;
+                rsteps = (int)__reduce_max_sync(0xffffffffu, (unsigned)left);
+                st = 0;
+            }
             bool pass = false;
             uint32_t entry = 0;
-            int own = 0;
-            if (c < T) {
-                own = (int)(s0 + __popc(bm & lt_mask));
-                entry = dec::decode_light(S, own, c - S.cstart[own], S.tmask[own], SCALED ? (int)S.ush[own] : 0, &pass);
+            if (st < left) {
+                entry = dec::cursor_eval<SCALED>(S, own, cur, my_nl0, &pass);
+                // candidates scored = enumerated minus the (few) structurally infeasible ones, per record
+                if (!entry) atomicAdd(&S.cnt[own], 1u);
+                dec::cursor_advance(S, own, cur, my_nl0);
             }
-            // candidates scored = enumerated minus the (few) structurally infeasible ones, per record
-            if (c < T && !entry) atomicAdd(&S.cnt[own], 1u);
-            s0 += __popc(bm);
-            cb0 += 32;
             const uint32_t bal = __ballot_sync(0xffffffffu, pass);
             if (pass) S.qh[qh + __popc(bal & lt_mask)] = entry;
             qh += __popc(bal);
-            __syncwarp();
+            ++st;
         }
         if (A.emit == EMIT_BEST) {
             // every record emits its arg-min child (tot, then search order)
             __syncwarp();
-            const unsigned long long bk = S.best[lane];
+            const unsigned long long bk = S.best()[lane];
             const bool has = lane < ns && bk != ~0ull;
             const uint32_t hm = __ballot_sync(0xffffffffu, has);
             if (has) {
@@ -478,7 +528,8 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
         __syncwarp();
         if (lane < 4 && T) atomicAdd(&A.funnel[lane], (unsigned long long)(lane == 0 ? T : (lane == 1 ? n_heavy : (lane == 2 ? n_write : n_hcalls))));
         if (lane < ns) {
-            atomicAdd(&A.cand_count[S.prob[lane]], (unsigned long long)(S.cstart[lane + 1] - S.cstart[lane] - S.cnt[lane]));
+            // candidates of a record = its configurations (counted in phase 1) minus the structurally infeasible ones met
+            if (S.cnt[lane]) atomicAdd(&A.cand_count[S.prob[lane]], 0ull - (unsigned long long)S.cnt[lane]);
             atomicAdd(&A.node_count[S.prob[lane]], 1ull);
         }
         __syncwarp();
@@ -498,10 +549,10 @@ k_expand(LevelArgs A_param)
 
 // ---------------------------------------------------------------------------
 // K3a: merge records that reached the same column state.
-// A dropped record is flagged in its own header (bit 31 of the tgs word), so no
-// per-level flag array has to be cleared.
+// A byte per key record says what it is: 0 an open record, 2 a completed assignment (both written by k_expand with
+// the child), 1 dropped by the merge.  The keys themselves are never modified, a level's flags stay L2 resident, and
+// the passes that follow (finalize, beam histogram, materialise) read a key only when they need the record.
 // ---------------------------------------------------------------------------
-constexpr uint32_t DEAD_BIT = 0x80000000u;
 
 struct DedupArgs {
     uint8_t *recs;
@@ -522,6 +573,8 @@ struct DedupArgs {
     const uint2 *links;         // per key record: (parent, row code)
     const uint8_t *parents;     // full records of the previous level (prefix rows for the tie-break)
     int pstride;
+    uint8_t *dead;              // [record] dropped by the merge
+    int tshift;                 // table slots per record: at least 1 << tshift
 };
 
 // beam bins: width 1 from the level's minimum f, everything beyond in the last bin (the cut for the W best
@@ -529,16 +582,11 @@ struct DedupArgs {
 // previous level's minimum, lose the resolution that matters and cost hard partitions their incumbent)
 __device__ __forceinline__ int beam_bin(int f, int base) { return max(0, min(f - base, BEAM_BINS - 1)); }
 
-__device__ __forceinline__ uint32_t hdr_tgs(const NodeHdr *h) {
-    return *reinterpret_cast<const volatile uint32_t *>(&h->tgs) & ~DEAD_BIT;
-}
-__device__ __forceinline__ bool hdr_dead(const NodeHdr *h) { return (uint32_t)h->tgs & DEAD_BIT; }
-__device__ __forceinline__ void hdr_kill(NodeHdr *h) { atomicOr(reinterpret_cast<unsigned int *>(&h->tgs), DEAD_BIT); }
 
 // `wide`: some partition of the batch has more than 16 segments (otherwise columns 16..31 are zero everywhere
 // and only the first sector of either record is touched)
 __device__ __forceinline__ bool same_state(const NodeHdr *x, const NodeHdr *y, bool wide) {
-    if (x->prob != y->prob || hdr_tgs(x) != hdr_tgs(y)) return false;
+    if (x->prob != y->prob || x->tgs != y->tgs) return false;
     const uint4 *a = reinterpret_cast<const uint4 *>(x->col), *b = reinterpret_cast<const uint4 *>(y->col);
     const uint4 a0 = a[0], b0 = b[0];
     if (!(a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w)) return false;
@@ -568,17 +616,17 @@ __device__ __forceinline__ void dedup_body(const DedupArgs &A)
     if (*A.overflow) return;
     uint32_t cnt = min(*A.count, A.cap);
     const uint32_t gen = *A.gen_base + A.gen_off;
-    // use only as much of the table as this level needs (>= 4 slots per record), so that small
+    // use only as much of the table as this level needs (>= 1 << tshift slots per record), so that small
     // levels stay L2 resident; generation stamps make whatever is left there harmless
     uint32_t tmask = 1023u;
-    while (tmask < A.tmask && (tmask >> 2) < cnt) tmask = (tmask << 1) | 1u;
+    while (tmask < A.tmask && (tmask >> A.tshift) < cnt) tmask = (tmask << 1) | 1u;
     tmask = min(tmask, A.tmask);
     const bool wide = A.nmax > 16;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         uint8_t *rec = A.recs + (size_t)i * A.stride;
         NodeHdr *h = reinterpret_cast<NodeHdr *>(rec);
         const uint32_t *cw = reinterpret_cast<const uint32_t *>(h->col);
-        uint32_t hv = mix32((uint32_t)h->prob * 0x9e3779b9u + hdr_tgs(h));
+        uint32_t hv = mix32((uint32_t)h->prob * 0x9e3779b9u + (uint32_t)h->tgs);
 #pragma unroll
         for (int k = 0; k < 4; ++k) hv = mix32(hv ^ cw[k]) + 0x85ebca6bu * (k + 1);
         if (wide) {
@@ -600,15 +648,14 @@ __device__ __forceinline__ void dedup_body(const DedupArgs &A)
             if (same_state(h, reinterpret_cast<const NodeHdr *>(orec), wide)) {
                 if (rec_better(A, i, o)) {
                     unsigned long long old = atomicCAS(&A.table[slot], cur, mine);
-                    if (old == cur) { hdr_kill(reinterpret_cast<NodeHdr *>(orec)); alive = true; break; }
+                    if (old == cur) { A.dead[o] = 1; alive = true; break; }
                     continue;
-                } else { hdr_kill(h); break; }
+                } else { A.dead[i] = 1; break; }
             }
             slot = (slot + 1) & tmask;
         }
         if (A.fmin_cur && alive) {
-            const int prob = h->prob;
-            if (A.probs[prob].n != A.level + 1) atomicMin(&A.fmin_cur[prob], h->f);   // completed assignments are not part of the beam
+            if (A.dead[i] != 2) atomicMin(&A.fmin_cur[h->prob], h->f);   // completed assignments are not part of the beam
         }
     }
 }
@@ -633,6 +680,7 @@ struct FinalizeArgs {
     const uint2 *links;         // the key records' (parent, row code)
     const uint8_t *parents;     // full records of the previous level
     int pstride;
+    const uint8_t *dead;
 };
 
 __device__ __forceinline__ void finalize_body(const FinalizeArgs &A)
@@ -640,11 +688,11 @@ __device__ __forceinline__ void finalize_body(const FinalizeArgs &A)
     if (*A.overflow) return;
     uint32_t cnt = min(*A.count, A.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        if (A.dead[i] != 2) continue;
         const uint8_t *rec = A.recs + (size_t)i * A.stride;
         const NodeHdr *h = reinterpret_cast<const NodeHdr *>(rec);
-        if (hdr_dead(h)) continue;
         const int n = A.probs[h->prob].n;
-        if (n == A.level + 1) {
+        {
             // all completed assignments of a problem share the empty column state, so the
             // merge above left exactly one alive: the arg-min in (score, search order)
             const uint2 lk = A.links[i];
@@ -688,15 +736,16 @@ struct BeamArgs {
     int width_div;              // cooperative beam: this rank runs 1/width_div of the width on its share of the prefixes
     int stride;
     int level;
+    const uint8_t *dead;
 };
 
 __device__ __forceinline__ void beam_hist_body(const BeamArgs &A)
 {
     uint32_t cnt = min(*A.count, A.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        if (A.dead[i]) continue;
         const NodeHdr *h = reinterpret_cast<const NodeHdr *>(A.recs + (size_t)i * A.stride);
         const int prob = h->prob;
-        if (hdr_dead(h) || A.probs[prob].n == A.level + 1) continue;
         atomicAdd(&A.hist[(size_t)prob * BEAM_BINS + beam_bin(h->f, A.fmin[prob])], 1u);
     }
 }
@@ -734,6 +783,7 @@ struct MatArgs {
     const uint32_t *overflow;
     // beam selection (cutq != nullptr): keep below the cut bin, draw a ticket in the cut bin
     const int32_t *fmin; const uint32_t *cutq; uint32_t *ticket;
+    const uint8_t *dead;
 };
 
 __device__ __forceinline__ void materialise_body(const MatArgs &A)
@@ -741,44 +791,64 @@ __device__ __forceinline__ void materialise_body(const MatArgs &A)
     if (*A.overflow) return;
     const uint32_t cnt = min(*A.count, A.cap);
     const int lane = threadIdx.x & 31;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const int nq = (A.nmax + 3) >> 2;
-    const uint32_t nthreads = gridDim.x * blockDim.x;
-    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < cnt; i0 += nthreads) {
-        const uint32_t i = i0 + lane;
-        bool keep = false;
-        const NodeHdr *h = nullptr;
-        if (i < cnt) {
-            h = reinterpret_cast<const NodeHdr *>(A.keys + (size_t)i * A.kstride);
-            keep = !hdr_dead(h) && A.probs[h->prob].n != A.level + 1;
-            if (keep && A.cutq) {
-                const int bin = beam_bin(h->f, A.fmin[h->prob]);
-                const uint32_t cq = A.cutq[h->prob];
+    const uint32_t wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
+    // a warp takes 128 key records at a time, four per lane: one word of flags per lane, then -- for the open
+    // records only -- independent loads of keys, links and parent rows (the kernel waits on memory, not on issue
+    // slots), and one append to the frontier counter per 128 records
+    for (uint32_t w0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 128u; w0 < cnt; w0 += nwarps * 128u) {
+        const uint32_t ib = w0 + 4u * (uint32_t)lane;
+        uint32_t dw = 0x01010101u;
+        if (ib < cnt) dw = *reinterpret_cast<const uint32_t *>(A.dead + ib);      // (the flag array is padded to a multiple of 4)
+        uint32_t km = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (ib + k < cnt && ((dw >> (8 * k)) & 0xffu) == 0u) km |= 1u << k;
+        if (A.cutq) {
+            int4 hd[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hd[k] = ((km >> k) & 1u) ? *reinterpret_cast<const int4 *>(A.keys + (size_t)(ib + k) * A.kstride) : make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if ((km >> k) & 1u) {
+                const int bin = beam_bin(hd[k].y, A.fmin[hd[k].z]);
+                const uint32_t cq = A.cutq[hd[k].z];
                 const int cut = (int)(cq >> 16);
-                keep = bin < cut;
-                if (bin == cut) keep = atomicAdd(&A.ticket[h->prob], 1u) < (cq & 0xffffu);
+                bool keep = bin < cut;
+                if (bin == cut) keep = atomicAdd(&A.ticket[hd[k].z], 1u) < (cq & 0xffffu);
+                if (!keep) km &= ~(1u << k);
             }
         }
-        const uint32_t km = __ballot_sync(0xffffffffu, keep);
+        const int c = __popc(km);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
         uint32_t base = 0;
-        if (lane == 0 && km) base = atomicAdd(A.out_count, (uint32_t)__popc(km));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (!keep) continue;
-        const uint32_t o = base + __popc(km & lt_mask);
-        if (o >= A.out_cap) continue;                       // cannot happen: out_cap >= cap
-        uint8_t *dst = A.out + (size_t)o * A.pstride;
-        const uint4 *ksrc = reinterpret_cast<const uint4 *>(h);
-        reinterpret_cast<uint4 *>(dst)[0] = ksrc[0];
-        reinterpret_cast<uint4 *>(dst)[1] = ksrc[1];
-        reinterpret_cast<uint4 *>(dst)[2] = A.kstride > 32 ? ksrc[2] : make_uint4(0, 0, 0, 0);
-        const uint2 lk = A.links[i];
-        const uint4 *src = reinterpret_cast<const uint4 *>(A.parents + (size_t)lk.x * A.pstride + sizeof(NodeHdr));
-        uint4 *rd = reinterpret_cast<uint4 *>(dst + sizeof(NodeHdr));
+        if (lane == 31 && total) base = atomicAdd(A.out_count, (uint32_t)total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        uint32_t o = base + (uint32_t)(incl - c);
         const int a = A.level;
-        for (int q = 0; q < nq; ++q) {
-            uint4 v = src[q];
-            if ((a >> 2) == q) { const int r = a & 3; if (r == 0) v.x = lk.y; else if (r == 1) v.y = lk.y; else if (r == 2) v.z = lk.y; else v.w = lk.y; }
-            rd[q] = v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!((km >> k) & 1u)) continue;
+            const uint32_t i = ib + k;
+            if (o < A.out_cap) {                                 // always: out_cap >= cap
+                uint8_t *dst = A.out + (size_t)o * A.pstride;
+                const uint4 *ksrc = reinterpret_cast<const uint4 *>(A.keys + (size_t)i * A.kstride);
+                const uint2 lk = A.links[i];
+                const uint4 k0 = ksrc[0], k1 = ksrc[1];
+                const uint4 k2 = A.kstride > 32 ? ksrc[2] : make_uint4(0, 0, 0, 0);
+                const uint4 *src = reinterpret_cast<const uint4 *>(A.parents + (size_t)lk.x * A.pstride + sizeof(NodeHdr));
+                reinterpret_cast<uint4 *>(dst)[0] = k0;
+                reinterpret_cast<uint4 *>(dst)[1] = k1;
+                reinterpret_cast<uint4 *>(dst)[2] = k2;
+                uint4 *rd = reinterpret_cast<uint4 *>(dst + sizeof(NodeHdr));
+                for (int q = 0; q < nq; ++q) {
+                    uint4 v = src[q];
+                    if ((a >> 2) == q) { const int r = a & 3; if (r == 0) v.x = lk.y; else if (r == 1) v.y = lk.y; else if (r == 2) v.z = lk.y; else v.w = lk.y; }
+                    rd[q] = v;
+                }
+            }
+            ++o;
         }
     }
 }
@@ -950,7 +1020,7 @@ StageA::~StageA() { release(); }
 
 void StageA::release()
 {
-    cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]); cudaFree(kbuf_); cudaFree(lbuf_); kbuf_ = nullptr; lbuf_ = nullptr;
+    cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(list_[0]); cudaFree(list_[1]); cudaFree(kbuf_); cudaFree(lbuf_); cudaFree(dbuf_); kbuf_ = nullptr; lbuf_ = nullptr; dbuf_ = nullptr;
     cudaFree(table_); cudaFree(counters_); cudaFree(d_funnel_); cudaFree(d_flag_); cudaFree(pool_); pool_ = nullptr; d_funnel_ = nullptr; d_flag_ = nullptr;
     cudaFree(d_prog_); d_prog_ = nullptr; d_prog_cap_ = 0; prog_valid_ = false;
     cudaFree(d_arena_); d_arena_ = nullptr; cudaFree(d_stamp0_); d_stamp0_ = nullptr; cudaFreeHost(h_flag_); h_flag_ = nullptr;
@@ -994,21 +1064,36 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     beam_ = beam_width > 0 ? beam_width : 16;
     if (const char *e = getenv("AMBI_BEAM_WIDTH")) { int v = atoi(e); if (v > 0) beam_ = v; }   // tuning knobs; results do not depend on them
     if (const char *e = getenv("AMBI_BEAM_DELTA")) beam_delta_ = atoi(e);
+    if (const char *e = getenv("AMBI_DEDUP_SHIFT")) dedup_shift_ = std::max(0, std::min(3, atoi(e)));
     if (const char *e = getenv("AMBI_GPW")) gpw_ = std::max(1, atoi(e));
     if (const char *e = getenv("AMBI_BEAM_GROWTH")) beam_growth_ = (float)atof(e);
     if (const char *e = getenv("AMBI_BEAM_FLOOR_MAX")) beam_floor_max_ = std::max(1, atoi(e));
     if (const char *e = getenv("AMBI_BEAM_SHIFT")) beam_shift_ = std::max(0, std::min(8, atoi(e)));
     rank_ = rank; world_ = world > 0 ? world : 1; shard_level_ = shard_level;
-    // buffers are sized in bytes for the widest record (n = 32); narrower batches fit more records
-    buf_bytes_ = (size_t)cap_base_ * stride_;
-    cap_max_ = (uint32_t)std::min<uint64_t>(2ull * cap_base_, buf_bytes_ / ambi_node_stride(2));
-    CK(cudaMalloc(&buf_[0], buf_bytes_));
-    CK(cudaMalloc(&buf_[1], buf_bytes_));
-    CK(cudaMalloc(&kbuf_, (size_t)cap_max_ * 48));
-    CK(cudaMalloc(&lbuf_, (size_t)cap_max_ * sizeof(uint2)));
-    CK(cudaMalloc(&list_[0], (size_t)cap_max_ * 4));
-    tsize_ = next_pow2((uint64_t)cap_max_ * 2);
-    CK(cudaMalloc(&table_, (size_t)tsize_ * 8));
+    // buffers are sized in bytes for the widest record (n = 32); narrower batches fit more records.  An automatic size
+    // backs off (halves) when the device cannot give it -- several processes may share the GPU, each sizing itself
+    // from what was free when it looked; an explicit node_capacity is taken as given.
+    for (;;) {
+        buf_bytes_ = (size_t)cap_base_ * stride_;
+        cap_max_ = (uint32_t)std::min<uint64_t>(2ull * cap_base_, buf_bytes_ / ambi_node_stride(2));
+        tsize_ = next_pow2((uint64_t)cap_max_ * 2);
+        cudaError_t e = cudaMalloc(&buf_[0], buf_bytes_);
+        if (e == cudaSuccess) e = cudaMalloc(&buf_[1], buf_bytes_);
+        if (e == cudaSuccess) e = cudaMalloc(&kbuf_, (size_t)cap_max_ * 48);
+        if (e == cudaSuccess) e = cudaMalloc(&lbuf_, (size_t)cap_max_ * sizeof(uint2));
+        if (e == cudaSuccess) e = cudaMalloc(&dbuf_, (size_t)cap_max_ + 4);
+        if (e == cudaSuccess) e = cudaMalloc(&list_[0], (size_t)cap_max_ * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&table_, (size_t)tsize_ * 8);
+        if (e == cudaSuccess) break;
+        cudaGetLastError();
+        cudaFree(buf_[0]); cudaFree(buf_[1]); cudaFree(kbuf_); cudaFree(lbuf_); cudaFree(dbuf_); cudaFree(list_[0]); cudaFree(table_);
+        buf_[0] = buf_[1] = nullptr; kbuf_ = nullptr; lbuf_ = nullptr; dbuf_ = nullptr; list_[0] = nullptr; table_ = nullptr;
+        if (e != cudaErrorMemoryAllocation || node_capacity > 0 || cap_base_ <= (1u << 20)) {
+            snprintf(err_, sizeof err_, "candidate buffers for %u records: %s", cap_base_, cudaGetErrorString(e)); return -4;
+        }
+        cap_base_ = std::max<uint32_t>(1u << 20, cap_base_ / 2);
+    }
+    cap_ = cap_base_;
     CK(cudaMemsetAsync(table_, 0, (size_t)tsize_ * 8, stream_));
     CK(cudaMalloc(&counters_, CTR_TOTAL * sizeof(uint32_t)));
     CK(cudaMalloc(&d_funnel_, 4 * sizeof(unsigned long long)));
@@ -1227,7 +1312,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     LevelArgs L;
     // the frontier of a level is a dense array of full records (k_materialise); its children are key records + links
     L.probs = d_probs_; L.parents = buf_[cur]; L.plist = nullptr; L.pcount = c_cur;
-    L.children = kbuf_; L.links = lbuf_; L.kstride = kstride_; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
+    L.children = kbuf_; L.links = lbuf_; L.dead = dbuf_; L.kstride = kstride_; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
     L.cand_count = d_cand_; L.node_count = d_node_; L.funnel = d_funnel_; L.work_counter = c_work; L.overflow = c_over;
     L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = mode == 0 ? EMIT_BEST : EMIT_ALL;
     L.beam_delta = mode == 1 ? beam_delta_ : -1; L.beam_shift = beam_shift_;
@@ -1245,14 +1330,14 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     if (beam) { if (int rc = op_memset(d_hist_, 0, (size_t)count_ * BEAM_BINS * 4, false)) return rc; }     // used after the merge's barrier
     if (merge) {
         DedupArgs D;
-        D.recs = kbuf_; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
+        D.recs = kbuf_; D.dead = dbuf_; D.tshift = dedup_shift_; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = (uint32_t)(mode * 40 + level); D.stride = kstride_; D.level = level; D.overflow = c_over;
         D.probs = d_probs_; D.fmin_cur = beam ? fmin_cur : nullptr; D.nmax = nmax_;
         D.links = lbuf_; D.parents = buf_[cur]; D.pstride = stride_;
         { Op o; memset(&o, 0, sizeof o); o.kind = OP_DEDUP; o.sync_after = 1; o.u.dd = D; if (int rc = op(o)) return rc; }
     }
     FinalizeArgs F;
-    F.probs = d_probs_; F.recs = kbuf_; F.count = c_child; F.cap = cap_;
+    F.probs = d_probs_; F.recs = kbuf_; F.dead = dbuf_; F.count = c_child; F.cap = cap_;
     F.best_score = mode == 2 ? d_best_score_ : d_beam_score_; F.best_rows = mode == 2 ? d_best_rows_ : d_beam_rows_;
     F.stride = kstride_; F.level = level;
     F.limit = nullptr; F.merge_best = 0; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
@@ -1261,12 +1346,12 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     // (it reads what the merge left and writes per-problem results only: no barrier needed before the next operation)
     if ((leaf_levels_ >> level) & 1u) { Op o; memset(&o, 0, sizeof o); o.kind = OP_FINALIZE; o.sync_after = 0; o.u.fz = F; if (int rc = op(o)) return rc; }
     MatArgs M;
-    M.probs = d_probs_; M.keys = kbuf_; M.links = lbuf_; M.count = c_child; M.cap = cap_; M.parents = buf_[cur]; M.pstride = stride_;
+    M.probs = d_probs_; M.keys = kbuf_; M.dead = dbuf_; M.links = lbuf_; M.count = c_child; M.cap = cap_; M.parents = buf_[cur]; M.pstride = stride_;
     M.out = buf_[cur ^ 1]; M.out_count = c_nxt; M.out_cap = cap_; M.kstride = kstride_; M.level = level; M.nmax = nmax_; M.overflow = c_over;
     M.fmin = nullptr; M.cutq = nullptr; M.ticket = nullptr;
     if (beam) {
         BeamArgs B;
-        B.probs = d_probs_; B.recs = kbuf_; B.count = c_child; B.cap = cap_;
+        B.probs = d_probs_; B.recs = kbuf_; B.dead = dbuf_; B.count = c_child; B.cap = cap_;
         B.fmin = fmin_cur; B.hist = hist; B.cutq = d_cutq_ + (size_t)level * count_;
         B.ticket = d_ticket_ + (size_t)level * count_;
         B.nprob = count_; B.width = beam_; B.width_floor = std::min(beam_floor_max_, std::max(beam_, beam_ * 4096 / std::max(count_, 1)));
@@ -1595,7 +1680,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         k_iota<<<(m + 255) / 256, 256, 0, stream_>>>(list_[0], sg.pos, m, c_par); ++launches_;
         LevelArgs L;
         L.probs = d_probs_; L.parents = pool_ + sg.off; L.plist = list_[0]; L.pcount = c_par;
-        L.children = kbuf_; L.links = lbuf_; L.kstride = kstride_; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
+        L.children = kbuf_; L.links = lbuf_; L.dead = dbuf_; L.kstride = kstride_; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
         L.cand_count = d_cand_; L.node_count = d_node_; L.funnel = d_funnel_; L.work_counter = c_work; L.overflow = c_over;
         L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = EMIT_ALL; L.beam_delta = -1; L.beam_shift = 1;
         L.shard_world = sw; L.shard_rank = rank_; L.shard_level = shard_level_eff_; L.gpw = gpw_;
@@ -1614,14 +1699,14 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         sg.pos += m;
         ++chunks; ++since_exchange;
         DedupArgs D;
-        D.recs = kbuf_; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
+        D.recs = kbuf_; D.dead = dbuf_; D.tshift = dedup_shift_; D.count = c_child; D.cap = cap_; D.table = table_; D.tmask = tsize_ - 1;
         D.gen_base = counters_ + CTR_GEN; D.gen_off = 0; D.stride = kstride_; D.level = level; D.overflow = c_over;
         D.probs = d_probs_; D.fmin_cur = nullptr; D.nmax = nmax_;
         D.links = lbuf_; D.parents = pool_ + sg.off; D.pstride = stride_;
         k_bump_gen<<<1, 1, 0, stream_>>>(counters_ + CTR_GEN); ++launches_;
         k_dedup<<<sms_ * 8, 256, 0, stream_>>>(D); ++launches_;
         FinalizeArgs F;
-        F.probs = d_probs_; F.recs = kbuf_; F.count = c_child; F.cap = cap_;
+        F.probs = d_probs_; F.recs = kbuf_; F.dead = dbuf_; F.count = c_child; F.cap = cap_;
         F.best_score = d_best_score_; F.best_rows = d_best_rows_;
         F.limit = d_limit_; F.stride = kstride_; F.level = level; F.merge_best = 1; F.overflow = c_over; F.seen = d_seen_; F.stamps = d_stamps_;
         F.links = lbuf_; F.parents = pool_ + sg.off; F.pstride = stride_;
@@ -1629,7 +1714,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         // the survivors become full records on top of the pool (the next, deeper segment of the stack)
         const uint64_t room = (pool_bytes_ - pool_top) / (size_t)stride_;
         MatArgs M;
-        M.probs = d_probs_; M.keys = kbuf_; M.links = lbuf_; M.count = c_child; M.cap = cap_; M.parents = pool_ + sg.off; M.pstride = stride_;
+        M.probs = d_probs_; M.keys = kbuf_; M.dead = dbuf_; M.links = lbuf_; M.count = c_child; M.cap = cap_; M.parents = pool_ + sg.off; M.pstride = stride_;
         M.out = pool_ + pool_top; M.out_count = c_next; M.out_cap = (uint32_t)std::min<uint64_t>(room, 0xffffffffu);
         M.kstride = kstride_; M.level = level; M.nmax = nmax_; M.overflow = c_over; M.fmin = nullptr; M.cutq = nullptr; M.ticket = nullptr;
         k_materialise<<<sms_ * 8, 256, 0, stream_>>>(M); ++launches_;

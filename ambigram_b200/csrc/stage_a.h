@@ -103,6 +103,8 @@ private:
     uint8_t *buf_[2] = {nullptr, nullptr};      // full records of the current / next frontier
     uint8_t *kbuf_ = nullptr;                   // key records of a level's children
     uint2 *lbuf_ = nullptr;                     // their (parent, row code) links
+    uint8_t *dbuf_ = nullptr;                   // their dropped-by-the-merge flags
+    int dedup_shift_ = 1;                       // merge table: at least 1 << shift slots per record (measured: 1 beats 2 and 0)
     int kstride_ = 48;
     uint32_t *list_[2] = {nullptr, nullptr};
     unsigned long long *table_ = nullptr;
