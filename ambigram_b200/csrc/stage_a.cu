@@ -60,6 +60,7 @@ struct LevelArgs {
     int nmax;
     int emit;                       // EMIT_ALL: every child within the limit; EMIT_BEST: arg-min child per record
     int beam_shift;
+    int beam_delta_short, beam_shift_short, beam_short_n;   // the band of partitions of up to beam_short_n segments
     int beam_delta;                 // >= 0 (incumbent beam only): also drop children whose f exceeds the parent's by more
     int shard_world, shard_rank, shard_level;
     int gpw;                        // target number of record groups per resident warp
@@ -321,7 +322,10 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
             slack = A.limit[hd.z] - hd.x;
             // heuristic band (the beam only feeds the incumbent): a child may exceed its parent's f by
             // beam_delta, or by half of what is left up to the current limit if that is more
-            if (A.beam_delta >= 0) slack = min(slack, hd.y - hd.x + max(A.beam_delta, (A.limit[hd.z] - hd.y) >> A.beam_shift));
+            if (A.beam_delta >= 0) {
+                const bool shortp = my_n <= A.beam_short_n;
+                slack = min(slack, hd.y - hd.x + max(shortp ? A.beam_delta_short : A.beam_delta, (A.limit[hd.z] - hd.y) >> (shortp ? A.beam_shift_short : A.beam_shift)));
+            }
         }
         // masks of all columns at once, 4 column bytes per word (bytes of closed columns and beyond the partition are
         // zero): a byte-wise "at least" test leaves bit 7 of each byte, one multiply gathers the four bits
@@ -1054,11 +1058,14 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     stride_ = (int)ambi_node_stride(AMBI_MAXN);
     if (node_capacity > 0) cap_base_ = (uint32_t)std::min<int64_t>(node_capacity, 1ll << 28);
     else {
-        // size the two candidate buffers for the 180 GB part: a fifth of what is free, at most 64 M records each
+        // automatic size: a quarter of what is free right now, at most 32 GB (64 M records) -- several processes may
+        // share the GPU (one context per Ambigram process), and everything else the library allocates later (problem
+        // arrays, the depth-first pool, Stage B) has to fit beside it.  ~540 bytes per record: two frontier buffers
+        // for the widest record, keys, links, flags, list and the merge table.
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        uint64_t recs = (free_b / 5) / (2ull * stride_ + 64);
-        cap_base_ = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(recs, 64ull << 20));
+        const uint64_t budget = std::min<uint64_t>(free_b / 4, 32ull << 30);
+        cap_base_ = (uint32_t)std::max<uint64_t>(1u << 20, std::min<uint64_t>(budget / 540, 64ull << 20));
     }
     cap_ = cap_base_;
     beam_ = beam_width > 0 ? beam_width : 16;
@@ -1069,6 +1076,9 @@ int StageA::init(cudaStream_t stream, int64_t node_capacity, int beam_width, int
     if (const char *e = getenv("AMBI_BEAM_GROWTH")) beam_growth_ = (float)atof(e);
     if (const char *e = getenv("AMBI_BEAM_FLOOR_MAX")) beam_floor_max_ = std::max(1, atoi(e));
     if (const char *e = getenv("AMBI_BEAM_SHIFT")) beam_shift_ = std::max(0, std::min(8, atoi(e)));
+    if (const char *e = getenv("AMBI_BEAM_DELTA_SHORT")) beam_delta_short_ = atoi(e);
+    if (const char *e = getenv("AMBI_BEAM_SHIFT_SHORT")) beam_shift_short_ = std::max(0, std::min(8, atoi(e)));
+    if (const char *e = getenv("AMBI_BEAM_SHORT_N")) beam_short_n_ = atoi(e);
     rank_ = rank; world_ = world > 0 ? world : 1; shard_level_ = shard_level;
     // buffers are sized in bytes for the widest record (n = 32); narrower batches fit more records.  An automatic size
     // backs off (halves) when the device cannot give it -- several processes may share the GPU, each sizing itself
@@ -1316,6 +1326,7 @@ int StageA::run_level(int level, int cur, int mode, int shard_world)
     L.cand_count = d_cand_; L.node_count = d_node_; L.funnel = d_funnel_; L.work_counter = c_work; L.overflow = c_over;
     L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = mode == 0 ? EMIT_BEST : EMIT_ALL;
     L.beam_delta = mode == 1 ? beam_delta_ : -1; L.beam_shift = beam_shift_;
+    L.beam_delta_short = beam_delta_short_; L.beam_shift_short = beam_shift_short_; L.beam_short_n = beam_short_n_;
     L.shard_world = shard_world; L.shard_rank = rank_; L.shard_level = shard_level_eff_; L.gpw = gpw_;
     const bool prof = profile_ && !capturing_;
     if (prof) {
@@ -1682,7 +1693,7 @@ int StageA::run_chunked_core(bool sharded, int start_level, bool exchange)
         L.probs = d_probs_; L.parents = pool_ + sg.off; L.plist = list_[0]; L.pcount = c_par;
         L.children = kbuf_; L.links = lbuf_; L.dead = dbuf_; L.kstride = kstride_; L.ccount = c_child; L.cap = cap_; L.limit = d_limit_;
         L.cand_count = d_cand_; L.node_count = d_node_; L.funnel = d_funnel_; L.work_counter = c_work; L.overflow = c_over;
-        L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = EMIT_ALL; L.beam_delta = -1; L.beam_shift = 1;
+        L.level = level; L.stride = stride_; L.nmax = nmax_; L.emit = EMIT_ALL; L.beam_delta = -1; L.beam_shift = 1; L.beam_delta_short = 0; L.beam_shift_short = 1; L.beam_short_n = 0;
         L.shard_world = sw; L.shard_rank = rank_; L.shard_level = shard_level_eff_; L.gpw = gpw_;
         launch_expand(L);
         uint32_t ctr[2] = {0, 0};

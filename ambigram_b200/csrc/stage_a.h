@@ -95,8 +95,11 @@ private:
     int beam_floor_max_ = 16;     // cap of the batch-scaled beam width `16*4096/count` (measured: with the width growing
                                   // in n a wide beam for small batches only costs time; AMBI_BEAM_FLOOR_MAX restores it)
     float beam_growth_ = 0.5f;    // beam width doubles every 1/growth segments beyond 12 (see k_beam_select)
-    int gpw_ = 4;                 // k_expand: record groups per resident warp (load balance vs lane utilisation)
+    int gpw_ = 2;                 // k_expand: record groups per resident warp (load balance vs lane utilisation)
     int beam_delta_ = 8;          // heuristic band of the incumbent beam (see k_expand)
+    // ... and for partitions of up to beam_short_n_ segments (measured on the B200, DESIGN.md section 5: the band is a
+    // trade between the beam's own cost and the incumbent it leaves the exact pass; results do not depend on it)
+    int beam_delta_short_ = 16, beam_shift_short_ = 3, beam_short_n_ = 20;
     int beam_ = 64, rank_ = 0, world_ = 1, shard_level_ = 0, shard_level_eff_ = -1;
     int stride_ = 0, sms_ = 148;
     uint32_t leaf_levels_ = 0;      // bit a: some problem of the batch has n == a+1
