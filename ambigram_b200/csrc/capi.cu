@@ -18,6 +18,9 @@
 #include <algorithm>
 #include <dlfcn.h>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
 #include <atomic>
 #include <chrono>
 
@@ -71,20 +74,72 @@ struct ambi_batch {
     bool ran = false;
 };
 
-// Host-side flattening / result mapping of a large batch is spread over a few threads (it is
-// per-problem independent work that would otherwise sit between the H2D copy and the launch).
+// Host-side flattening / result mapping of a large batch is per-problem independent work that would otherwise sit
+// between the H2D copy and the launch: it runs on a small pool of worker threads that lives as long as the process
+// (starting threads per call cost as much as the work itself at 32768 problems).  Chunks are handed out through an
+// atomic cursor; the calling thread works too.  A second caller arriving while the pool is busy does its work inline.
+namespace {
+struct HostPool {
+    std::mutex m, run_m;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::thread> workers;
+    const std::function<void(int, int)> *fn = nullptr;
+    int count = 0, chunk = 1, pending = 0;
+    unsigned long long epoch = 0;
+    std::atomic<int> next{0};
+
+    explicit HostPool(int nworkers)
+    {
+        for (int i = 0; i < nworkers; ++i) { workers.emplace_back([this] { work(); }); workers.back().detach(); }
+    }
+    void drain(const std::function<void(int, int)> &f, int cnt, int ch)
+    {
+        for (;;) {
+            const int lo = next.fetch_add(ch);
+            if (lo >= cnt) break;
+            f(lo, std::min(cnt, lo + ch));
+        }
+    }
+    void work()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m);
+            cv_work.wait(lk, [&] { return epoch != seen; });
+            seen = epoch;
+            const std::function<void(int, int)> *f = fn;
+            const int cnt = count, ch = chunk;
+            lk.unlock();
+            drain(*f, cnt, ch);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+    void run(int cnt, int ch, const std::function<void(int, int)> &f)
+    {
+        std::unique_lock<std::mutex> only(run_m, std::try_to_lock);
+        if (!only.owns_lock()) { f(0, cnt); return; }
+        {
+            std::lock_guard<std::mutex> lk(m);
+            fn = &f; count = cnt; chunk = ch; next.store(0); pending = (int)workers.size(); ++epoch;
+        }
+        cv_work.notify_all();
+        drain(f, cnt, ch);
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return pending == 0; });     // every worker has left drain(): `f` may go out of scope
+    }
+};
+}  // namespace
+
 template <class F> static void parallel_for(int count, F fn)
 {
     unsigned hw = std::thread::hardware_concurrency();
-    int nt = (int)std::min<unsigned>(hw ? hw : 1u, 8u);
-    if (const char *e = getenv("AMBI_HOST_THREADS")) nt = std::max(1, atoi(e));
-    nt = std::min(nt, count / 2048);
-    if (nt <= 1) { fn(0, count); return; }
-    std::vector<std::thread> th;
-    const int per = (count + nt - 1) / nt;
-    for (int t = 1; t < nt; ++t) { const int lo = t * per, hi = std::min(count, lo + per); if (lo < hi) th.emplace_back([=] { fn(lo, hi); }); }
-    fn(0, std::min(count, per));
-    for (std::thread &t : th) t.join();
+    int nt = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+    if (const char *e = getenv("AMBI_HOST_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
+    if (nt <= 1 || count < 4096) { fn(0, count); return; }
+    static HostPool *pool = new HostPool(nt - 1);           // never destroyed: its threads sleep until the process ends
+    const std::function<void(int, int)> f = fn;
+    pool->run(count, 512, f);
 }
 
 static thread_local std::string g_err;
@@ -238,23 +293,56 @@ extern "C" int ambi_batch_upload(ambi_ctx *ctx, int32_t count, const ambi_bfb_pr
 {
     if (!ctx || !out || count <= 0 || !problems) return fail(ctx, AMBI_ERR_BAD_ARG, "ambi_batch_upload: bad argument");
     cudaSetDevice(ctx->cfg.device);
-    DevProblem *stage = ctx->sa.staging(count);
-    if (!stage) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
+    static const bool timing = getenv("AMBI_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    // what travels over PCIe is a compact form (StageA::compact_words): header + the segments' 2c|2J words, sized by
+    // the longest partition of the batch; the device expands it (k_unpack).  Pieces are copied by the threads that
+    // flattened them, while the others are still working.
+    int nmax = 1;
+    bool any_tgs = false;
+    for (int i = 0; i < count; ++i) {
+        nmax = std::max(nmax, (int)problems[i].n);
+        any_tgs = any_tgs || (problems[i].n_tgs > 0 && (problems[i].flags & AMBI_FLAG_JUNC_INFO) && problems[i].tgs_pairs);
+    }
+    nmax = std::min(nmax, (int)AMBI_MAXN);
+    const int words = StageA::compact_words(nmax, any_tgs);
+    uint32_t *hc = ctx->sa.compact_staging(count);
+    if (!hc) return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error());
+    uint32_t *dc = ctx->sa.device_compact();
+    const int device = ctx->cfg.device;
+    cudaStream_t stream = ctx->stream;
+    std::atomic<int> copy_err{0};
     ambi_batch *b = new ambi_batch();
     b->count = count; b->n.resize(count); b->bias.resize(count); b->ush.resize(count);
     std::atomic<int> bad_rc{0}, bad_i{-1};
     std::string bad_why;
     parallel_for(count, [&](int lo, int hi) {
+        DevProblem d;
         for (int i = lo; i < hi; ++i) {
             std::string why;
-            int rc = to_dev(problems[i], stage[i], why);
+            int rc = to_dev(problems[i], d, why);
             if (rc) { int expect = 0; if (bad_rc.compare_exchange_strong(expect, rc)) { bad_i = i; bad_why = why; } return; }
             b->n[i] = problems[i].n; b->bias[i] = problems[i].bias; b->ush[i] = (int8_t)problems[i].unit_shift;
+            uint32_t *c = hc + (size_t)i * words;
+            c[0] = (uint32_t)d.n | ((uint32_t)d.lmax << 8) | ((uint32_t)d.ush << 16) | (d.has_tgs ? 1u << 24 : 0u);
+            c[1] = (uint32_t)d.loop_ub; c[2] = (uint32_t)d.zero_score; c[3] = (uint32_t)d.root_lb;
+            for (int j = 0; j < nmax; ++j) c[4 + j] = d.cj[j];
+            if (any_tgs) for (int j = 0; j < nmax; ++j) c[4 + nmax + j] = d.tgs_mask[j];
         }
+        if (cudaSetDevice(device) != cudaSuccess ||
+            cudaMemcpyAsync(dc + (size_t)lo * words, hc + (size_t)lo * words, (size_t)(hi - lo) * words * 4, cudaMemcpyHostToDevice, stream) != cudaSuccess) copy_err = 1;
     });
+    auto t1 = std::chrono::steady_clock::now();
     if (bad_rc) { delete b; return fail(ctx, bad_rc, "problem " + std::to_string(bad_i.load()) + ": " + bad_why); }
-    if (int urc = ctx->sa.upload(stage, count)) { delete b; return fail(ctx, urc == -5 ? AMBI_ERR_FRONTIER_OVERFLOW : AMBI_ERR_CUDA, ctx->sa.error()); }
+    if (copy_err) { delete b; (void)cudaGetLastError(); return fail(ctx, AMBI_ERR_CUDA, "ambi_batch_upload: host to device copy failed"); }
+    if (ctx->sa.unpack_compact(count, nmax, any_tgs)) { delete b; return fail(ctx, AMBI_ERR_CUDA, ctx->sa.error()); }
+    if (int urc = ctx->sa.upload(nullptr, count, true, b->n.data(), b->ush.data())) { delete b; return fail(ctx, urc == -5 ? AMBI_ERR_FRONTIER_OVERFLOW : AMBI_ERR_CUDA, ctx->sa.error()); }
     cudaStreamSynchronize(ctx->stream);
+    if (timing) {
+        auto t2 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+        fprintf(stderr, "[ambi] upload %d problems: flatten (+ copies enqueued) %.3f ms, bookkeeping + copies done %.3f ms\n", count, ms(t0, t1), ms(t1, t2));
+    }
     ctx->resident = b;
     *out = b;
     return AMBI_OK;

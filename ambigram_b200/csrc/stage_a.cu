@@ -1045,6 +1045,7 @@ void StageA::free_problem_arrays()
     cudaFree(d_beam_score_); cudaFree(d_beam_rows_); cudaFree(d_cand_); cudaFree(d_node_);
     cudaFree(d_fmin_); cudaFree(d_hist_); cudaFree(d_ticket_); cudaFree(d_cutq_); cudaFree(d_incumbent_); d_cutq_ = nullptr;
     cudaFreeHost(h_probs_); cudaFreeHost(h_res_); h_probs_ = nullptr; h_res_ = nullptr; h_cap_ = 0;
+    cudaFreeHost(h_compact_); cudaFree(d_compact_); h_compact_ = nullptr; d_compact_ = nullptr;
     cudaFree(d_small_list_); cudaFree(d_active_); cudaFree(d_active_base_); cudaFree(d_seen_); cudaFree(d_stamps_);
     d_small_list_ = nullptr; d_active_ = d_active_base_ = nullptr; d_seen_ = nullptr; d_stamps_ = nullptr;
     d_probs_ = nullptr; d_limit_ = d_best_score_ = d_beam_score_ = d_fmin_ = d_incumbent_ = nullptr;
@@ -1180,6 +1181,7 @@ int StageA::ensure_problem_arrays(int count)
     CK(cudaMalloc(&d_small_list_, (size_t)c * 4)); CK(cudaMalloc(&d_active_, (size_t)c)); CK(cudaMalloc(&d_active_base_, (size_t)c));
     CK(cudaMalloc(&d_seen_, (size_t)c * 4)); CK(cudaMalloc(&d_stamps_, (size_t)c * 32));
     CK(cudaMallocHost(&h_probs_, (size_t)c * sizeof(DevProblem)));
+    CK(cudaMallocHost(&h_compact_, (size_t)c * compact_words(AMBI_MAXN, true) * 4)); CK(cudaMalloc(&d_compact_, (size_t)c * compact_words(AMBI_MAXN, true) * 4));
     CK(cudaMallocHost(&h_res_, (size_t)c * (4 + 4 + 8 + 8 + 4 * AMBI_MAXN + 32 + 1) + 64));
     h_cap_ = c;
     prob_cap_ = c;
@@ -1193,46 +1195,81 @@ void StageA::drop_graphs()
     if (graph_exec2_) { cudaGraphExecDestroy(graph_exec2_); graph_exec2_ = nullptr; }
 }
 
+uint32_t *StageA::compact_staging(int count)
+{
+    if (ensure_problem_arrays(count)) return nullptr;
+    return h_compact_;
+}
+
+// one warp per problem, lane = segment: compact words -> DevProblem (coalesced 128-byte stores)
+__global__ void k_unpack(const uint32_t *compact, int words, int nmax, int any_tgs, DevProblem *out, int count)
+{
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= count) return;
+    const uint32_t *c = compact + (size_t)p * words;
+    DevProblem &d = out[p];
+    if (lane == 0) {
+        const uint32_t h = c[0];
+        d.n = (int32_t)(h & 0xffu); d.lmax = (int32_t)((h >> 8) & 0xffu); d.ush = (int32_t)((h >> 16) & 0xffu); d.has_tgs = (int32_t)(h >> 24);
+        d.loop_ub = (int32_t)c[1]; d.zero_score = (int32_t)c[2]; d.root_lb = (int32_t)c[3]; d.pad = 0;
+    }
+    const uint32_t cj = lane < nmax ? c[4 + lane] : 0u;
+    d.c2[lane] = (int32_t)(cj & 0xffffu); d.j2[lane] = (int32_t)(cj >> 16); d.cj[lane] = cj;
+    d.tgs_mask[lane] = (any_tgs && lane < nmax) ? c[4 + nmax + lane] : 0u;
+}
+
+int StageA::unpack_compact(int count, int nmax, bool any_tgs)
+{
+    const int wpb = 8;
+    k_unpack<<<(count + wpb - 1) / wpb, wpb * 32, 0, stream_>>>(d_compact_, compact_words(nmax, any_tgs), nmax, any_tgs ? 1 : 0, d_probs_, count);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 DevProblem *StageA::staging(int count)
 {
     if (ensure_problem_arrays(count)) return nullptr;
     return h_probs_;
 }
 
-int StageA::upload(const DevProblem *host_probs, int count)
+int StageA::upload(const DevProblem *host_probs, int count, bool copied, const int32_t *n_arr, const int8_t *ush_arr)
 {
     if (int rc = ensure_problem_arrays(count)) return rc;
     if (count != count_) drop_graphs();
     count_ = count;
+    // one pass over the staged problems: longest partition, finer units anywhere, levels at which a partition ends
     int nmax = 0;
-    for (int i = 0; i < count; ++i) nmax = std::max(nmax, (int)host_probs[i].n);
+    bool scaled = false;
+    uint32_t leaf = 0;
+    for (int i = 0; i < count; ++i) {
+        const int n = n_arr ? n_arr[i] : host_probs[i].n;
+        nmax = std::max(nmax, n);
+        scaled = scaled || (ush_arr ? ush_arr[i] : host_probs[i].ush) != 0;
+        if (n >= 2) leaf |= 1u << (n - 1);
+    }
     if (nmax != nmax_) drop_graphs();
     nmax_ = nmax;
-    bool scaled = false;
-    for (int i = 0; i < count; ++i) scaled = scaled || host_probs[i].ush != 0;
     if (scaled != scaled_) drop_graphs();
     scaled_ = scaled;
-    uint32_t leaf = 0;
-    for (int i = 0; i < count; ++i) if (host_probs[i].n >= 2) leaf |= 1u << (host_probs[i].n - 1);
     if (leaf != leaf_levels_) drop_graphs();
     leaf_levels_ = leaf;
     stride_ = (int)ambi_node_stride(nmax_);
     kstride_ = nmax_ <= 16 ? 32 : 48;          // key record: header + 16 or 32 column bytes
     cap_ = (uint32_t)std::min<uint64_t>(cap_max_, buf_bytes_ / stride_);
     if ((uint64_t)count > cap_) { snprintf(err_, sizeof err_, "batch of %d partitions exceeds node capacity %u", count, cap_); return -5; }
-    CK(cudaMemcpyAsync(d_probs_, host_probs, (size_t)count * sizeof(DevProblem), cudaMemcpyHostToDevice, stream_));
+    if (!copied) CK(cudaMemcpyAsync(d_probs_, host_probs, (size_t)count * sizeof(DevProblem), cudaMemcpyHostToDevice, stream_));
     {   // partitions of 2..16 segments go to the warp-per-partition kernel first; the others are active for the
         // global-memory path from the start (single-segment partitions are solved in closed form)
         std::vector<uint32_t> lst; std::vector<uint8_t> act((size_t)count, 0);
         n_large_ = 0;
         for (int i = 0; i < count; ++i) {
-            const int n = host_probs[i].n;
-            if (small_on_ && n >= 2 && n <= 16 && host_probs[i].ush == 0) lst.push_back((uint32_t)i);
+            const int n = n_arr ? n_arr[i] : host_probs[i].n;
+            if (small_on_ && n >= 2 && n <= 16 && (ush_arr ? ush_arr[i] : host_probs[i].ush) == 0) lst.push_back((uint32_t)i);
             else if (n >= 2) { act[i] = 1; ++n_large_; }
         }
         n_small_ = (int)lst.size();
         // heaviest first would be better still; longest partitions first keeps the tail of the launch short
-        std::stable_sort(lst.begin(), lst.end(), [&](uint32_t x, uint32_t y) { return host_probs[x].n > host_probs[y].n; });
+        std::stable_sort(lst.begin(), lst.end(), [&](uint32_t x, uint32_t y) { return n_arr ? n_arr[x] > n_arr[y] : host_probs[x].n > host_probs[y].n; });
         if (n_small_) CK(cudaMemcpyAsync(d_small_list_, lst.data(), (size_t)n_small_ * 4, cudaMemcpyHostToDevice, stream_));
         CK(cudaMemcpyAsync(d_active_base_, act.data(), (size_t)count, cudaMemcpyHostToDevice, stream_));
         CK(cudaStreamSynchronize(stream_));      // the host vectors go out of scope

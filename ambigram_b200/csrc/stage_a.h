@@ -27,7 +27,19 @@ public:
     // pinned staging for `count` problem descriptors; the caller fills it and then calls upload(ptr, count)
     DevProblem *staging(int count);
     // copy `count` problem descriptors to the device (async on the ctx stream)
-    int upload(const DevProblem *host_probs, int count);
+    // `copied`: the caller has already enqueued the H2D copies of the problems on the stream (in pieces, from the threads
+    // that flattened them: device_problems())
+    // `n_arr` / `ush_arr`: the problems' lengths and units as compact arrays (a pass over the 416-byte staged structs that
+    // other threads have just written costs milliseconds at 32768 problems)
+    int upload(const DevProblem *host_probs, int count, bool copied = false, const int32_t *n_arr = nullptr, const int8_t *ush_arr = nullptr);
+    DevProblem *device_problems() { return d_probs_; }
+    // Compact upload of a large host batch (capi.cu ambi_batch_upload): a problem travels as 4 header words + the 2c|2J
+    // words of its segments (+ the third-generation masks when any partition has some), `words` 32-bit words per problem,
+    // and is expanded into DevProblem on the device -- 64 instead of 544 bytes per 12-segment partition over PCIe.
+    static int compact_words(int nmax, bool any_tgs) { return 4 + nmax * (any_tgs ? 2 : 1); }
+    uint32_t *compact_staging(int count);                  // pinned, room for compact_words(32, true) per problem
+    uint32_t *device_compact() { return d_compact_; }
+    int unpack_compact(int count, int nmax, bool any_tgs); // after the pieces were copied to device_compact()
     // enqueue the whole search (incumbent pass + exact pass); no host sync
     int run(bool sharded);
     // wait and read back per-problem results (pinned staging; pointers stay valid until the next fetch)
@@ -117,6 +129,7 @@ private:
     // per-problem arrays
     int prob_cap_ = 0, count_ = 0, nmax_ = 0;
     DevProblem *d_probs_ = nullptr, *h_probs_ = nullptr;   // device array, pinned host staging
+    uint32_t *d_compact_ = nullptr, *h_compact_ = nullptr;  // compact form of a host batch (see compact_words)
     uint8_t *h_res_ = nullptr;                              // pinned result staging
     int h_cap_ = 0;
     int32_t *d_limit_ = nullptr, *d_incumbent_ = nullptr, *d_best_score_ = nullptr, *d_beam_score_ = nullptr, *d_fmin_ = nullptr;

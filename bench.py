@@ -520,7 +520,10 @@ def main():
                            "batch_per_gpu": args.batch, "l2": "256 MB buffer written between timed steps",
                            "parallelism": f"sample-sharded x{world}"},
                 "e2e": {"value": e2e_value, "unit": UNIT,
-                        "h2d_bytes_per_step": args.batch * 416 * world, "d2h_bytes_per_step": args.batch * 156 * world},
+                        # per partition: compact problem (4 header words + one 2c|2J word per segment) + active flag in;
+                        # score, incumbent, row codes, two 64-bit counters, four time stamps, active flag out
+                        "h2d_bytes_per_step": args.batch * (4 * (4 + N_SEG) + 1) * world,
+                        "d2h_bytes_per_step": args.batch * (4 + 4 + 4 * N_SEG + 8 + 8 + 32 + 1) * world},
                 "gpu_launches": launches_all,
                 "candidates_per_step": cand_all, "records_expanded_per_step": nodes_per_step, "problems_per_s": args.batch * world / (ms_per_step * 1e-3),
                 "time_to_best_ms_per_lh": 1e3 * t_best, "time_to_best": time_to_best, "single_lh_solve_ms": single_ms, "stage_b": stage_b,
