@@ -8,14 +8,17 @@
 //
 // Kernels (all INT32 + shared memory; no tensor cores -- nothing here is a
 // dense contraction):
-//   k_expand    K1+K2  one warp per frontier record: enumerate the feasible row
-//                      configurations, score them (exact deviation of segment a
-//                      + admissible bound for the rest), write the survivors
-//   k_dedup     K3a    hash-table merge of records that reach the same column
-//                      state: keep min (score, prefix in search order)
-//   k_finalize  K3b    per-problem arg-min of completed assignments, frontier
-//                      list for the next level, beam statistics
-//   k_beam_*    K3c    per-problem top-W selection by f-histogram (incumbent pass)
+//   k_expand       K1+K2  one warp per group of up to 32 frontier records: enumerate the
+//                         feasible row configurations, score them (exact deviation of
+//                         segment a + admissible bound for the rest), write the survivors
+//                         as key records + links + flags
+//   k_dedup        K3a    hash-table merge of key records that reach the same column
+//                         state: keep min (score, prefix in search order)
+//   k_finalize     K3b    per-problem arg-min of completed assignments
+//   k_beam_*       K3c    per-problem top-W cut by f-histogram (incumbent pass)
+//   k_materialise  K3d    full records (key + the parent's rows + the row code) for the
+//                         survivors only: the next level's dense frontier
+//   k_unpack              compact host problems -> DevProblem
 #include "ambi_common.cuh"
 #include "stage_a.h"
 #include "decode_common.cuh"

@@ -110,7 +110,8 @@ typedef struct {
     int32_t *element_cn;       /* [n(n+1)] caller-allocated                     */
     int64_t score2;            /* 2U * sum(eps)  (integer; U = 1 << unit_shift)  */
     int64_t objective2;        /* score2 - 2U*bias: divide by 2U for what cbc prints as "objective value" */
-    uint64_t candidates_scored;/* row configurations scored on the device      */
+    uint64_t candidates_scored;/* row configurations of the expanded records the device disposed of (by the
+                                  column-mask bound, the O(1) prefilter or the O(n) bound)               */
     uint64_t nodes_expanded;   /* partial assignments expanded                  */
     int32_t status;
     int32_t incumbent_score2;  /* score2 found by the beam (incumbent) pass     */
@@ -242,7 +243,8 @@ typedef struct {
     double total_ms;           /* whole search (incumbent + exact pass)         */
     double incumbent_pass_ms;
     uint64_t record_stride;    /* bytes per candidate record in HBM             */
-    uint64_t configs_enumerated; /* row configurations decoded (light test)     */
+    uint64_t configs_enumerated; /* row configurations enumerated one by one (light test); the others were
+                                    dropped with their columns before the enumeration                  */
     uint64_t bounds_evaluated;   /* ... that reached the O(n) admissible bound  */
     uint64_t children_written;   /* ... that were materialised as records       */
     uint64_t bound_batches;      /* 32-lane batches the bound ran in (lane use = bounds_evaluated / (32*bound_batches)) */
