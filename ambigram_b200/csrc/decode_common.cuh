@@ -351,6 +351,25 @@ static __device__ __noinline__ uint32_t allowed_cols(uint32_t over, uint32_t fov
     return (mA & ~fover) | (mB & fover);
 }
 
+// Phase 1 of k_expand: take out of the three column masks every column the light test would refuse in every
+// configuration.  An end at column c charges ovt[c] << ush (a loop end twice, two loop ends at one column four times
+// that); the exact deviation of segment a is at least its minimum over the weights the end can come with (a pattern
+// end: w >= 1, a loop end: w >= 2, two loop ends: w >= 4; w <= 6).  Returns true when something was removed.
+__device__ __forceinline__ bool restrict_masks(uint32_t over, uint32_t fover, int lslack, int d0, int f0, int ush,
+                                               uint32_t *okP, uint32_t *okL1, uint32_t *okL2)
+{
+    int e[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) e[k] = abs(d0 + (k << (ush + 1))) + abs(f0 + (k << ush));
+    const int m4 = min(e[4], min(e[5], e[6])), m2 = min(min(e[2], e[3]), m4), m1 = min(e[1], m2);
+    const uint32_t rP = allowed_cols(over, fover, (lslack - m1) >> ush);
+    const uint32_t rL1 = allowed_cols(over, fover, (lslack - m2) >> (ush + 1));
+    const uint32_t rL2 = allowed_cols(over, fover, (lslack - m4) >> (ush + 2));
+    if (!((*okP & ~rP) | (*okL1 & ~rL1) | (*okL2 & ~rL2))) return false;
+    *okP &= rP; *okL1 &= rL1; *okL2 &= rL2;
+    return true;
+}
+
 // Owner of candidate cb0 + lane by a run-length walk over the records' candidate ranges: s0 = record that owns
 // candidate cb0; bit (e - cb0 - 1) of the returned mask marks a record that ends at e, so the owner of lane k is
 // s0 + popc(mask & below(k)) and the next chunk starts at record s0 + popc(mask).  Every staged record must have at

@@ -403,17 +403,8 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
             total = total_all;
             if (lslack < 0) total = 0;                    // the record's own bound is already beyond the limit
             else {
-                int e[7];
-#pragma unroll
-                for (int k = 0; k < 7; ++k) e[k] = abs(d0 + (k << (ush + 1))) + abs(f0 + (k << ush));
-                const int m4 = min(e[4], min(e[5], e[6])), m2 = min(min(e[2], e[3]), m4), m1 = min(e[1], m2);
-                const uint32_t rP = dec::allowed_cols(over, fover, (lslack - m1) >> ush);
-                const uint32_t rL1 = dec::allowed_cols(over, fover, (lslack - m2) >> (ush + 1));
-                const uint32_t rL2 = dec::allowed_cols(over, fover, (lslack - m4) >> (ush + 2));
-                if ((okP & ~rP) | (okL1 & ~rL1) | (okL2 & ~rL2)) {
-                    okP &= rP; okL1 &= rL1; okL2 &= rL2;
+                if (dec::restrict_masks(over, fover, lslack, d0, f0, ush, &okP, &okL1, &okL2))
                     total = dec::count_configs_call(okP, parP, okL1, okL2, par1, par2, &nl0);
-                }
                 dec::write_lists2(S, slot, okP, parP, okL1, okL2, par1, par2, nl0);
             }
             atomicAdd(&A.cand_count[hd.z], (unsigned long long)total_all);
