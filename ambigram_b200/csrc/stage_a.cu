@@ -753,7 +753,7 @@ __device__ __forceinline__ void beam_hist_body(const BeamArgs &A)
 __device__ __forceinline__ void beam_cut_body(const BeamArgs &A)
 {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < A.nprob; p += gridDim.x * blockDim.x) {
-    const uint32_t width = max(16u, (uint32_t)max((float)A.width_floor, min(8192.0f, (float)A.width * exp2f(A.growth * (float)max(0, A.probs[p].n - 12)))) / (uint32_t)A.width_div);
+    const uint32_t width = max((uint32_t)min(A.width, 16), (uint32_t)max((float)A.width_floor, min(8192.0f, (float)A.width * exp2f(A.growth * (float)max(0, A.probs[p].n - 12)))) / (uint32_t)A.width_div);
     const uint32_t *hs = A.hist + (size_t)p * BEAM_BINS;
     uint32_t below = 0;
     int cut = BEAM_BINS;                                // keep everything
