@@ -105,6 +105,32 @@ def test_random_profiles_ragged_batch(any_ctx):
         check_against_oracle(p, s)
 
 
+def test_large_host_batch_compact_upload_in_pieces(ctx):
+    """6000 partitions in one ambi_bfb_solve_batch call: the host side flattens them on its worker pool into the compact
+    form (with third-generation masks: some partitions have them), copies it in 512-partition pieces and the device
+    expands it; results are mapped back on the pool.  200 distinct ragged problems, 30 shuffled copies of each: every
+    copy must carry the oracle's answer for its problem."""
+    rng = random.Random(77)
+    distinct = []
+    for _ in range(200):
+        n = rng.randint(1, 9)
+        tg = []
+        for _ in range(rng.choice([0, 0, 1, 2])):
+            a = rng.randrange(n); b = rng.randrange(a, n); tg += [a + 1, b + 1]
+        distinct.append(Problem(n=n, seg_cn2=[rng.choice([0, 1, 2, 4, 6, 7, 12]) for _ in range(n)],
+                                fbi_cn2=[rng.choice([0, 0, 1, 2, 4]) for _ in range(n)], start_id=1,
+                                loop_ub=rng.choice([0, 1, 2, 9]), bias=1, tgs_pairs=tg, junc_info=rng.choice([False, True])))
+    order = [i for i in range(200) for _ in range(30)]
+    rng.shuffle(order)
+    sols = ctx.solve_batch([distinct[i] for i in order])
+    want = {}
+    for i, s in zip(order, sols):
+        if i not in want:
+            check_against_oracle(distinct[i], s)
+            want[i] = (s.score2, tuple(int(v) for v in s.element_cn))
+        assert (s.score2, tuple(int(v) for v in s.element_cn)) == want[i]
+
+
 def test_small_n_vs_bruteforce(any_ctx):
     ctx = any_ctx
     rng = random.Random(9)
