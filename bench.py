@@ -309,6 +309,14 @@ def run_workload(args):
     return 0
 
 
+def arm_config(batch: int, world: int):
+    """`config` of the bench line -- the same object for our arm and for --impl reference"""
+    return {"workload": f"synthetic BFB .lh, {N_SEG} segments / {N_FOLDS} folds (BASELINE configs[1]), "
+                        f"{batch} partitions per step per GPU, seeds rank*batch..",
+            "batch_per_gpu": batch, "l2": "256 MB buffer written between timed steps (GPU arm)",
+            "parallelism": f"sample-sharded x{world}"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path for this metric = the oracle port (Cbc, the reference's
     solver, is not in the image and does not count candidates; DESIGN.md 'Reference arm')."""
@@ -335,10 +343,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"synthetic BFB .lh, {N_SEG} segments / {N_FOLDS} folds, bounded sample of "
-                                   f"{per_step} of {args.batch} partitions per step", "batch": args.batch},
+            "config": arm_config(args.batch, max(1, args.gpus)),         # the config of our own arm, word for word
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": th, "kind": "port",
-                             "sample": f"{per_step} partitions per step, oracle/ambi_oracle.c (OpenMP)"},
+                             "sample": f"{per_step} of the step's {args.batch} partitions per step (rank 0's), oracle/ambi_oracle.c (OpenMP)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "problems_per_s": per_step * args.steps / tot_t, "reference_binary": reference_binary_timing()}
     print(json.dumps(line))
@@ -515,10 +522,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": f"synthetic BFB .lh, {N_SEG} segments / {N_FOLDS} folds (BASELINE configs[1]), "
-                                       f"{args.batch} partitions per step per GPU, seeds rank*batch..",
-                           "batch_per_gpu": args.batch, "l2": "256 MB buffer written between timed steps",
-                           "parallelism": f"sample-sharded x{world}"},
+                "config": arm_config(args.batch, world),
                 "e2e": {"value": e2e_value, "unit": UNIT,
                         # per partition: compact problem (4 header words + one 2c|2J word per segment) + active flag in;
                         # score, incumbent, row codes, two 64-bit counters, four time stamps, active flag out
