@@ -5,7 +5,7 @@ own code here (tools/make_golden.py large -> tests/golden/cases_large.json):
   * ref_inject_paths[_rev] -- what the unmodified reference prints for our Stage-A assignment (comparable for k <= 16);
   * ref_fixed_paths[_rev]  -- the same from the reference with compareLoops made a strict weak order
     (tools/patches/reference_fixed_sort.patch, oracle/_ref/Ambigram_ref_fixedsort): the parity target for k > 16,
-    where the unmodified comparator scrambles the DAG (it hangs or crashes on 7 of these 12 inputs).
+    where the unmodified comparator scrambles the DAG (it hangs or crashes on 11 of these 20 inputs).
 CPU part: the oracle against all of it.  GPU part (-m gpu): the CUDA path against the fixtures."""
 import json
 import os

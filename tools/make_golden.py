@@ -379,7 +379,9 @@ def extra_large(which):
     rng = random.Random(29)
     spec = [(25, 7, 0.0, 0), (25, 7, 0.0, 1), (25, 7, 0.5, 2), (25, 7, 0.5, 3),
             (30, 8, 0.0, 0), (30, 8, 0.5, 0), (30, 8, 0.5, 1), (30, 8, 0.5, 3),
-            (20, 6, 0.5, 4), (20, 6, 0.5, 5), (30, 8, 0.0, 4), (25, 7, 0.5, 6)]
+            (20, 6, 0.5, 4), (20, 6, 0.5, 5), (30, 8, 0.0, 4), (25, 7, 0.5, 6),
+            (25, 7, 0.5, 7), (25, 7, 0.0, 5), (30, 8, 0.5, 5), (30, 8, 0.5, 6), (30, 8, 0.0, 2), (28, 8, 0.5, 2),
+            (22, 6, 0.5, 1), (20, 6, 0.0, 7)]
     if which:
         spec = [sp for sp in spec if f"n{sp[0]}" in which]
     for n, folds, noise, seed in spec:
