@@ -489,7 +489,28 @@ def extra_trx():
     print("wrote", out, len(cases), "cases")
 
 
+def extra_juncs20(seeds):
+    """BASELINE config 3 (n = 20 / 6 folds with .juncs and --junc_info): reference-pinned like cases.json
+    -> tests/golden/cases_juncs20.json (one process per seed may run side by side)"""
+    import fcntl
+    out = os.path.join(ROOT, "tests", "golden", "cases_juncs20.json")
+    for seed in seeds:
+        sm = synth.generate(20, 6, int(seed), 0.0, with_juncs=True)
+        case = make_case(f"synth_juncs_n20_s{seed}", sm.lh_text(), sm.juncs_text(), True, rng=random.Random(41 + int(seed)))
+        with open(out + ".lock", "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            doc = json.load(open(out)) if os.path.exists(out) else {"generator": "tools/make_golden.py juncs20", "cases": []}
+            if case["name"] not in {c["name"] for c in doc["cases"]}:
+                doc["cases"].append(case)
+            doc["cases"].sort(key=lambda c: c["name"])
+            json.dump(doc, open(out, "w"), indent=0)
+        print(case["name"], "k", len(case["oracle_x_nz"]), "oracle", case["oracle_score2"], "highs", case.get("ref_highs_objective"),
+              "tgs", len(case["tgs_pairs"]) // 2, "ref rc", case["ref_inject_rc"], flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "juncs20":
+        return extra_juncs20(sys.argv[2:])
     if len(sys.argv) > 1 and sys.argv[1] == "trx":
         return extra_trx()
     if len(sys.argv) > 1 and sys.argv[1] == "large":
