@@ -204,8 +204,8 @@ def get_indel_bias(g: LhGraph, start_id: int, end_id: int) -> None:
 def flatten(g: LhGraph, components: Optional[List[List[int]]] = None, junc_info: bool = False, unit: int = 1) -> List[Partition]:
     """Per SOURCE/SINK pair: getJuncCN (LGM:3989-4050), bias (localhap.cpp:141-146), getIndelBias,
     component selection (localhap.cpp:158-162) -> the integer arrays of ambi_bfb_problem.
-    `unit`: the arrays are 2*unit*copies (copy numbers that are multiples of 1/(2*unit)); the library takes
-    unit 1 only, larger units exist for the oracle's *_units entry points."""
+    `unit`: the arrays are 2*unit*copies (copy numbers that are multiples of 1/(2*unit)); the library takes powers of
+    two up to 64 (ambi_bfb_problem.unit_shift), the oracle's *_units entry points any unit."""
     components = components or []
     parts: List[Partition] = []
     for s_id, e_id in zip(g.sources, g.sinks):

@@ -16,7 +16,7 @@ BY_NAME = {c["name"]: c for c in CASES}
 # in (0.5, 1)); generated the same way (`tools/make_golden.py inputs`), CPU parity only in this round
 CASES = CASES + json.load(open(os.path.join(ROOT, "tests", "golden", "cases_extra.json")))["cases"]
 # copy numbers that are multiples of 1/8 (case["unit"] = 4): what the oracle's *_units entry points are pinned by
-# (`tools/make_golden.py fractional`); the CUDA path takes unit 1 only so far
+# (`tools/make_golden.py fractional`); the CUDA path is pinned by the same fixtures (tests/test_gpu_parity.py)
 CASES = CASES + json.load(open(os.path.join(ROOT, "tests", "golden", "cases_fractional.json")))["cases"]
 # BASELINE config 3: n = 20 / 6 folds with .juncs and --junc_info (`tools/make_golden.py juncs20`)
 CASES = CASES + json.load(open(os.path.join(ROOT, "tests", "golden", "cases_juncs20.json")))["cases"]
