@@ -272,8 +272,9 @@ __device__ __forceinline__ void cursor_start(const SH &S, int slot, uint32_t r, 
             r -= blk;
         }
         m &= m - 1;
-        // r < 2^16 and width < 2^11: (r + 0.5) / width is at least 2^-12 away from every integer, far more than the
-        // error of the approximate float division, so truncation gives the exact quotient
+        // r < 2^18 (at most ~2.6e5 configurations for 32 open columns), width <= 1024 and the quotient <= 512:
+        // (r + 0.5) / width is at least 2^-11 away from every integer, the approximate float division is off by at
+        // most 2 ulp of a value below 512 (2^-13), so truncation gives the exact quotient
         const uint32_t pi = __float2uint_rz(__fdividef((float)r + 0.5f, (float)c.width));
         c.pi = (int)pi;
         c.li = r - pi * c.width;

@@ -100,7 +100,7 @@ struct GroupShared {
     int32_t  lslack[GRP];               // slack minus the record's own bound on segments > a (light-test limit)
     uint32_t pidx[GRP];
     uint16_t nl0[GRP];                  // loop multisets whose parents already exist (class 0)
-    uint16_t ncfg[GRP];                 // configurations of the record
+    uint32_t ncfg[GRP];                 // configurations of the record (up to ~2^18 for 32 open columns: not 16 bits)
     uint32_t cstart[GRP + 1];           // exclusive prefix of the records' chunk counts (work items of phase 2)
     uint8_t  n[GRP];
     uint8_t  ptgs[GRP];                 // running third-generation count (at most 5)
@@ -413,7 +413,7 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
             S.slack[slot] = slack; S.lslack[slot] = lslack; S.n[slot] = (uint8_t)my_n;
             S.d0[slot] = d0; S.f0[slot] = f0;
             S.tmask[slot] = P->has_tgs ? P->tgs_mask[a] : 0u;
-            S.ncfg[slot] = (uint16_t)total;
+            S.ncfg[slot] = total;
         }
         // phase 2 works in chunks of CHUNK consecutive configurations of a record (a record left without any still owns
         // one, empty, chunk): exclusive prefix of the chunk counts over the staged records
