@@ -508,7 +508,28 @@ def extra_juncs20(seeds):
               "tgs", len(case["tgs_pairs"]) // 2, "ref rc", case["ref_inject_rc"], flush=True)
 
 
+def extra_sc_probe():
+    """`--op sc_bfb` on two 4-segment clones: the LP the reference's BFB_ILP_SC (LGM:4754-5093) emits, kept as evidence
+    for DESIGN.md section 9 (the joint model's deviation columns alias for every clone after the first)
+    -> tests/golden/sc_probe.json"""
+    a = synth.generate(4, 2, 0, 0.0).lh_text()
+    b = synth.generate(4, 2, 1, 0.0).lh_text()
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "a.lh"), "w").write(a)
+        open(os.path.join(d, "b.lh"), "w").write(b)
+        env = dict(os.environ, PATH=BIN + ":" + os.environ["PATH"])
+        r = subprocess.run([REF, "--op", "sc_bfb", "--in_lh", "a.lh,b.lh", "--lp_prefix", "p"], cwd=d, env=env, capture_output=True, text=True, timeout=600)
+        lp = open(os.path.join(d, "p.lp")).read()
+    paths = [ln.strip() for ln in r.stdout.splitlines() if PATH_RE.match(ln.strip())]
+    out = os.path.join(ROOT, "tests", "golden", "sc_probe.json")
+    json.dump({"generator": "tools/make_golden.py sc_probe", "command": "Ambigram --op sc_bfb --in_lh a.lh,b.lh --lp_prefix p",
+               "a_lh": a, "b_lh": b, "rc": r.returncode, "paths": paths, "lp": lp}, open(out, "w"), indent=0)
+    print("wrote", out, "rc", r.returncode, lp.splitlines()[1], paths)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sc_probe":
+        return extra_sc_probe()
     if len(sys.argv) > 1 and sys.argv[1] == "juncs20":
         return extra_juncs20(sys.argv[2:])
     if len(sys.argv) > 1 and sys.argv[1] == "trx":
