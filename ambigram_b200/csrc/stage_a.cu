@@ -20,7 +20,9 @@
 //                         survivors only: the next level's dense frontier
 //   k_unpack              compact host problems -> DevProblem
 #include "ambi_common.cuh"
+#ifndef AMBI_EMU            // tests/emu/expand_emu.cpp compiles the device bodies of this file with g++ (test infrastructure)
 #include "stage_a.h"
+#endif
 #include "decode_common.cuh"
 #include <cstdio>
 #include <cstring>
@@ -534,6 +536,7 @@ __device__ __forceinline__ void expand_body(const LevelArgs &A, uint8_t *s_raw)
     }
 }
 
+#ifndef AMBI_EMU
 template <int NMAX, bool SCALED>
 __global__ void __launch_bounds__(WPB * 32, NMAX <= 16 ? 4 : 3)
 k_expand(LevelArgs A_param)
@@ -544,6 +547,8 @@ k_expand(LevelArgs A_param)
     __syncthreads();
     expand_body<NMAX, SCALED>(s_args, s_raw);
 }
+
+#endif
 
 // ---------------------------------------------------------------------------
 // K3a: merge records that reached the same column state.
@@ -851,11 +856,13 @@ __device__ __forceinline__ void materialise_body(const MatArgs &A)
     }
 }
 
+#ifndef AMBI_EMU
 __global__ void k_dedup(DedupArgs A) { dedup_body(A); }
 __global__ void k_finalize(FinalizeArgs A) { finalize_body(A); }
 __global__ void k_beam_hist(BeamArgs A) { beam_hist_body(A); }
 __global__ void k_beam_cut(BeamArgs A) { beam_cut_body(A); }
 __global__ void k_materialise(MatArgs A) { materialise_body(A); }
+#endif
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -884,6 +891,7 @@ __device__ __forceinline__ void init_roots_body(const InitRootsArgs &A)
         A.list[s] = s;
     }
 }
+#ifndef AMBI_EMU
 __global__ void k_init_roots(InitRootsArgs A) { init_roots_body(A); }
 
 // Single-segment partitions: no a<b rows exist; P[s,s] in {0,1}, L[s,s] in [0,loop_ub]
@@ -917,6 +925,7 @@ __global__ void k_prepare(const DevProblem *probs, int count, int32_t *best_scor
     stamps[(size_t)p * 4] = 0; stamps[(size_t)p * 4 + 1] = 0; stamps[(size_t)p * 4 + 2] = 0; stamps[(size_t)p * 4 + 3] = 0;
 }
 
+#endif
 struct SetLimitArgs {
     const DevProblem *probs; int count; int32_t *limit; const int32_t *best_score; int32_t *incumbent;
     const uint8_t *active; int32_t *seen; unsigned long long *stamps;
@@ -932,6 +941,7 @@ __device__ __forceinline__ void set_limit_body(const SetLimitArgs &A)
         A.limit[p] = l; A.incumbent[p] = l;
     }
 }
+#ifndef AMBI_EMU            // everything below is the launch side (CUDA runtime)
 __global__ void k_set_limit(SetLimitArgs A) { set_limit_body(A); }
 
 // ---------------------------------------------------------------------------
@@ -1881,4 +1891,5 @@ int StageA::fetch(HostResult *out)
     return F.overflow ? -5 : 0;
 }
 
+#endif  // AMBI_EMU
 }  // namespace ambi

@@ -22,6 +22,11 @@
 
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
+struct int4 { int32_t x, y, z, w; };
+static inline int4 make_int4(int32_t x, int32_t y, int32_t z, int32_t w) { int4 r = {x, y, z, w}; return r; }
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 r = {x, y}; return r; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
 
 namespace emu {
 constexpr int W = 32;
@@ -156,6 +161,20 @@ static inline unsigned long long emu_globaltimer()
 {
     struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (unsigned long long)ts.tv_sec * 1000000000ull + ts.tv_nsec;
 }
+
+// grid coordinates of the emulated warp: the harness sets them before it runs a warp (one block = its warps in turn)
+namespace emu {
+struct Dim3 { unsigned x, y, z; };
+static unsigned g_block_idx = 0, g_grid_dim = 1, g_block_dim = 32, g_warp_in_block = 0;
+static inline Dim3 thread_idx() { Dim3 d = {g_warp_in_block * 32u + (unsigned)lane(), 0, 0}; return d; }
+static inline Dim3 block_idx() { Dim3 d = {g_block_idx, 0, 0}; return d; }
+static inline Dim3 block_dim() { Dim3 d = {g_block_dim, 1, 1}; return d; }
+static inline Dim3 grid_dim() { Dim3 d = {g_grid_dim, 1, 1}; return d; }
+}
+#define threadIdx (emu::thread_idx())
+#define blockIdx (emu::block_idx())
+#define blockDim (emu::block_dim())
+#define gridDim (emu::grid_dim())
 
 #define __ballot_sync(...) (emu::g_line[emu::lane()] = __LINE__, emu__ballot_sync(__VA_ARGS__))
 #define __shfl_sync(...) (emu::g_line[emu::lane()] = __LINE__, emu__shfl_sync(__VA_ARGS__))
