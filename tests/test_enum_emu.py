@@ -28,10 +28,11 @@ def lib():
 @pytest.mark.parametrize("scaled", [0, 1])
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_cursor_and_mask_restriction_against_flat_decode(lib, seed, scaled):
-    stats = (C.c_longlong * 4)()
+    stats = (C.c_longlong * 5)()
     rc = lib.emu_enum_check(C.c_uint64(seed * 7919 + scaled), 400, scaled, stats)
     assert rc == 0
-    checked, passed, removed, slow = (int(v) for v in stats)
+    checked, passed, removed, slow, big = (int(v) for v in stats)
     # the sample must exercise what it claims to: many steps, passing configurations, records whose masks shrink,
     # records with more class-0 loop multisets than the list holds
     assert checked > 100_000 and passed > 1_000 and removed > 50 and slow > 5
+    assert big >= 1              # ... and records with more configurations than 16 bits hold (sampled)
