@@ -40,6 +40,7 @@ struct Search {
     unsigned long long funnel[4] = {0, 0, 0, 0};
     uint32_t overflow = 0, gen = 1;
     int beam = 16;
+    int shard_world = 1, shard_rank = 0, shard_level = -1;     // prefix sharding of the exact pass (StageA::enqueue_exact)
 
     void expand(const LevelArgs &L)
     {
@@ -59,7 +60,7 @@ struct Search {
         L.limit = limit.data(); L.cand_count = cand.data(); L.node_count = node.data(); L.funnel = funnel; L.work_counter = &c_work[level];
         L.overflow = &overflow; L.level = level; L.stride = stride; L.nmax = nmax; L.emit = mode == 0 ? EMIT_BEST : EMIT_ALL;
         L.beam_delta = beam_pass ? 8 : -1; L.beam_shift = 2; L.beam_delta_short = 16; L.beam_shift_short = 3; L.beam_short_n = 20;
-        L.shard_world = 1; L.shard_rank = 0; L.shard_level = -1; L.gpw = 2;
+        L.shard_world = mode == 2 ? shard_world : 1; L.shard_rank = shard_rank; L.shard_level = mode == 2 && shard_world > 1 ? shard_level : -1; L.gpw = 2;
         expand(L);
         int32_t *fmin_cur = fmin.data() + (size_t)level * count;
         if (beam_pass) std::fill(hist.begin(), hist.end(), 0u);
@@ -131,12 +132,13 @@ struct Search {
 
 // `count` partitions of 2..32 segments through the emulated level-synchronous search.
 // c2 / j2 / tgs: [count][32] / [count][32] / [count][2 * max_tgs]; -> 0 solved, 1 a level did not fit `cap` records, < 0 bad input
-extern "C" int emu_expand_solve(int32_t count, const int32_t *n, const int32_t *c2, const int32_t *j2, const int32_t *loop_ub,
-                                const int32_t *unit_shift, const int32_t *n_tgs, const int32_t *tgs, int32_t max_tgs, const int32_t *junc_info,
-                                int32_t cap, int32_t beam_width, int32_t *x_out, int64_t *score2, int32_t *incumbent_out, uint64_t *cand_out,
-                                uint64_t *funnel4)
+static int solve_impl(int32_t count, const int32_t *n, const int32_t *c2, const int32_t *j2, const int32_t *loop_ub,
+                      const int32_t *unit_shift, const int32_t *n_tgs, const int32_t *tgs, int32_t max_tgs, const int32_t *junc_info,
+                      int32_t cap, int32_t beam_width, int32_t *x_out, int64_t *score2, int32_t *incumbent_out, uint64_t *cand_out,
+                      uint64_t *funnel4, int world, int rank, int level, uint32_t *rows_out)
 {
     Search S;
+    S.shard_world = world; S.shard_rank = rank;
     S.count = count; S.probs.resize(count); S.nmax = 0; S.scaled = false; S.beam = beam_width > 0 ? beam_width : 16;
     for (int i = 0; i < count; ++i) {
         ambi_bfb_problem p; memset(&p, 0, sizeof p);
@@ -160,12 +162,61 @@ extern "C" int emu_expand_solve(int32_t count, const int32_t *n, const int32_t *
     S.limit.assign(count, 0); S.best_score.assign(count, 0x7fffffff); S.beam_score.assign(count, 0x7fffffff);
     S.incumbent.assign(count, 0); S.seen.assign(count, 0x7fffffff); S.fmin.assign((size_t)count * AMBI_MAXN, 0x7f7f7f7f);
     for (int i = 0; i < count; ++i) S.incumbent[i] = S.probs[i].zero_score;
+    S.shard_level = world > 1 ? std::min(level, std::max(0, S.nmax - 2)) : -1;
     S.run();
     if (S.overflow) return 1;
+    if (rows_out) memcpy(rows_out, S.best_rows.data(), (size_t)count * AMBI_MAXN * 4);
     for (int i = 0; i < count; ++i) {
         score2[i] = S.best_score[i]; incumbent_out[i] = S.incumbent[i]; cand_out[i] = S.cand[i];
         if (S.best_score[i] != 0x7fffffff) rows_to_element_cn(S.probs[i].n, S.best_rows.data() + (size_t)i * AMBI_MAXN, x_out + (size_t)i * 32 * 33);
     }
     for (int k = 0; k < 4; ++k) funnel4[k] = S.funnel[k];
+    return 0;
+}
+
+extern "C" int emu_expand_solve(int32_t count, const int32_t *n, const int32_t *c2, const int32_t *j2, const int32_t *loop_ub,
+                                const int32_t *unit_shift, const int32_t *n_tgs, const int32_t *tgs, int32_t max_tgs, const int32_t *junc_info,
+                                int32_t cap, int32_t beam_width, int32_t *x_out, int64_t *score2, int32_t *incumbent_out, uint64_t *cand_out,
+                                uint64_t *funnel4)
+{
+    return solve_impl(count, n, c2, j2, loop_ub, unit_shift, n_tgs, tgs, max_tgs, junc_info, cap, beam_width, x_out, score2, incumbent_out,
+                      cand_out, funnel4, 1, 0, -1, nullptr);
+}
+
+// The multi-GPU split of one search: every "rank" runs the incumbent part and the first
+// `level` rows redundantly and keeps the children of row `level` whose prefix hashes to it; the ranks' optima are
+// combined by (score, row codes in search order) like ambi_bfb_solve does after its all-gather.
+extern "C" int emu_expand_solve_sharded(int32_t world, int32_t level, int32_t count, const int32_t *n, const int32_t *c2, const int32_t *j2,
+                                        const int32_t *loop_ub, const int32_t *unit_shift, const int32_t *n_tgs, const int32_t *tgs, int32_t max_tgs,
+                                        const int32_t *junc_info, int32_t cap, int32_t beam_width, int32_t *x_out, int64_t *score2, uint64_t *cand_total)
+{
+    std::vector<int64_t> best(count, 0x7fffffff);
+    std::vector<uint32_t> best_rows((size_t)count * AMBI_MAXN, 0);
+    std::vector<int32_t> x((size_t)count * 32 * 33), inc(count);
+    std::vector<int64_t> sc(count);
+    std::vector<uint64_t> cand(count);
+    std::vector<uint32_t> rows((size_t)count * AMBI_MAXN);
+    uint64_t fun[4];
+    for (int i = 0; i < count; ++i) cand_total[i] = 0;
+    for (int r = 0; r < world; ++r) {
+        const int rc = solve_impl(count, n, c2, j2, loop_ub, unit_shift, n_tgs, tgs, max_tgs, junc_info, cap, beam_width, x.data(), sc.data(), inc.data(),
+                                  cand.data(), fun, world, r, level, rows.data());
+        if (rc) return rc;
+        for (int i = 0; i < count; ++i) {
+            cand_total[i] += cand[i];
+            if (sc[i] == 0x7fffffff) continue;                     // this shard saw no completed assignment
+            bool take = sc[i] < best[i];
+            if (sc[i] == best[i]) {
+                take = false;
+                for (int k = 0; k < n[i]; ++k) { const uint32_t a = rows[(size_t)i * AMBI_MAXN + k], b = best_rows[(size_t)i * AMBI_MAXN + k]; if (a != b) { take = a < b; break; } }
+            }
+            if (take) {
+                best[i] = sc[i];
+                memcpy(&best_rows[(size_t)i * AMBI_MAXN], &rows[(size_t)i * AMBI_MAXN], AMBI_MAXN * 4);
+                memcpy(x_out + (size_t)i * 32 * 33, x.data() + (size_t)i * 32 * 33, 32 * 33 * 4);
+            }
+        }
+    }
+    for (int i = 0; i < count; ++i) score2[i] = best[i];
     return 0;
 }

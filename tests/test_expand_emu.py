@@ -111,3 +111,32 @@ def test_copy_numbers_in_finer_units(emu):
         probs.append(base)                            # half-copy partitions in the same batch
     res, _ = solve_batch(emu, probs, cap=60000)
     check(probs, res)
+
+
+def solve_sharded(emu, problems, world, level, cap=200000, beam=16):
+    cnt = len(problems)
+    n = np.array([p.n for p in problems], dtype=np.int32)
+    c2 = np.zeros((cnt, 32), dtype=np.int32); j2 = np.zeros((cnt, 32), dtype=np.int32)
+    for i, p in enumerate(problems):
+        c2[i, :p.n] = p.seg_cn2; j2[i, :p.n] = p.fbi_cn2
+    lub = np.array([p.effective_loop_ub() for p in problems], dtype=np.int32)
+    zero = np.zeros(cnt, dtype=np.int32); tgs = np.zeros((cnt, 2), dtype=np.int32)
+    x = np.zeros((cnt, 32 * 33), dtype=np.int32)
+    sc = np.zeros(cnt, dtype=np.int64); cand = np.zeros(cnt, dtype=np.uint64)
+    ptr = lambda a: a.ctypes.data_as(I32P)
+    rc = emu.emu_expand_solve_sharded(world, level, cnt, ptr(n), ptr(c2), ptr(j2), ptr(lub), ptr(zero), ptr(zero), ptr(tgs), 1, ptr(zero), cap, beam,
+                                      ptr(x), sc.ctypes.data_as(C.POINTER(C.c_int64)), cand.ctypes.data_as(C.POINTER(C.c_uint64)))
+    assert rc == 0, rc
+    return [(int(sc[i]), x[i, :p.n * (p.n + 1)].copy(), int(cand[i])) for i, p in enumerate(problems)]
+
+
+@pytest.mark.parametrize("world,level", [(2, 2), (3, 1), (4, 2), (8, 3)])
+def test_prefix_shards_combine_to_the_optimum(emu, world, level):
+    """north_star's multi-GPU split of one search: each rank keeps the children of row `level` whose
+    prefix hashes to it; the arg-min over the ranks in (score, search order) is the unsharded optimum, tie-break included"""
+    probs = [lh.problem_from_lh(synth.generate(n, f, 40 + s, noise).lh_text()) for (n, f, s, noise) in
+             [(6, 3, 0, 0.5), (9, 3, 1, 0.5), (10, 4, 2, 0.0), (12, 4, 3, 0.5), (12, 4, 4, 0.0)]]
+    got = solve_sharded(emu, probs, world, level)
+    for p, (score, x, cand) in zip(probs, got):
+        xo, st = orc.solve(p, want_unique=False)
+        assert score == st.score2 and np.array_equal(x, xo), (p.n, score, st.score2)
